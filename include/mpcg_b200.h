@@ -1,0 +1,90 @@
+/* mpcg_b200.h -- C ABI of libmpcg_b200.so: the B200 (sm_100a) signal-conditioning hot path of
+ * mpcg_wav2vec (MilanMarocchi/wav2vec-heart-sounds).
+ *
+ * The reference has no FFI of its own: its boundary for this path is a set of module-level Python
+ * functions (signalproc/torchproc.py, augment/torchaug.py, signalproc/spectrogram.py).  Each entry
+ * point below replaces the body of one of them; the file:line it stands in for is cited.  The Python
+ * mirror in wav2vec-heart-sounds_b200/ binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer named x / y / out / work is a DEVICE pointer to fp32 unless its comment says "host";
+ *  - rows are contiguous, time last: element (r, i) of a [rows, t] block is p[r * t + i];
+ *  - nothing here allocates, synchronises or owns memory; kernels are enqueued on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - return value: 0 success; < 0 argument error (MPCG_E*); > 0 a cudaError_t from the launch.
+ *  - there is no host/CPU fallback anywhere in this library.
+ */
+#ifndef MPCG_B200_H
+#define MPCG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCG_ABI_VERSION 1
+
+#define MPCG_OK 0
+#define MPCG_EINVAL (-1)
+#define MPCG_ERANGE (-2)
+#define MPCG_EUNSUPPORTED (-3)
+
+/* despike median rule */
+#define MPCG_MEDIAN_LOWER 0 /* torch.median: lower of the two middle values (torchproc.py:82)      */
+#define MPCG_MEDIAN_MEAN 1  /* numpy.median: mean of the two middle values, stop when 0 (despike.py:45-46) */
+
+/* normalise flags */
+#define MPCG_NORM_NAN_TO_NUM 1 /* torch.nan_to_num first (torchproc.py:63); without it = torchaug._normalise */
+#define MPCG_NORM_PEAK_GT0 2   /* numpy rule: divide only if peak > 0 (normalize.py:28-29) instead of clamp_min(1e-12) */
+
+int mpcg_abi_version(void);
+const char* mpcg_error_string(int code);
+
+/* Causal cascade of second-order sections, zero initial state.
+ * Replaces torchproc._causal / lowpass / highpass / bandpass_cascade (signalproc/torchproc.py:38-53),
+ * filters.lowpass/highpass/bandpass_cascade (signalproc/filters.py:25-39) and the five lfilter calls of
+ * torchaug.parametric_eq (augment/torchaug.py:92-99).
+ * sos: HOST pointer, n_sections rows of SciPy layout [b0 b1 b2 a0 a1 a2] (1 <= n_sections <= 6). */
+int mpcg_biquad_cascade_f32(const float* x, float* y, int64_t rows, int64_t t, const double* sos, int n_sections,
+                            void* stream);
+
+/* Rational polyphase resampler in dense frame form:
+ *   y[i*up + p] = sum_{d<taps_per_phase} x[i*down + offset + d] * taps[p*taps_per_phase + d],  x = 0 outside [0, t_in)
+ * for 0 <= i*up + p < t_out.  The host shim builds `taps` for either oracle:
+ * torchaudio sinc/Hann (torchproc.resample, signalproc/torchproc.py:56-59) or SciPy Kaiser resample_poly
+ * (signalproc/resample.py:11-22).  taps: HOST pointer, up * taps_per_phase floats. */
+int mpcg_resample_f32(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, const float* taps, int up,
+                      int down, int taps_per_phase, int64_t offset, void* stream);
+
+/* Schmidt spike removal, in place on x[rows, t] (give it a copy: the reference clones first,
+ * torchproc.py:72 / despike.py:34).  Replaces torchproc.remove_spikes (signalproc/torchproc.py:69-98) and
+ * despike.remove_spikes (signalproc/despike.py:31-54).  win = round(fs/2) is computed by the caller.
+ * edits (optional, device, [rows] int32): number of flattening passes each row ran.
+ * trace (optional, device, [rows, trace_cap, 4] int32): (frame, peak, lo, hi) of each pass, for parity tests. */
+int mpcg_despike_f32(float* x, int64_t rows, int64_t t, int64_t win, double threshold, int max_iterations,
+                     int median_mode, int32_t* edits, int32_t* trace, int trace_cap, void* stream);
+
+/* Row-wise  clip((x - mean) / max|x - mean|, -1, 1).
+ * Replaces torchproc.abs_max_normalise (signalproc/torchproc.py:62-66), torchaug._normalise
+ * (augment/torchaug.py:24-27) and normalize.abs_max_normalise (signalproc/normalize.py:20-30, without its
+ * NaN interpolation).  flags: MPCG_NORM_*. */
+int mpcg_absmax_norm_f32(const float* x, float* y, int64_t rows, int64_t t, int flags, void* stream);
+
+/* Overlapping-window gather.  x is [rows, channels, t]; window k of a row starts at start + k*hop and is
+ * zero-filled past t.  channels_last = 0: out[rows, channels, n, win] (torchproc.segment on [B,C,T],
+ * signalproc/torchproc.py:119-129, returned there as a view);  channels_last = 1: out[rows, n, win, channels]
+ * (loader layout of segment.segment on [T,C], signalproc/segment.py:40-52).  n is computed by the caller
+ * with mpcg_window_count. */
+int mpcg_segment_f32(const float* x, float* out, int64_t rows, int64_t channels, int64_t t, int64_t start,
+                     int64_t win, int64_t hop, int64_t n, int channels_last, void* stream);
+
+/* Window count of the tensor path (torchproc.py:124-128): after dropping `start` samples and zero-padding
+ * to one window if short, (len - win) / hop + 1.  Pure host arithmetic. */
+int64_t mpcg_window_count(int64_t t, int64_t start, int64_t win, int64_t hop);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCG_B200_H */

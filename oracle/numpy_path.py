@@ -1,0 +1,185 @@
+"""CPU oracle, float64 NumPy/SciPy leg -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Restates, in this repo's own words, the arithmetic of the reference's NumPy conditioning
+chain so the CUDA path can be checked against it on a box that has no copy of the
+reference.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this package; nothing under
+``wav2vec-heart-sounds_b200/`` does.
+
+What is restated (reference file:line -> function here):
+
+* ``signalproc/normalize.py:11-17``   -> :func:`fill_nans`
+* ``signalproc/normalize.py:20-30``   -> :func:`abs_max_normalise`
+* ``signalproc/resample.py:11-22``    -> :func:`resample` (SciPy ``resample_poly`` does the work)
+* ``signalproc/despike.py:16-54``     -> :func:`remove_spikes`
+* ``signalproc/filters.py:25-39``     -> :func:`lowpass` / :func:`highpass` / :func:`bandpass_cascade`
+* ``signalproc/preprocess.py:24-37``  -> :func:`preprocess_pcg` / :func:`preprocess_ecg`
+* ``signalproc/segment.py:17-52``     -> :class:`WindowSpec`, :func:`window_starts`, :func:`segment`
+
+Third-party arithmetic (SciPy ``resample_poly``/``butter``/``sosfilt``) is called, not
+restated: SciPy is installed on the GPU box too, and it is the very code the reference runs.
+
+Pinning: ``tests/test_oracle_pinned.py`` checks every function here (a) bit-for-bit against
+the reference itself when ``/root/reference`` is importable and (b) against the committed
+fixtures in ``tests/golden/`` that ``oracle/make_golden.py`` produced by running the
+reference.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+from scipy import signal as _sig
+
+PCG_BAND = (25.0, 450.0)   # Hz, divided by fs (not Nyquist) when designing -- reference convention
+ECG_BAND = (2.0, 40.0)
+SPIKE_FILL = 1e-4
+
+
+# --------------------------------------------------------------------------- NaN repair
+def fill_nans(x) -> np.ndarray:
+    """Copy ``x`` to float64 and bridge NaN runs by linear interpolation (edges hold)."""
+    out = np.array(x, dtype=np.float64)
+    bad = np.isnan(out)
+    if bad.any() and not bad.all():
+        good_idx = np.flatnonzero(~bad)
+        out[bad] = np.interp(np.flatnonzero(bad), good_idx, out[good_idx])
+    return out
+
+
+# --------------------------------------------------------------------------- normalise
+def abs_max_normalise(x) -> np.ndarray:
+    """Remove the mean, scale by the largest magnitude (when non-zero), clip to [-1, 1]."""
+    v = fill_nans(x)
+    v = v - np.mean(v)
+    top = np.max(np.abs(v))
+    if top > 0:
+        v = v / top
+    return np.clip(v, -1.0, 1.0)
+
+
+# --------------------------------------------------------------------------- resample
+def rational_ratio(fs_in: float, fs_out: float) -> tuple[int, int]:
+    up, down = int(round(fs_out)), int(round(fs_in))
+    g = math.gcd(up, down)
+    return up // g, down // g
+
+
+def resample(x, fs_in: float, fs_out: float) -> np.ndarray:
+    if fs_in == fs_out:
+        return np.asarray(x)
+    up, down = rational_ratio(fs_in, fs_out)
+    return _sig.resample_poly(x, up, down)
+
+
+# --------------------------------------------------------------------------- Schmidt despike
+def _flip_positions(frame: np.ndarray) -> np.ndarray:
+    """Indices i where sign(frame[i]) and sign(frame[i+1]) are strictly opposite (+1/-1)."""
+    sg = np.sign(frame)
+    return np.flatnonzero(np.abs(sg[1:] - sg[:-1]) > 1)
+
+
+def spike_span(frame: np.ndarray, peak: int) -> tuple[int, int]:
+    """Half-open sample range flattened around ``peak``: after the last flip before the
+    peak, up to the first flip at or after it (``len-1`` when there is none)."""
+    flips = _flip_positions(frame)
+    left = flips[flips < peak]
+    right = flips[flips >= peak]
+    lo = int(left[-1]) + 1 if left.size else 0
+    hi = int(right[0]) if right.size else frame.size - 1
+    return lo, hi
+
+
+def remove_spikes(x, fs: float, threshold: float = 3.0, max_iterations: int = 1000,
+                  trace: list | None = None) -> np.ndarray:
+    """Schmidt spike removal on one recording, 500 ms frames, float64, mean-of-middle median.
+
+    ``trace`` (optional) collects ``(frame, peak, lo, hi)`` per iteration so tests can check
+    the integer decisions bit-exactly.
+    """
+    v = np.array(x, dtype=np.float64)
+    win = round(float(fs) / 2.0)
+    if win < 1 or v.size < win:
+        return v
+    covered = v.size - v.size % win
+    frames = v[:covered].reshape(-1, win)            # view: row w = samples [w*win, (w+1)*win)
+    for _ in range(max_iterations):
+        tops = np.abs(frames).max(axis=1)
+        mid = np.median(tops)
+        if mid == 0 or not (tops > threshold * mid).any():
+            break
+        w = int(np.argmax(tops))
+        peak = int(np.argmax(np.abs(frames[w])))
+        lo, hi = spike_span(frames[w], peak)
+        if trace is not None:
+            trace.append((w, peak, lo, hi))
+        frames[w, lo:hi] = SPIKE_FILL
+    return v
+
+
+# --------------------------------------------------------------------------- band limiting
+def _sos(cutoff: float, fs: float, kind: str, order: int) -> np.ndarray:
+    return _sig.butter(order, cutoff / fs, btype=kind, output="sos")
+
+
+def lowpass(x, fs: float, cutoff: float, order: int = 2) -> np.ndarray:
+    return _sig.sosfilt(_sos(cutoff, fs, "lowpass", order), np.asarray(x, dtype=np.float64))
+
+
+def highpass(x, fs: float, cutoff: float, order: int = 2) -> np.ndarray:
+    return _sig.sosfilt(_sos(cutoff, fs, "highpass", order), np.asarray(x, dtype=np.float64))
+
+
+def bandpass_cascade(x, fs: float, low: float, high: float, order: int = 2) -> np.ndarray:
+    """Low-pass at the upper edge first, then high-pass at the lower edge (both causal)."""
+    return highpass(lowpass(x, fs, high, order), fs, low, order)
+
+
+# --------------------------------------------------------------------------- chains
+def preprocess_pcg(x, fs_in: float, fs_out: float, *, despike: bool = True) -> np.ndarray:
+    v = resample(fill_nans(x), fs_in, fs_out)
+    if despike:
+        v = remove_spikes(v, fs_out)
+    return abs_max_normalise(bandpass_cascade(v, fs_out, *PCG_BAND, order=2))
+
+
+def preprocess_ecg(x, fs_in: float, fs_out: float) -> np.ndarray:
+    v = resample(fill_nans(x), fs_in, fs_out)
+    return abs_max_normalise(bandpass_cascade(v, fs_out, *ECG_BAND, order=2))
+
+
+# --------------------------------------------------------------------------- segmentation
+@dataclass(frozen=True)
+class WindowSpec:
+    window_s: float
+    overlap_s: float = 0.25
+    start_pad_s: float = 0.3
+
+    def window_len(self, fs: float) -> int:
+        return int(round(self.window_s * fs))
+
+    def hop_len(self, fs: float) -> int:
+        return max(1, int(round((self.window_s - self.overlap_s) * fs)))
+
+
+def window_starts(n_samples: int, fs: float, spec) -> list[int]:
+    """First-sample index of every window; ``[]`` when the start pad eats the recording,
+    a single (to be zero-padded) window when fewer than ``win`` samples remain."""
+    first = int(round(spec.start_pad_s * fs))
+    if n_samples <= first:
+        return []
+    final = max(first, n_samples - spec.window_len(fs))
+    return list(range(first, final + 1, spec.hop_len(fs)))
+
+
+def segment(x, fs: float, spec) -> np.ndarray:
+    """``[T]`` -> ``[N, win]`` or ``[T, C]`` -> ``[N, win, C]`` (copy, zero-padded if short)."""
+    v = np.asarray(x)
+    win = spec.window_len(fs)
+    starts = window_starts(v.shape[0], fs, spec)
+    out = np.zeros((len(starts), win) + v.shape[1:], dtype=v.dtype)
+    for k, s in enumerate(starts):
+        piece = v[s:s + win]
+        out[k, :piece.shape[0]] = piece
+    return out

@@ -1,0 +1,124 @@
+"""CPU checks of the host side: tap design for both resampler oracles, window arithmetic, the C-ABI
+library's exported symbols.  No kernel is launched here."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_path as onp
+from oracle import torch_path as otp
+from helpers import dense_frames_apply, rel_err
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("fs_in,fs_out,n", [(2000, 16000, 1500), (2000, 4125, 3000), (4000, 4125, 3211), (4125, 2000, 2000),
+                                            (1000, 1500, 777)])
+def test_sinc_frames_equal_torchaudio(fs_in, fs_out, n):
+    from wav2vec_heart_sounds_b200 import design
+    up, down = design.reduce_ratio(fs_in, fs_out)
+    g, off, depth = design.sinc_hann_frames(up, down)
+    x = np.random.default_rng(0).standard_normal(n)
+    want = otp.resample(torch.from_numpy(x), fs_in, fs_out).numpy()
+    t_out = design.sinc_out_len(n, up, down)
+    assert t_out == want.shape[-1]
+    got = dense_frames_apply(x, g, up, down, off, t_out)
+    assert rel_err(got, want) < 1e-13
+
+
+@pytest.mark.parametrize("fs_in,fs_out,n", [(2000, 16000, 1500), (2000, 4125, 3000), (4000, 4125, 3211), (4125, 2000, 2000),
+                                            (1000, 1500, 777), (2000, 4125, 17)])
+def test_kaiser_frames_equal_scipy(fs_in, fs_out, n):
+    from wav2vec_heart_sounds_b200 import design
+    up, down = design.reduce_ratio(fs_in, fs_out)
+    g, off, depth = design.kaiser_poly_frames(up, down, n)
+    x = np.random.default_rng(1).standard_normal(n)
+    want = onp.resample(x, fs_in, fs_out)
+    t_out = design.kaiser_out_len(n, up, down)
+    assert t_out == want.shape[-1]
+    got = dense_frames_apply(x, g, up, down, off, t_out)
+    assert rel_err(got, want) < 1e-13
+
+
+def test_named_config_shapes():
+    """The three ratios of BASELINE.json's configs land on the specialised kernel instances."""
+    from wav2vec_heart_sounds_b200 import design
+    assert design.sinc_hann_frames(8, 1)[1:] == (-7, 15)
+    assert design.sinc_hann_frames(33, 16)[1:] == (-7, 30)
+    assert design.sinc_hann_frames(33, 32)[1:] == (-7, 46)
+    assert design.kaiser_poly_frames(8, 1, 60000)[1:] == (-10, 22)
+    assert design.kaiser_poly_frames(33, 16, 60000)[1:] == (-10, 36)
+    assert design.kaiser_poly_frames(33, 32, 32000)[1:] == (-10, 52)
+    assert design.sinc_out_len(60000, 33, 16) == 123750 and design.sinc_out_len(60000, 8, 1) == 480000
+    assert design.sinc_out_len(32000, 33, 32) == 33000
+
+
+def test_butter_sections_are_the_reference_design():
+    from wav2vec_heart_sounds_b200 import design
+    b, a = otp.butter_ba(450.0, 4125.0, "lowpass", 2)
+    s = design.butter_sos(450.0 / 4125.0, "lowpass", 2)
+    np.testing.assert_array_equal(s[0], np.concatenate([b, a]))
+    # SURVEY section 8a row C quotes these
+    assert abs(s[0, 0] - 0.02349489526897043) < 1e-15
+    s4 = design.butter_sos(0.05, "highpass", 4)
+    assert s4.shape == (2, 6)
+
+
+def test_window_spec_matches_oracle_and_survey():
+    from wav2vec_heart_sounds_b200.segment import WindowSpec, start_index
+    for fs in (1000, 2000, 4000, 4125, 16000, 22050):
+        for ws in (1.0, 2.0, 4.0):
+            a, b = WindowSpec(ws), onp.WindowSpec(ws)
+            assert a.window_len(fs) == b.window_len(fs) and a.hop_len(fs) == b.hop_len(fs)
+    s = WindowSpec(4.0)
+    assert (s.window_len(4125), s.hop_len(4125), start_index(4125, s)) == (16500, 15469, 1238)
+    assert (s.window_len(16000), s.hop_len(16000), start_index(16000, s)) == (64000, 60000, 4800)
+    v = WindowSpec(2.0)
+    assert (v.window_len(4125), v.hop_len(4125)) == (8250, 7219)
+
+
+def test_window_count_matches_reference_table(golden, built_lib):
+    """mpcg_window_count (host arithmetic in the library) against the reference's window_starts();
+    where the NumPy path returns no window at all the tensor path returns one zero window."""
+    lib = built_lib.lib()
+    tab = golden("segment_index.npz")["table"]
+    for fs, ws, n, win, hop, start, count, first, last in tab:
+        got = lib.mpcg_window_count(int(n), int(start), int(win), int(hop))
+        assert got == max(int(count), 1)
+    assert lib.mpcg_window_count(123750, 1238, 16500, 15469) == 7
+    assert lib.mpcg_window_count(480000, 4800, 64000, 60000) == 7
+    assert lib.mpcg_window_count(33000, 1238, 8250, 7219) == 4
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = (ROOT / "include" / "mpcg_b200.h").read_text()
+    names = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(mpcg_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert names, "no prototypes found in the header"
+    handle = ctypes.CDLL(str(built_lib.LIB_PATH))
+    for n in sorted(names):
+        assert hasattr(handle, n), f"{n} declared in include/mpcg_b200.h but not exported"
+    assert names == set(built_lib.declared_symbols())
+    assert handle.mpcg_abi_version() == 1
+
+
+def test_argument_errors_are_reported_without_a_gpu(built_lib):
+    lib = built_lib.lib()
+    sos = np.zeros((7, 6))
+    sos[:, 0] = sos[:, 3] = 1.0
+    assert lib.mpcg_biquad_cascade_f32(0, 0, 1, 10, sos.ctypes.data, 7, None) == -2      # too many sections
+    assert lib.mpcg_biquad_cascade_f32(0, 0, -1, 10, sos.ctypes.data, 1, None) == -1
+    assert lib.mpcg_biquad_cascade_f32(0, 0, 0, 10, sos.ctypes.data, 1, None) == 0        # empty batch is fine
+    assert lib.mpcg_segment_f32(0, 0, 1, 1, 100, 0, 10, 5, 3, 0, None) == -1             # wrong window count
+    assert lib.mpcg_despike_f32(0, 1, 100, 10, 3.0, 5, 9, None, None, 0, None) == -1      # bad median mode
+    assert b"invalid" in lib.mpcg_error_string(-1)
+
+
+def test_cpu_tensors_are_refused():
+    from wav2vec_heart_sounds_b200 import torchproc
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        torchproc.abs_max_normalise(torch.zeros(2, 8))
+    with pytest.raises(TypeError):
+        torchproc.lowpass(np.zeros(8), 1000, 100)

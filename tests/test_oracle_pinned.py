@@ -1,0 +1,142 @@
+"""Pin the oracle restatement (oracle/*.py) to the reference: against the committed golden vectors that
+oracle/make_golden.py produced by RUNNING the reference, and -- when /root/reference is mounted (build
+container) -- against the reference itself, bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_path as onp
+from oracle import torch_path as otp
+from conftest import reference_modules
+
+
+def test_numpy_chain_matches_golden(golden):
+    g = golden("preprocess_2k_4125.npz")
+    fs_in, fs_out = float(g["fs_in"]), float(g["fs_out"])
+    pcg, ecg = g["pcg"], g["ecg"]
+    for r in range(pcg.shape[0]):
+        rs = onp.resample(pcg[r].astype(np.float64), fs_in, fs_out)
+        np.testing.assert_array_equal(rs, g["np_resample"][r])
+        ds = onp.remove_spikes(rs, fs_out)
+        np.testing.assert_array_equal(ds, g["np_despike"][r])
+        bd = onp.bandpass_cascade(ds, fs_out, 25.0, 450.0)
+        np.testing.assert_array_equal(bd, g["np_band"][r])
+        np.testing.assert_array_equal(onp.abs_max_normalise(bd), g["np_norm"][r])
+        np.testing.assert_array_equal(onp.preprocess_pcg(pcg[r], fs_in, fs_out), g["np_pcg"][r])
+        np.testing.assert_array_equal(onp.preprocess_ecg(ecg[r], fs_in, fs_out), g["np_ecg"][r])
+        np.testing.assert_array_equal(onp.segment(g["np_pcg"][r], fs_out, onp.WindowSpec(1.0)), g["np_windows"][r])
+    pair = np.stack([g["np_pcg"][0], g["np_ecg"][0]], axis=1)
+    np.testing.assert_array_equal(onp.segment(pair, fs_out, onp.WindowSpec(1.0)), g["np_windows_tc"])
+
+
+def test_numpy_despike_does_real_work(golden):
+    g = golden("preprocess_2k_4125.npz")
+    assert np.any(g["np_despike"] != g["np_resample"])       # the fixture really contains spikes
+
+
+@pytest.mark.parametrize("dtype,tag", [(torch.float64, "t64"), (torch.float32, "t32")])
+def test_tensor_chain_matches_golden(golden, dtype, tag):
+    g = golden("preprocess_2k_4125.npz")
+    fs_in, fs_out = float(g["fs_in"]), float(g["fs_out"])
+    xp = torch.from_numpy(g["pcg"]).to(dtype)
+    xe = torch.from_numpy(g["ecg"]).to(dtype)
+    rs = otp.resample(xp, fs_in, fs_out)
+    ds = otp.remove_spikes(rs, fs_out)
+    np.testing.assert_array_equal(ds.numpy(), g[f"{tag}_despike"])
+    np.testing.assert_array_equal(otp.preprocess_pcg(xp, fs_in, fs_out).numpy(), g[f"{tag}_pcg"])
+    np.testing.assert_array_equal(otp.preprocess_ecg(xe, fs_in, fs_out).numpy(), g[f"{tag}_ecg"])
+    if tag == "t64":
+        np.testing.assert_array_equal(rs.numpy(), g["t64_resample"])
+        bd = otp.bandpass_cascade(ds, fs_out, 25.0, 450.0)
+        np.testing.assert_array_equal(bd.numpy(), g["t64_band"])
+        np.testing.assert_array_equal(otp.abs_max_normalise(bd).numpy(), g["t64_norm"])
+        w = otp.segment(otp.preprocess_pcg(xp, fs_in, fs_out), fs_out, onp.WindowSpec(1.0))
+        np.testing.assert_array_equal(w.contiguous().numpy(), g["t64_windows"])
+
+
+def test_other_ratios_match_golden(golden):
+    g = golden("resample_ratios.npz")
+    x2, x4 = g["x_2k"], g["x_4k"]
+    for r in range(2):
+        np.testing.assert_array_equal(onp.resample(x2[r].astype(np.float64), 2000, 16000), g["np_2k_16k"][r])
+        np.testing.assert_array_equal(onp.resample(x4[r].astype(np.float64), 4000, 4125), g["np_4k_4125"][r])
+        np.testing.assert_array_equal(onp.preprocess_pcg(x2[r], 2000, 16000), g["np_pcg_2k_16k"][r])
+    np.testing.assert_array_equal(otp.resample(torch.from_numpy(x2).double(), 2000, 16000).numpy(), g["t64_2k_16k"])
+    np.testing.assert_array_equal(otp.resample(torch.from_numpy(x4).double(), 4000, 4125).numpy(), g["t64_4k_4125"])
+    np.testing.assert_array_equal(otp.preprocess_pcg(torch.from_numpy(x2).double(), 2000, 16000).numpy(),
+                                  g["t64_pcg_2k_16k"])
+    np.testing.assert_array_equal(otp.preprocess_ecg(torch.from_numpy(x2).double(), 2000, 16000).numpy(),
+                                  g["t64_ecg_16k"])
+
+
+def test_window_index_table(golden):
+    """Integer decisions of segmentation: bit-exact against the reference's window_starts()."""
+    tab = golden("segment_index.npz")["table"]
+    for fs, ws, n, win, hop, start, count, first, last in tab:
+        spec = onp.WindowSpec(float(ws))
+        assert spec.window_len(fs) == int(win) and spec.hop_len(fs) == int(hop)
+        st = onp.window_starts(int(n), fs, spec)
+        assert len(st) == int(count)
+        if st:
+            assert st[0] == int(first) and st[-1] == int(last)
+
+
+def test_augment_replay_matches_golden(golden):
+    g = golden("torchaug_replay.npz")
+    x = torch.from_numpy(g["x"])
+    fs = int(g["fs"])
+    out = otp.add_white_noise(x, float(g["noise_std"]), torch.from_numpy(g["noise_scale"]),
+                              torch.from_numpy(g["noise_noise"]))
+    np.testing.assert_array_equal(out.numpy(), g["noise_out"])
+    out = otp.sinusoidal_envelope(x, fs, *(torch.from_numpy(g[k]) for k in ("sine_amp", "sine_freq", "sine_phase")))
+    np.testing.assert_array_equal(out.numpy(), g["sine_out"])
+    out = otp.baseline_wander(x, fs, *(torch.from_numpy(g[k]) for k in ("wander_amp", "wander_freq", "wander_phase")))
+    np.testing.assert_array_equal(out.numpy(), g["wander_out"])
+    np.testing.assert_array_equal(otp.amplitude_warp(x, torch.from_numpy(g["warp_amps"])).numpy(), g["warp_out"])
+    bands = [tuple(b) for b in g["eq_bands"]]
+    np.testing.assert_array_equal(otp.parametric_eq(x, fs, bands).numpy(), g["eq_out"])
+    np.testing.assert_array_equal(otp.parametric_eq(x.double(), fs, bands).numpy(), g["eq_out64"])
+    draws = {k[len("chain_"):]: g[k] for k in g.files if k.startswith("chain_") and k != "chain_out"}
+    for k, v in list(draws.items()):
+        if k.startswith(("std",)):
+            draws[k] = float(v)
+        elif k == "bands":
+            draws[k] = [tuple(b) for b in v]
+        else:
+            draws[k] = torch.from_numpy(np.asarray(v))
+    np.testing.assert_array_equal(otp.augment_pcg_batch(x, fs, draws).numpy(), g["chain_out"])
+
+
+def test_mel_presets_match_golden(golden):
+    import warnings
+    g = golden("mel_presets.npz")
+    x = torch.from_numpy(g["x"])
+    presets = {"dw4k": dict(sample_rate=4000, n_fft=1024, hop_length=256, n_mels=80, f_max=500.0),
+               "c4_16k": dict(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500.0),
+               "wg4k": dict(sample_rate=4000, n_fft=2048, win_length=1200, hop_length=300, n_mels=128, f_max=500.0)}
+    for tag, kw in presets.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr = otp.mel_transform(**kw)
+            np.testing.assert_array_equal(otp.log_mel(x, tr).numpy(), g[f"{tag}_logmel"])
+
+
+def test_against_live_reference_when_mounted():
+    """Build container only: fresh random inputs through the reference and the oracle, bit for bit."""
+    mods = reference_modules()
+    if mods is None:
+        pytest.skip("reference not mounted (GPU box)")
+    sp, tp, ta = mods
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((2, 4000)).astype(np.float32)
+    x[0, 1000:1005] += 30.0
+    x[1, 2500:2503] -= 25.0
+    for r in range(2):
+        np.testing.assert_array_equal(onp.preprocess_pcg(x[r], 2000, 4125), sp.preprocess_pcg(x[r], 2000, 4125))
+        np.testing.assert_array_equal(onp.preprocess_ecg(x[r], 2000, 4125), sp.preprocess_ecg(x[r], 2000, 4125))
+    xt = torch.from_numpy(x).double()
+    np.testing.assert_array_equal(otp.preprocess_pcg(xt, 2000, 4125).numpy(), tp.preprocess_pcg(xt, 2000, 4125).numpy())
+    np.testing.assert_array_equal(otp.remove_spikes(xt.float(), 2000).numpy(), tp.remove_spikes(xt.float(), 2000).numpy())
+    from mpcg_wav2vec.signalproc.segment import WindowSpec as RefSpec
+    w1 = otp.segment(xt, 2000, onp.WindowSpec(1.0)).numpy()
+    np.testing.assert_array_equal(w1, tp.segment(xt, 2000, RefSpec(1.0)).numpy())

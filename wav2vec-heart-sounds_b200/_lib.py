@@ -1,0 +1,98 @@
+"""ctypes binding of ``libmpcg_b200.so`` (C ABI declared in ``include/mpcg_b200.h``).
+
+The shared object is built in-tree by ``__graft_entry__.build()`` / ``make -C csrc`` with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is no fallback of any kind: if the
+library is missing, or a tensor is not a CUDA float32 tensor, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import pathlib
+import subprocess
+
+import torch
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libmpcg_b200.so"
+_lib = None
+
+c_f32p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+
+_SIGNATURES = {
+    "mpcg_abi_version": (c_int, []),
+    "mpcg_error_string": (ctypes.c_char_p, [c_int]),
+    "mpcg_biquad_cascade_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_resample_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, ctypes.c_void_p, c_int, c_int, c_int, c_i64,
+                                  ctypes.c_void_p]),
+    "mpcg_despike_f32": (c_int, [c_f32p, c_i64, c_i64, c_i64, ctypes.c_double, c_int, c_int, ctypes.c_void_p,
+                                 ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_absmax_norm_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, ctypes.c_void_p]),
+    "mpcg_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
+                                 ctypes.c_void_p]),
+    "mpcg_window_count": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
+}
+
+MEDIAN_LOWER, MEDIAN_MEAN = 0, 1
+NORM_NAN_TO_NUM, NORM_PEAK_GT0 = 1, 2
+
+
+def build(verbose: bool = False) -> pathlib.Path:
+    """Compile every ``csrc/*.cu`` for sm_100a into ``libmpcg_b200.so`` (idempotent: make decides)."""
+    proc = subprocess.run(["make", "-C", str(_HERE / "csrc"), "-j8"], capture_output=True, text=True)
+    if verbose or proc.returncode != 0:
+        print(proc.stdout)
+        print(proc.stderr)
+    if proc.returncode != 0:
+        raise RuntimeError("building libmpcg_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+def declared_symbols() -> list[str]:
+    return list(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for this path)")
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)           # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        if handle.mpcg_abi_version() != 1:
+            raise RuntimeError("libmpcg_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    msg = lib().mpcg_error_string(code).decode()
+    if code < 0:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: CUDA error {code}: {msg}")
+
+
+def require_cuda_f32(x: torch.Tensor, name: str = "x") -> torch.Tensor:
+    if not torch.is_tensor(x):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device (got {type(x).__name__})")
+    if not x.is_cuda:
+        raise ValueError(f"{name} is on {x.device}: this path runs on B200 only and has no CPU fallback")
+    if x.dtype != torch.float32:
+        raise ValueError(f"{name} has dtype {x.dtype}: the CUDA path is float32 in / float32 out")
+    return x.contiguous()
+
+
+def stream_ptr(x: torch.Tensor) -> int:
+    return torch.cuda.current_stream(x.device).cuda_stream
+
+
+def ptr(x) -> int:
+    return 0 if x is None else x.data_ptr()
