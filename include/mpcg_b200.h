@@ -84,6 +84,43 @@ int mpcg_segment_f32(const float* x, float* out, int64_t rows, int64_t channels,
  * to one window if short, (len - win) / hop + 1.  Pure host arithmetic. */
 int64_t mpcg_window_count(int64_t t, int64_t start, int64_t win, int64_t hop);
 
+/* ---- fused chain ---------------------------------------------------------------------------------
+ * One kernel for  resample -> [despike] -> low-pass + high-pass -> abs-max normalise -> windows, i.e.
+ * torchproc.preprocess_pcg / preprocess_ecg followed by torchproc.segment (signalproc/torchproc.py:101-129;
+ * NumPy twins signalproc/preprocess.py:24-37 + signalproc/segment.py:40-52; loader call sites
+ * datasets/cinc.py:86-94,115 and datasets/vest.py:50-51,84).  Raw samples are read from HBM once and the
+ * windows written once; every intermediate stays in shared memory of a thread-block cluster. */
+typedef struct mpcg_chain_kind {
+  int despike;        /* 1: Schmidt despike before the band filter (PCG); 0: none (ECG)            */
+  int n_sections;     /* 1 or 2 second-order sections, applied in order                            */
+  double sos[2][6];   /* SciPy layout [b0 b1 b2 a0 a1 a2]                                          */
+} mpcg_chain_kind;
+
+typedef struct mpcg_chain_desc {
+  int64_t t_in, t_out;          /* samples per row before / after resampling                         */
+  int up, down, taps_per_phase; /* resampler in dense frame form (see mpcg_resample_f32); up == down  */
+  int64_t offset;               /*   means "no resampling" and taps may be NULL                       */
+  const float* taps;            /* HOST pointer, up * taps_per_phase floats                           */
+  int64_t despike_win;          /* round(fs_out / 2)                                                  */
+  double despike_threshold;
+  int despike_max_iterations;
+  int median_mode;              /* MPCG_MEDIAN_*                                                      */
+  int norm_flags;               /* MPCG_NORM_*                                                        */
+  int64_t seg_start, seg_win, seg_hop, seg_n;   /* seg_n = mpcg_window_count(t_out, start, win, hop)  */
+  int channels_last;            /* 0: out[rec, ch, n, win]   1: out[rec, n, win, ch]                  */
+  int n_kinds;                  /* 1 or 2 distinct channel recipes                                    */
+  mpcg_chain_kind kinds[2];
+  uint8_t kind_of_channel[8];   /* recipe index of each channel (channels <= 8)                       */
+} mpcg_chain_desc;
+
+/* x: [recordings, channels, t_in] -> out (layout above).  edits / trace as in mpcg_despike_f32, indexed by
+ * row = recording * channels + channel.  Returns MPCG_EUNSUPPORTED when the geometry does not fit the fused
+ * kernel (row too long for an 8-CTA cluster, unknown resampling ratio, > 2 sections): the caller then chains
+ * the stand-alone entry points above, which accept everything. */
+int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t recordings, int channels,
+                                const mpcg_chain_desc* desc, int32_t* edits, int32_t* trace, int trace_cap,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

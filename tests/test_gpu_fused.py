@@ -1,0 +1,151 @@
+"""Parity of the fused cluster kernel (mpcg_preprocess_segment_f32) against the float64 oracle, the golden
+vectors and the stand-alone kernels.  Tolerance as in test_gpu_preprocess.py: 1e-5 of the reference's scale;
+despike decisions and window geometry bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_path as onp
+from oracle import torch_path as otp
+from helpers import rel_err
+from test_gpu_preprocess import _check_trace, _spiky
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pkg(built_lib):
+    import wav2vec_heart_sounds_b200 as m
+    return m
+
+
+def _dev(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+
+
+def _oracle_torch(x, fs_in, fs_out, ws, kind="pcg", despike=True):
+    xt = torch.from_numpy(x).double()
+    trace = []
+    v = otp.resample(xt, fs_in, fs_out)
+    if kind == "pcg":
+        if despike:
+            v = otp.remove_spikes(v, fs_out, trace=trace)
+        v = otp.abs_max_normalise(otp.bandpass_cascade(v, fs_out, *otp.PCG_BAND))
+    else:
+        v = otp.abs_max_normalise(otp.bandpass_cascade(v, fs_out, *otp.ECG_BAND))
+    return otp.segment(v, fs_out, onp.WindowSpec(ws)).contiguous().numpy(), trace
+
+
+@pytest.mark.parametrize("fs_in,fs_out,n,ws", [(2000, 4125, 60000, 4.0),     # config 2 row: 6-CTA clusters
+                                               (4000, 4125, 32000, 2.0),     # config 5 row: 2-CTA clusters
+                                               (2000, 4125, 9000, 1.0),      # short row: single CTA
+                                               (2000, 16000, 8000, 1.0)])    # 8x ratio
+def test_fused_pcg_vs_float64_oracle(pkg, fs_in, fs_out, n, ws):
+    x = _spiky(3, n, seed=21)
+    want, trace = _oracle_torch(x, fs_in, fs_out, ws)
+    got, edits, tr = pkg.preprocess_segment(_dev(x), fs_in, fs_out, pkg.WindowSpec(ws), fused=True, return_trace=True)
+    assert got.shape == want.shape
+    assert rel_err(got.cpu().numpy(), want) < TOL
+    assert len(trace) > 0
+    edits, tr = edits.cpu().numpy(), tr.cpu().numpy()
+    for r in range(3):
+        _check_trace(tr[r], int(edits[r]), [t[1:] for t in trace if t[0] == r])
+
+
+def test_fused_equals_chained_kernels(pkg):
+    x = _dev(_spiky(5, 60000, seed=22))
+    spec = pkg.WindowSpec(4.0)
+    a = pkg.preprocess_segment(x, 2000, 4125, spec, fused=True)
+    b = pkg.preprocess_segment(x, 2000, 4125, spec, fused=False)
+    assert a.shape == b.shape == (5, 7, 16500)
+    assert float((a - b).abs().max()) < 5e-6
+
+
+def test_fused_pcg_ecg_pair_and_layouts(pkg):
+    """Training-A shape: [B, 2, T] with a despiked PCG channel and an ECG channel, both output layouts."""
+    rng = np.random.default_rng(23)
+    pcg = _spiky(2, 20000, seed=24)
+    ecg = (np.sin(np.arange(20000) / 300.0)[None] + 0.05 * rng.standard_normal((2, 20000))).astype(np.float32)
+    x = np.stack([pcg, ecg], axis=1)
+    spec = pkg.WindowSpec(4.0)
+    want_p, _ = _oracle_torch(pcg, 2000, 4125, 4.0, "pcg")
+    want_e, _ = _oracle_torch(ecg, 2000, 4125, 4.0, "ecg")
+    planar = pkg.preprocess_segment(_dev(x), 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True).cpu().numpy()
+    assert planar.shape == (2, 2) + want_p.shape[1:]
+    assert rel_err(planar[:, 0], want_p) < TOL and rel_err(planar[:, 1], want_e) < TOL
+    last = pkg.preprocess_segment(_dev(x), 2000, 4125, spec, kinds=("pcg", "ecg"), channels_last=True,
+                                  fused=True).cpu().numpy()
+    assert last.shape == (2,) + want_p.shape[1:] + (2,)
+    np.testing.assert_array_equal(last[..., 0], planar[:, 0])
+    np.testing.assert_array_equal(last[..., 1], planar[:, 1])
+
+
+def test_fused_numpy_mode(pkg):
+    x = _spiky(2, 12000, seed=25)
+    spec = onp.WindowSpec(1.0)
+    got, edits, tr = pkg.preprocess_segment(_dev(x), 2000, 4125, pkg.WindowSpec(1.0), mode="numpy", fused=True,
+                                            return_trace=True)
+    got = got.cpu().numpy()
+    for r in range(2):
+        trace = []
+        v = onp.remove_spikes(onp.resample(x[r].astype(np.float64), 2000, 4125), 4125, trace=trace)
+        want = onp.segment(onp.abs_max_normalise(onp.bandpass_cascade(v, 4125, *onp.PCG_BAND)), 4125, spec)
+        assert rel_err(got[r], want) < TOL
+        assert rel_err(got[r], onp.segment(onp.preprocess_pcg(x[r], 2000, 4125), 4125, spec)) < TOL
+        # the kernel despikes the float32-rounded resampler output; its decisions must match the oracle run on
+        # the oracle's own float64 signal (ties between the two are vanishingly unlikely on this input)
+        _check_trace(tr[r].cpu().numpy(), int(edits[r]), trace)
+
+
+def test_fused_no_resampling_and_six_channels(pkg):
+    """Vest shape: six PCG channels; also the fs_in == fs_out identity path."""
+    x = np.stack([_spiky(2, 16000, seed=30 + c) for c in range(6)], axis=1)        # [2, 6, T]
+    spec = pkg.WindowSpec(2.0)
+    got = pkg.preprocess_segment(_dev(x), 4125, 4125, spec, channels_last=True, fused=True).cpu().numpy()
+    for c in range(6):
+        xt = torch.from_numpy(x[:, c]).double()
+        v = otp.abs_max_normalise(otp.bandpass_cascade(otp.remove_spikes(xt, 4125), 4125, *otp.PCG_BAND))
+        want = otp.segment(v, 4125, onp.WindowSpec(2.0)).contiguous().numpy()
+        assert rel_err(got[..., c], want) < TOL
+    got2 = pkg.preprocess_segment(_dev(x), 4000, 4125, spec, fused=True).cpu().numpy()
+    want2, _ = _oracle_torch(x[:, 3], 4000, 4125, 2.0)
+    assert got2.shape[:2] == (2, 6) and rel_err(got2[:, 3], want2) < TOL
+
+
+def test_fused_edge_lengths(pkg):
+    spec = pkg.WindowSpec(4.0)
+    for n in (300, 1000, 4000, 8001):        # shorter than the start pad / than one window / odd tails
+        x = _spiky(2, n, seed=40 + n % 7, spikes=1) if n > 50 else np.ones((2, n), np.float32)
+        want, _ = _oracle_torch(x, 2000, 4125, 4.0)
+        got = pkg.preprocess_segment(_dev(x), 2000, 4125, spec, fused=True).cpu().numpy()
+        assert got.shape == want.shape, n
+        assert rel_err(got, want) < TOL or np.abs(want).max() == 0
+        np.testing.assert_array_equal(got == 0, want == 0) if n <= 1000 else None
+    assert pkg.preprocess_segment(torch.zeros(0, 5000, device="cuda"), 2000, 4125, spec).shape[0] == 0
+
+
+def test_fused_vs_golden(pkg, golden):
+    g = golden("preprocess_2k_4125.npz")
+    got = pkg.preprocess_segment(_dev(g["pcg"]), 2000, 4125, pkg.WindowSpec(1.0), fused=True).cpu().numpy()
+    assert rel_err(got, g["t64_windows"]) < TOL
+    gotn = pkg.preprocess_segment(_dev(g["pcg"]), 2000, 4125, pkg.WindowSpec(1.0), mode="numpy", fused=True).cpu().numpy()
+    assert rel_err(gotn, g["np_windows"]) < TOL
+
+
+def test_fused_full_size_properties(pkg):
+    """Config-2 size (1024 recordings x {PCG, ECG} x 30 s): properties that need no oracle."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(1024, 2, 60000, device="cuda", generator=g)
+    x[:, 0, 7000:7004] += 25.0
+    spec = pkg.WindowSpec(4.0)
+    w = pkg.preprocess_segment(x, 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True)
+    assert w.shape == (1024, 2, 7, 16500)
+    assert torch.isfinite(w).all() and float(w.abs().max()) <= 1.0
+    # consecutive windows overlap by win - hop samples: the overlap must be bit-identical
+    ov = 16500 - 15469
+    assert torch.equal(w[:, :, :-1, -ov:], w[:, :, 1:, :ov])
+    # every row was scaled to hit +-1 somewhere in the full row (not necessarily inside the windows) and is
+    # unaffected by the other rows: recompute 3 rows alone
+    sub = pkg.preprocess_segment(x[5:8].contiguous(), 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True)
+    assert torch.equal(sub, w[5:8])

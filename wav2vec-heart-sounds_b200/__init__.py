@@ -7,5 +7,6 @@ name; the importable alias package next to it redirects here).
 from . import design, segment as _segment_mod  # noqa: F401
 from .segment import WINDOWS, WindowSpec, default_window
 from . import torchproc
+from .pipeline import preprocess_segment
 
-__all__ = ["torchproc", "WindowSpec", "WINDOWS", "default_window", "design"]
+__all__ = ["torchproc", "preprocess_segment", "WindowSpec", "WINDOWS", "default_window", "design"]

@@ -32,7 +32,25 @@ _SIGNATURES = {
     "mpcg_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
                                  ctypes.c_void_p]),
     "mpcg_window_count": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
+    "mpcg_preprocess_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, c_int, ctypes.c_void_p]),
 }
+EUNSUPPORTED = -3
+
+class ChainKind(ctypes.Structure):
+    """mpcg_chain_kind (include/mpcg_b200.h)."""
+    _fields_ = [("despike", c_int), ("n_sections", c_int), ("sos", (ctypes.c_double * 6) * 2)]
+
+
+class ChainDesc(ctypes.Structure):
+    """mpcg_chain_desc (include/mpcg_b200.h)."""
+    _fields_ = [("t_in", c_i64), ("t_out", c_i64), ("up", c_int), ("down", c_int), ("taps_per_phase", c_int),
+                ("offset", c_i64), ("taps", ctypes.c_void_p), ("despike_win", c_i64),
+                ("despike_threshold", ctypes.c_double), ("despike_max_iterations", c_int), ("median_mode", c_int),
+                ("norm_flags", c_int), ("seg_start", c_i64), ("seg_win", c_i64), ("seg_hop", c_i64),
+                ("seg_n", c_i64), ("channels_last", c_int), ("n_kinds", c_int), ("kinds", ChainKind * 2),
+                ("kind_of_channel", ctypes.c_uint8 * 8)]
+
 
 MEDIAN_LOWER, MEDIAN_MEAN = 0, 1
 NORM_NAN_TO_NUM, NORM_PEAK_GT0 = 1, 2

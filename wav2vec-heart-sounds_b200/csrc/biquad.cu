@@ -16,7 +16,7 @@ static inline double group_step(const double c[2][5], double z[4], double x) {
   return y1;
 }
 
-static void mat4_mul(const double* a, const double* b, double* out) {
+void bq_mat_mul(const double* a, const double* b, double* out) {
   double t[16];
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) {
@@ -25,6 +25,48 @@ static void mat4_mul(const double* a, const double* b, double* out) {
       t[r * 4 + c] = s;
     }
   memcpy(out, t, sizeof(t));
+}
+
+void bq_group_step(const double c[2][5], double z[4], double x) { group_step(c, z, x); }
+
+void bq_group_coeffs(const double* sos, int n_sections, int first, double c[2][5], bool* ok) {
+  *ok = true;
+  for (int s = 0; s < 2; ++s) {
+    for (int k = 0; k < 5; ++k) c[s][k] = 0.0;
+    const int idx = first + s;
+    if (idx < n_sections) {
+      const double* r = sos + 6 * idx;
+      const double a0 = r[3];
+      if (a0 == 0.0 || !isfinite(a0)) { *ok = false; return; }
+      c[s][0] = r[0] / a0; c[s][1] = r[1] / a0; c[s][2] = r[2] / a0;
+      c[s][3] = r[4] / a0; c[s][4] = r[5] / a0;
+    } else {
+      c[s][0] = 1.0;                           // pass-through padding section
+    }
+  }
+}
+
+void bq_group_AB(const double c[2][5], double A[16], double B[4]) {
+  for (int col = 0; col < 4; ++col) {
+    double z[4] = {0, 0, 0, 0};
+    z[col] = 1.0;
+    group_step(c, z, 0.0);
+    for (int r = 0; r < 4; ++r) A[r * 4 + col] = z[r];
+  }
+  double z[4] = {0, 0, 0, 0};
+  group_step(c, z, 1.0);
+  for (int r = 0; r < 4; ++r) B[r] = z[r];
+}
+
+void bq_mat_pow(const double A[16], long long n, double out[16]) {
+  double acc[16], base[16];
+  for (int i = 0; i < 16; ++i) { acc[i] = (i % 5 == 0) ? 1.0 : 0.0; base[i] = A[i]; }
+  while (n > 0) {
+    if (n & 1) bq_mat_mul(base, acc, acc);
+    bq_mat_mul(base, base, base);
+    n >>= 1;
+  }
+  for (int i = 0; i < 16; ++i) out[i] = acc[i];
 }
 
 int bq_make_plan(const double* sos, int n_sections, BqPlan* plan) {
@@ -68,9 +110,9 @@ int bq_make_plan(const double* sos, int n_sections, BqPlan* plan) {
     // M = A^L, then squarings.
     double M[16];
     for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    for (int k = 0; k < kBqL; ++k) mat4_mul(A, M, M);
+    for (int k = 0; k < kBqL; ++k) bq_mat_mul(A, M, M);
     memcpy(G.mp[0], M, sizeof(M));
-    for (int d = 1; d < 6; ++d) mat4_mul(G.mp[d - 1], G.mp[d - 1], G.mp[d]);
+    for (int d = 1; d < 6; ++d) bq_mat_mul(G.mp[d - 1], G.mp[d - 1], G.mp[d]);
   }
   return MPCG_OK;
 }

@@ -25,6 +25,13 @@ struct BqGroup {
   double wt[kBqL][kBqStates];            // pass-1 weights  A^(L-1-j) B
   double mp[6][kBqStates * kBqStates];   // M, M^2, M^4, M^8, M^16, M^32 (row-major)
 };
+
+// Host helpers shared with the fused kernel's planner (biquad.cu).
+void bq_group_coeffs(const double* sos, int n_sections, int first, double c[2][5], bool* ok);
+void bq_group_AB(const double c[2][5], double A[16], double B[4]);
+void bq_mat_pow(const double A[16], long long n, double out[16]);
+void bq_mat_mul(const double* a, const double* b, double* out);
+void bq_group_step(const double c[2][5], double z[4], double x);
 struct BqPlan {
   int ngroups;
   int pad_;

@@ -1,0 +1,5 @@
+// One resampler instance of the fused preprocess kernel (see fused_kernel.cuh).
+#include "fused_kernel.cuh"
+namespace mpcg {
+template int fz_launch<33, 32, 46, 1, 2>(const FzParams&, size_t, long long, cudaStream_t);
+}

@@ -5,82 +5,50 @@
 //   y[i*UP + p] = sum_{d<D} x[i*DOWN + off + d] * G[p][d]          (x = 0 outside the row)
 //
 // One thread owns FR consecutive frames i: it pulls the (FR-1)*DOWN + D input samples it needs from a
-// shared-memory tile into registers once, then runs UP*FR*D FFMAs whose tap operand comes straight
-// from the kernel-parameter constant bank (the taps travel as a __grid_constant__ struct, so there is
-// no tap buffer to allocate, upload or keep coherent between streams).  Outputs go through a second
+// shared-memory tile into registers once, then runs UP*FR*D FFMAs whose tap operand is an instruction
+// immediate: the taps of the named rate pairs are baked in at build time (resample_taps_gen.cuh) and the
+// launcher takes a baked instance only when the host-supplied taps match it bit for bit; any other
+// ratio goes to the generic kernel, whose taps ride in the parameter bank.  Outputs go through a second
 // shared tile so the global stores are fully coalesced.  Lane strides in both tiles are made odd by a
 // one-word-per-stride skew, which keeps every shared access conflict-free.
-#include "common.cuh"
+#include "resample.cuh"
 
 namespace mpcg {
 
 constexpr int kRsThreads = 256;
 
-template <int UP, int D>
-struct RsTaps {
-  float g[UP][D];
-};
-
-__host__ __device__ constexpr int rs_skew(int idx, int stride) { return (stride & 1) ? idx : idx + idx / stride; }
-
 template <int UP, int DOWN, int D, int FR>
 struct RsShape {
-  static constexpr int NF = kRsThreads * FR;                 // frames per CTA
-  static constexpr int NIN = (NF - 1) * DOWN + D;            // input samples per CTA
-  static constexpr int NOUT = NF * UP;                       // output samples per CTA
-  static constexpr int SIN = FR * DOWN;                      // lane stride in the input tile
+  using T = RsTile<UP, DOWN, D, FR, 1, kRsThreads>;
   static constexpr int SOUT = FR * UP;                       // lane stride in the output tile
-  static constexpr int IN_WORDS = rs_skew(NIN - 1, SIN) + 1;
-  static constexpr int OUT_WORDS = rs_skew(NOUT - 1, SOUT) + 1;
-  static constexpr int PER_THREAD_IN = (FR - 1) * DOWN + D;
-  static constexpr size_t SMEM = (size_t)(IN_WORDS + OUT_WORDS) * sizeof(float);
+  static constexpr int OUT_WORDS = rs_skew(T::NOUT - 1, SOUT) + 1;
+  static constexpr size_t SMEM = (size_t)(T::IN_WORDS + OUT_WORDS) * sizeof(float);
 };
 
 template <int UP, int DOWN, int D, int FR>
 __global__ void __launch_bounds__(kRsThreads)
 resample_frames_kernel(const float* __restrict__ x, float* __restrict__ y, long long t_in, long long t_out,
-                       long long off, const __grid_constant__ RsTaps<UP, D> taps) {
+                       long long off) {
   using S = RsShape<UP, DOWN, D, FR>;
+  using T = typename S::T;
   extern __shared__ __align__(16) float rs_smem[];
   float* xs = rs_smem;
-  float* ys = rs_smem + S::IN_WORDS;
+  float* ys = rs_smem + T::IN_WORDS;
   const int tid = threadIdx.x;
   const long long row = blockIdx.y;
-  const long long f0 = (long long)blockIdx.x * S::NF;         // first frame of this CTA
+  const long long f0 = (long long)blockIdx.x * T::NF;         // first frame of this CTA
   const float* xr = x + row * t_in;
   float* yr = y + row * t_out;
 
-  // ---- stage the input span (zero outside the row)
-  const long long in0 = f0 * DOWN + off;
-  for (int m = tid; m < S::NIN; m += kRsThreads) {
-    const long long src = in0 + m;
-    xs[rs_skew(m, S::SIN)] = (src >= 0 && src < t_in) ? ld_stream(xr + src) : 0.f;
-  }
+  T::stage(xs, xr, f0 * DOWN + off, t_in);
   __syncthreads();
-
-  // ---- registers <- this thread's input samples
-  float in[S::PER_THREAD_IN];
-  const int base = tid * S::SIN;
-#pragma unroll
-  for (int d = 0; d < S::PER_THREAD_IN; ++d) in[d] = xs[rs_skew(base + d, S::SIN)];
-
-  // ---- UP * FR outputs, taps as constant-bank operands
-  const int obase = tid * S::SOUT;
-#pragma unroll
-  for (int fr = 0; fr < FR; ++fr) {
-#pragma unroll
-    for (int p = 0; p < UP; ++p) {
-      float acc = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) acc = fmaf(in[fr * DOWN + d], taps.g[p][d], acc);
-      ys[rs_skew(obase + fr * UP + p, S::SOUT)] = acc;
-    }
-  }
+  auto sink = [&](int frame, int p, float v) { ys[rs_skew(frame * UP + p, S::SOUT)] = v; };
+  T::compute(xs, sink);
   __syncthreads();
 
   // ---- coalesced store of the CTA's output span
   const long long o0 = f0 * UP;
-  for (int o = tid; o < S::NOUT; o += kRsThreads) {
+  for (int o = tid; o < T::NOUT; o += kRsThreads) {
     const long long dst = o0 + o;
     if (dst < t_out) st_stream(yr + dst, ys[rs_skew(o, S::SOUT)]);
   }
@@ -128,20 +96,17 @@ resample_generic_kernel(const float* __restrict__ x, float* __restrict__ y, long
 }
 
 template <int UP, int DOWN, int D, int FR>
-static int launch_frames(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, const float* taps,
-                         int64_t off, cudaStream_t stream) {
+static int launch_frames(const float* x, float* y, int64_t rows, int64_t t_in, int64_t t_out, int64_t off,
+                         cudaStream_t stream) {
   using S = RsShape<UP, DOWN, D, FR>;
-  RsTaps<UP, D> tp;
-  for (int p = 0; p < UP; ++p)
-    for (int d = 0; d < D; ++d) tp.g[p][d] = taps[p * D + d];
   auto kern = resample_frames_kernel<UP, DOWN, D, FR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
   if (e != cudaSuccess) return (int)e;
   const int64_t frames = (t_out + UP - 1) / UP;
-  const int64_t tiles = (frames + S::NF - 1) / S::NF;
+  const int64_t tiles = (frames + S::T::NF - 1) / S::T::NF;
   if (tiles > 0x7fffffffLL || rows > 65535) return MPCG_ERANGE;
   dim3 grid((unsigned)tiles, (unsigned)rows);
-  kern<<<grid, kRsThreads, S::SMEM, stream>>>(x, y, (long long)t_in, (long long)t_out, (long long)off, tp);
+  kern<<<grid, kRsThreads, S::SMEM, stream>>>(x, y, (long long)t_in, (long long)t_out, (long long)off);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }
@@ -165,8 +130,8 @@ extern "C" int mpcg_resample_f32(const float* x, float* y, int64_t rows, int64_t
     int rc;
     const int D = taps_per_phase;
 #define MPCG_RS_CASE(U, DN, DD, FR)                                                            \
-  if (up == U && down == DN && D == DD) {                                                       \
-    rc = launch_frames<U, DN, DD, FR>(xs, ys, nr, t_in, t_out, taps, offset, stream);           \
+  if (up == U && down == DN && D == DD && rs_taps_match<U, DN, DD>(taps, offset)) {             \
+    rc = launch_frames<U, DN, DD, FR>(xs, ys, nr, t_in, t_out, offset, stream);                 \
     if (rc != MPCG_OK) return rc;                                                               \
     continue;                                                                                   \
   }
