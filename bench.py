@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: PCG audio-seconds preprocessed per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], named in `config.workload`): 1024 synthetic Training-A-shaped recordings per
+GPU, two channels (PCG + ECG), 30 s at 2 kHz -> resample to 4125 Hz, Schmidt despike (PCG), 25-450 Hz / 2-40 Hz
+band (fs-normalised, as the reference does), abs-max normalise, 4 s windows with 0.25 s overlap.
+A step = one pass of the hot path over that batch.
+
+  value      whole-job audio-s/s with inputs already resident in HBM (one fused kernel launch per step),
+             CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e        same metric through HostPipeline: pinned HOST buffers in, HOST buffers out, copies inside the
+             timed region.
+  roofline   algorithmic bytes of the fused kernel (input read once + windows written once) / its measured
+             duration, against the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline  the NumPy oracle (the reference's CPU algorithm, restated in oracle/numpy_path.py) timed on the
+             box's host cores on a bounded sample of the same workload (rank 0, N=1 only).
+
+--impl reference times that CPU implementation alone (all host threads) and prints the same line shape.
+Multi-GPU: recordings are sharded by index, no collective on the data path ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RECORDINGS = 1024           # per GPU
+T_IN = 60000                # 30 s at 2 kHz
+FS_IN, FS_OUT = 2000, 4125
+SECONDS = T_IN / FS_IN
+WINDOW_S = 4.0
+KINDS = ("pcg", "ecg")
+METRIC = "PCG audio-seconds preprocessed/sec"
+UNIT = "audio-s/s"
+WORKLOAD = ("configs[1]: Training-A-shaped PCG+ECG two-channel preprocessing, 1024 synthetic 30 s recordings per GPU, "
+            "2 kHz -> 4125 Hz, despike (PCG), PCG 25-450 Hz / ECG 2-40 Hz band, abs-max norm, 4 s / 0.25 s-overlap windows")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def _cpu_one(args):
+    """One recording through the reference's NumPy algorithm (oracle port): both channels + windows."""
+    import numpy as np
+    from oracle import numpy_path as onp
+    pcg, ecg = args
+    spec = onp.WindowSpec(WINDOW_S)
+    p = onp.preprocess_pcg(pcg, FS_IN, FS_OUT)
+    e = onp.preprocess_ecg(ecg, FS_IN, FS_OUT)
+    return onp.segment(np.stack([p, e], axis=1), FS_OUT, spec).shape[0]
+
+
+def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234):
+    """audio-s/s of the oracle port over `n_recordings` synthetic recordings using `cores` worker processes."""
+    import multiprocessing as mp
+    from wav2vec_heart_sounds_b200.synth import synth_pair
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    x = synth_pair(n_recordings, T_IN, FS_IN, seed=seed).numpy()
+    work = [(x[i, 0], x[i, 1]) for i in range(n_recordings)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_one, work[:cores])                     # warm the workers (imports, FFT plans)
+        t0 = time.perf_counter()
+        pool.map(_cpu_one, work, chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_recordings * SECONDS / dt, dt
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    # bounded sample: K + W steps must fit in ~90 s of wall clock at ~0.25 core-seconds per recording
+    per_step = int(90.0 / (args.steps + args.warmup) * cores / 0.25)
+    per_step = max(cores, min(per_step, RECORDINGS))
+    torch.set_num_threads(1)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_throughput(min(per_step, cores), cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_throughput(per_step, cores)
+        vals.append(v)
+        t_all += dt
+    value = per_step * SECONDS * args.steps / t_all
+    sample = f"{per_step} recordings per step (2 channels x 30 s), {cores} worker processes, NumPy/SciPy float64"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import wav2vec_heart_sounds_b200 as pkg
+    from wav2vec_heart_sounds_b200.pipeline import HostPipeline
+    from wav2vec_heart_sounds_b200.synth import synth_pair
+    spec = pkg.WindowSpec(WINDOW_S)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # shard `rank` of the job: its own 1024 recordings, generated on the device (no host or peer traffic)
+    x = synth_pair(RECORDINGS, T_IN, FS_IN, seed=1234 + rank, device=dev)
+    out = pkg.preprocess_segment(x, FS_IN, FS_OUT, spec, kinds=KINDS, fused=True)     # also the first warm-up
+    n_win, win = out.shape[2], out.shape[3]
+    algo_bytes = x.numel() * 4 + out.numel() * 4
+
+    def step():
+        pkg.preprocess_segment(x, FS_IN, FS_OUT, spec, kinds=KINDS, fused=True, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            step()
+        stop.record()
+        barrier()
+    ms = start.elapsed_time(stop)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * RECORDINGS * SECONDS * args.steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps                                   # one launch per step
+
+    # ---- end to end: host buffers in, host buffers out
+    hp = HostPipeline(RECORDINGS, 2, T_IN, FS_IN, FS_OUT, spec, kinds=KINDS, chunk=128, device=dev)
+    x_host = x.cpu().pin_memory()
+    out_host = hp.empty_output()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        hp(x_host, out_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hp(x_host, out_host)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * RECORDINGS * SECONDS * e2e_steps / float(t.item())
+    same = bool(torch.equal(out_host[:8], out[:8].cpu()))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 samples, f64 filter/normalise state", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "recordings_per_gpu": RECORDINGS, "channels": list(KINDS),
+                           "layout": f"[{RECORDINGS}, 2, {T_IN}] -> [{RECORDINGS}, 2, {n_win}, {win}]", "mode": "torch",
+                           "cache": "inputs (492 MB) and outputs (946 MB) per step exceed the 126 MB L2",
+                           "sharding": f"{world} x index-sharded, no collective"},
+                "gpu_launches": args.steps,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
+                        "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "matches_device_run": same},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": recorded_traffic(), "algorithmic_bytes_per_launch": algo_bytes,
+                             "kernel": "fused_preprocess_kernel<33,16,30,1,1>", "peak_source": peak_src},
+                "clocks": clocks.summary()}
+        if world == 1 and not args.no_cpu:
+            cores = host_cores()
+            n = min(RECORDINGS, 40 * cores)                   # ~10 s of wall clock on the host cores
+            v, dt = cpu_throughput(n, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} of the {RECORDINGS} recordings, NumPy/SciPy float64 oracle "
+                                              f"(oracle/numpy_path.py), {cores} worker processes, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

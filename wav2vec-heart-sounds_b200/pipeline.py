@@ -34,13 +34,13 @@ def _kind_struct(kind: str, fs_out: float, despike: bool) -> _lib.ChainKind:
 
 def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, kinds=None, despike: bool = True,
                        mode: str = "torch", channels_last: bool = False, return_trace: bool = False,
-                       trace_cap: int = 64, fused: bool | None = None):
+                       trace_cap: int = 64, fused: bool | None = None, out: torch.Tensor | None = None):
     """``[B, T]`` -> ``[B, N, win]``  or  ``[B, C, T]`` -> ``[B, C, N, win]`` (``[B, N, win, C]`` with
     ``channels_last``): resample, (PCG only) Schmidt despike, band-limit, abs-max normalise, segment.
 
     ``kinds``: one of ``"pcg"`` / ``"ecg"`` per channel (default: all ``"pcg"``), e.g. ``("pcg", "ecg")`` for the
     Training-A pair.  ``fused``: ``None`` = fused kernel when the geometry allows, ``True`` = require it,
-    ``False`` = always chain the stand-alone kernels.
+    ``False`` = always chain the stand-alone kernels.  ``out``: optional preallocated result tensor.
     """
     torchproc._check_mode(mode)
     x = _lib.require_cuda_f32(x)
@@ -90,7 +90,10 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
                 d.kinds[i] = _kind_struct(k, fs_out, despike)
             for ch in range(c):
                 d.kind_of_channel[ch] = uniq.index(kinds[ch])
-            out = torch.empty(shape, device=x.device, dtype=torch.float32)
+            if out is None:
+                out = torch.empty(shape, device=x.device, dtype=torch.float32)
+            elif tuple(out.shape) != tuple(shape) or not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {tuple(shape)}")
             rc = _lib.lib().mpcg_preprocess_segment_f32(v.data_ptr(), out.data_ptr(), b, c, ctypes.byref(d),
                                                         _lib.ptr(edits), _lib.ptr(trace),
                                                         trace_cap if return_trace else 0, _lib.stream_ptr(v))
@@ -118,5 +121,69 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
             col = torchproc.preprocess_ecg(col, fs_in, fs_out, mode=mode)
         chans.append(col)
     stacked = chans[0] if planar_in else torch.stack(chans, dim=1)
-    out = torchproc.segment(stacked, fs_out, spec, channels_last=channels_last)
-    return (out, edits, trace) if return_trace else out
+    res = torchproc.segment(stacked, fs_out, spec, channels_last=channels_last)
+    if out is not None:
+        out.copy_(res)
+        res = out
+    return (res, edits, trace) if return_trace else res
+
+
+class HostPipeline:
+    """Host buffers in, host buffers out: the call a loader makes per batch of recordings.
+
+    The batch is cut into chunks; chunk i's host->device copy, chunk i-1's kernel and chunk i-2's device->host
+    copy run concurrently on three CUDA streams (PCIe is full duplex), so a step costs about
+    max(H2D, D2H) instead of their sum.  Buffers are allocated once and reused.
+    """
+
+    def __init__(self, recordings: int, channels: int, t_in: int, fs_in: float, fs_out: float, spec, *, kinds=None,
+                 mode: str = "torch", channels_last: bool = False, chunk: int = 128, device="cuda"):
+        self.args = dict(fs_in=fs_in, fs_out=fs_out, spec=spec, kinds=kinds, mode=mode, channels_last=channels_last)
+        self.device = torch.device(device)
+        self.chunk = min(chunk, recordings)
+        self.recordings, self.channels, self.t_in = recordings, channels, t_in
+        probe = preprocess_segment(torch.zeros(1, channels, t_in, device=self.device), **self.args)
+        self.out_shape = (recordings,) + tuple(probe.shape[1:])
+        nbuf = 3
+        self.dev_in = [torch.empty(self.chunk, channels, t_in, device=self.device) for _ in range(nbuf)]
+        self.dev_out = [torch.empty((self.chunk,) + tuple(probe.shape[1:]), device=self.device) for _ in range(nbuf)]
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.h2d_bytes = recordings * channels * t_in * 4
+        self.d2h_bytes = int(torch.tensor(self.out_shape).prod()) * 4
+
+    def empty_output(self) -> torch.Tensor:
+        return torch.empty(self.out_shape, dtype=torch.float32).pin_memory()
+
+    def __call__(self, x_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
+        """x_host [recordings, channels, t_in] (pinned for speed) -> out_host (pinned), both on the host."""
+        if x_host.is_cuda or out_host.is_cuda:
+            raise ValueError("HostPipeline takes host tensors; use preprocess_segment for device tensors")
+        n = self.recordings
+        nbuf = len(self.dev_in)
+        copied = [torch.cuda.Event() for _ in range(nbuf)]
+        ran = [torch.cuda.Event() for _ in range(nbuf)]
+        drained = [torch.cuda.Event() for _ in range(nbuf)]
+        entry = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(entry)
+        for i, lo in enumerate(range(0, n, self.chunk)):
+            hi = min(lo + self.chunk, n)
+            b = i % nbuf
+            with torch.cuda.stream(self.s_in):
+                if i >= nbuf:
+                    self.s_in.wait_event(ran[b])              # the kernel that read this buffer is done
+                self.dev_in[b][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                copied[b].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(copied[b])
+                if i >= nbuf:
+                    self.s_run.wait_event(drained[b])         # the copy-out that read this buffer is done
+                preprocess_segment(self.dev_in[b][: hi - lo], out=self.dev_out[b][: hi - lo], **self.args)
+                ran[b].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ran[b])
+                out_host[lo:hi].copy_(self.dev_out[b][: hi - lo], non_blocking=True)
+                drained[b].record(self.s_out)
+        for s in (self.s_in, self.s_run, self.s_out):
+            entry.wait_stream(s)
+        return out_host
