@@ -121,6 +121,10 @@ int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t recordings, 
                                 const mpcg_chain_desc* desc, int32_t* edits, int32_t* trace, int trace_cap,
                                 void* stream);
 
+/* Profiling aid (tools/ only): device buffer [ctas, 16] of int64 that the fused kernel fills with clock64 stamps at
+ * its phase boundaries; NULL switches it off.  Not part of the data path. */
+void mpcg_debug_set_phase_clock_buffer(void* dev_ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,7 +95,7 @@ def test_window_count_matches_reference_table(golden, built_lib):
 
 def test_library_exports_every_declared_symbol(built_lib):
     header = (ROOT / "include" / "mpcg_b200.h").read_text()
-    names = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(mpcg_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    names = set(re.findall(r"^(?:int|int64_t|void|const char\*)\s+(mpcg_[a-z0-9_]+)\s*\(", header, flags=re.M))
     assert names, "no prototypes found in the header"
     handle = ctypes.CDLL(str(built_lib.LIB_PATH))
     for n in sorted(names):

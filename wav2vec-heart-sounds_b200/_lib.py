@@ -34,6 +34,7 @@ _SIGNATURES = {
     "mpcg_window_count": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
     "mpcg_preprocess_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_debug_set_phase_clock_buffer": (None, [ctypes.c_void_p]),
 }
 EUNSUPPORTED = -3
 

@@ -63,13 +63,107 @@ __device__ __forceinline__ SpikeDecision spike_decide(const float* tops, int nfr
   return d;
 }
 
+// Same decision computed by ONE WARP from shared memory, no block barrier: every warp of a CTA (and of
+// every CTA of a cluster) runs it redundantly and arrives at identical bits.  O(n^2 / 32) per warp.
+__device__ __forceinline__ SpikeDecision spike_decide_warp(const float* tops, int nframes, double threshold,
+                                                           int median_mode) {
+  const int lane = threadIdx.x & 31;
+  SpikeDecision d;
+  float bv = -1.f;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < nframes; i += 32) {
+    const float v = tops[i];
+    if (v > bv) { bv = v; bi = i; }
+  }
+  warp_argmax_first(bv, bi);
+  d.worst = bi;
+  const int k_lo = (nframes - 1) >> 1, k_hi = nframes >> 1;
+  float c_lo = -1.f, c_hi = -1.f;                    // frame maxima are >= 0, so -1 means "not mine"
+  for (int i = lane; i < nframes; i += 32) {
+    const float vi = tops[i];
+    int less = 0, leq = 0;
+    for (int j = 0; j < nframes; ++j) {
+      const float vj = tops[j];
+      less += (vj < vi);
+      leq += (vj <= vi);
+    }
+    if (less <= k_lo && k_lo < leq) c_lo = vi;
+    if (less <= k_hi && k_hi < leq) c_hi = vi;
+  }
+  const float lo_mid = warp_max(c_lo), hi_mid = warp_max(c_hi);
+  if (median_mode == MPCG_MEDIAN_LOWER) {
+    d.active = bv > __fmul_rn((float)threshold, lo_mid);
+  } else {
+    const double med = ((double)lo_mid + (double)hi_mid) * 0.5;
+    d.active = (med != 0.0) && ((double)bv > threshold * med);
+  }
+  return d;
+}
+
+// <= 64 frames (a 30 s recording has 60): bitonic sort of 64 (value, ~index) keys held two per lane.
+// key = float bits << 32 | (0xffffffff - index): frame maxima are >= 0 so the bit pattern orders like the
+// value, and among equal values the smaller index sorts higher, which makes the largest key the FIRST arg-max.
+__device__ __forceinline__ SpikeDecision spike_decide_sort64(const float* tops, int nframes, double threshold,
+                                                             int median_mode) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long k0, k1;                       // elements 2*lane and 2*lane+1 of the 64-element array
+  {
+    const int i0 = 2 * lane, i1 = 2 * lane + 1;
+    // padding keys are the smallest possible (0) so real frames occupy the top `nframes` sorted slots
+    k0 = (i0 < nframes) ? (((unsigned long long)__float_as_uint(tops[i0]) << 32) | (0xffffffffu - (unsigned)i0)) : 0ull;
+    k1 = (i1 < nframes) ? (((unsigned long long)__float_as_uint(tops[i1]) << 32) | (0xffffffffu - (unsigned)i1)) : 0ull;
+  }
+  // bitonic network over 64 elements, element e = 2*lane + b
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 1) {                           // partner is the other element of the same lane
+        const bool up = ((2 * lane) & size) == 0;  // ascending block?
+        const unsigned long long lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+        k0 = up ? lo : hi;
+        k1 = up ? hi : lo;
+      } else {                                     // partner element lives in lane ^ (stride / 2), same b
+        const int pl = stride >> 1;
+        const unsigned long long o0 = __shfl_xor_sync(kFull, k0, pl), o1 = __shfl_xor_sync(kFull, k1, pl);
+        const bool up = ((2 * lane) & size) == 0;
+        const bool lower = (lane & pl) == 0;       // am I the lower index of the pair?
+        const bool take_min = (up == lower);
+        k0 = take_min ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+        k1 = take_min ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+      }
+    }
+  }
+  // ascending: sorted position s holds element s; real frames sit at positions 64 - nframes .. 63
+  auto at = [&](int pos) -> unsigned long long {
+    const unsigned long long a = __shfl_sync(kFull, k0, pos >> 1), b = __shfl_sync(kFull, k1, pos >> 1);
+    return (pos & 1) ? b : a;
+  };
+  const int base = 64 - nframes;
+  const unsigned long long top = at(63);
+  SpikeDecision d;
+  d.worst = (int)(0xffffffffu - (unsigned)(top & 0xffffffffu));
+  const float bv = __uint_as_float((unsigned)(top >> 32));
+  const float lo_mid = __uint_as_float((unsigned)(at(base + ((nframes - 1) >> 1)) >> 32));
+  if (median_mode == MPCG_MEDIAN_LOWER) {
+    d.active = bv > __fmul_rn((float)threshold, lo_mid);
+  } else {
+    const float hi_mid = __uint_as_float((unsigned)(at(base + (nframes >> 1)) >> 32));
+    const double med = ((double)lo_mid + (double)hi_mid) * 0.5;
+    d.active = (med != 0.0) && ((double)bv > threshold * med);
+  }
+  return d;
+}
+
 // Flatten the spike in one frame held in shared memory.  Returns (through refs) the integer decisions;
 // `changed` tells whether any sample actually moved (an unchanged pass is a fixed point: every later
 // pass of the reference would repeat it, so the caller may stop).  All threads call.
 template <int THREADS>
 __device__ __forceinline__ void spike_flatten(float* fr, int win, int& peak, int& lo, int& hi, bool& changed,
                                               float& new_top, float* fscr, int* iscr) {
-  const int tid = threadIdx.x;
+  constexpr int NW = THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (1) first arg-max of |x|
   float bv = -1.f;
   int bi = 0x7fffffff;
   for (int i = tid; i < win; i += THREADS) {
@@ -78,7 +172,8 @@ __device__ __forceinline__ void spike_flatten(float* fr, int win, int& peak, int
   }
   block_argmax_first<THREADS>(bv, bi, fscr, iscr);
   peak = bi;
-  // strict sign flips between i and i+1 (zeros are not flips)
+  // (2) strict sign flips between i and i+1 (zeros are not flips): last one before the peak, first at/after it.
+  //     One exchange for both: iscr[0..NW) holds the per-warp maxima, iscr[NW..2NW) the per-warp minima.
   int last_before = -1, first_after = 0x7fffffff;
   for (int i = tid; i < win - 1; i += THREADS) {
     const float a = fr[i], b = fr[i + 1];
@@ -88,19 +183,40 @@ __device__ __forceinline__ void spike_flatten(float* fr, int win, int& peak, int
       else first_after = min(first_after, i);
     }
   }
-  last_before = block_max_i<THREADS>(last_before, iscr);
-  first_after = block_min_i<THREADS>(first_after, iscr);
+  last_before = warp_max_i(last_before);
+  first_after = warp_min_i(first_after);
+  __syncthreads();
+  if (lane == 0) { iscr[warp] = last_before; iscr[NW + warp] = first_after; }
+  __syncthreads();
+  last_before = iscr[0]; first_after = iscr[NW];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) { last_before = max(last_before, iscr[w]); first_after = min(first_after, iscr[NW + w]); }
   lo = last_before + 1;                          // -1 + 1 = 0 when there is no earlier flip
   hi = (first_after == 0x7fffffff) ? win - 1 : first_after;
+  // (3) fill the span; the frame's new maximum is max(|fill|, max |x| outside the span); one exchange for
+  //     (moved?, outside maximum)
   int moved = 0;
-  for (int i = lo + tid; i < hi; i += THREADS) {
-    moved |= (fr[i] != kSpikeFill);
-    fr[i] = kSpikeFill;
-  }
-  changed = block_max_i<THREADS>(moved, iscr) != 0;
   float m = 0.f;
-  for (int i = tid; i < win; i += THREADS) m = fmaxf(m, fabsf(fr[i]));   // block_max's leading sync orders the writes
-  new_top = block_max<THREADS>(m, fscr);
+  for (int i = tid; i < win; i += THREADS) {
+    const float v = fr[i];
+    if (i >= lo && i < hi) {
+      moved |= (v != kSpikeFill);
+      fr[i] = kSpikeFill;
+      m = fmaxf(m, kSpikeFill);
+    } else {
+      m = fmaxf(m, fabsf(v));
+    }
+  }
+  moved = warp_max_i(moved);
+  m = warp_max(m);
+  __syncthreads();                               // every thread is done reading iscr from step (2)
+  if (lane == 0) { iscr[warp] = moved; fscr[warp] = m; }
+  __syncthreads();
+  moved = iscr[0]; m = fscr[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) { moved |= iscr[w]; m = fmaxf(m, fscr[w]); }
+  changed = moved != 0;
+  new_top = m;
 }
 
 }  // namespace mpcg

@@ -27,21 +27,29 @@ namespace cg = cooperative_groups;
 
 namespace mpcg {
 
-constexpr int kFzThreads = 256;
+#ifndef MPCG_FZ_THREADS
+#define MPCG_FZ_THREADS 512              // threads per CTA (512 x 2 CTAs/SM measured faster than 1024 x 1)
+#endif
+#ifndef MPCG_FZ_MINBLOCKS
+#define MPCG_FZ_MINBLOCKS 2              // CTAs per SM the register allocation is sized for
+#endif
+constexpr int kFzThreads = MPCG_FZ_THREADS;
 constexpr int kFzWarps = kFzThreads / 32;
-constexpr int kFzLmax = 161;              // longest per-thread chunk (odd)
-constexpr int kFzMaxFrames = 1024;        // despike frames per row the fused kernel accepts
+constexpr int kFzChunks = kFzThreads;     // one filter chunk per thread
+constexpr int kFzLmax = 81;               // longest chunk (odd)
+constexpr int kFzMaxFrames = 256;        // despike frames per row the fused kernel accepts
 constexpr int kFzMaxCluster = 8;
-constexpr int kFzStageWords = 4400;       // resampler input staging (largest instance: 4110 + skew)
+constexpr int kFzStageWords = 4400;       // resampler input staging (largest instance: 4116 + skew)
 
 struct FzKind {                           // per channel kind (PCG / ECG): despike on/off + its filter
   int despike;
   int pad_;
   double c[2][5];                         // two sections, b0 b1 b2 a1 a2
   double wt[kFzLmax][4];                  // A^(L-1-j) B
-  double mp[8][16];                       // M^(2^d), d = 0..7, M = A^L  (d >= 5 move whole warps)
+  double mp[10][16];                      // M^(2^d), d = 0..9, M = A^L  (d >= 5 move whole warps)
   double prop_slice[16];                  // A^S: state across one full slice
   double prop_part[16];                   // A^nq: state across the valid part of the last chunk of a full slice
+  double mlane[32][16];                   // M^lane, lane = 0..31
 };
 
 struct FzParams {
@@ -49,12 +57,13 @@ struct FzParams {
   float* out;
   int* edits;
   int* trace;
+  long long* dbg;                         // optional [ctas, 16] clock64 stamps per phase (tools/ only)
   int trace_cap;
   int channels;                           // rows per recording
   int t_in, t;                            // samples per row before / after resampling
   int off;                                // resampler input offset
   int identity;                           // 1: no resampling (copy)
-  int ncl, S, L, cap;                     // cluster size, slice length, chunk length, L * threads
+  int ncl, S, L, cap;                     // cluster size, slice length, chunk length, L * chunks
   int q, nq;                              // chunk holding the last sample of a full slice, valid samples in it
   int win_d, nframes, fpc;                // despike frame length, frames per row, frames per CTA
   double threshold;
@@ -62,28 +71,79 @@ struct FzParams {
   int start, win, hop, n;                 // window geometry
   long long so_b, so_c, so_k, so_j;       // output strides (elements): recording, channel, window, sample
   unsigned char kind_of_channel[8];
-  FzKind kind[2];
+  const FzKind* kinds;                    // DEVICE pointer to the (up to two) channel recipes of this call
 };
 
+struct FzFilterScratch {                  // this row's recipe, copied from global memory once per CTA
+  double mtab[16][32];                    // M^lane, element-major so a warp's loads are conflict-free
+  double wt[kFzLmax][4];                  // pass-1 weights
+  double mp[10][16];                      // M^(2^d)
+  double prop_slice[16];
+  double prop_part[16];
+  double c[2][5];
+  double wagg[kFzWarps][4];               // warp aggregates
+  double wcar[kFzWarps][4];               // state at the start of each warp's first chunk (zero slice start)
+};
 struct FzShared {
-  double mtab[32][16];                    // M^lane
-  double wagg[kFzWarps][4];
-  double wcar[kFzWarps][4];
+  union {                                 // the resampler's input staging is dead once the slice is in `sig`
+    float xs[kFzStageWords];
+    FzFilterScratch f;
+  };
   double xE[kFzMaxCluster][4];            // end states exported by each rank
   double xstat[kFzMaxCluster][4];         // (sum, min, max, -) exported by each rank
-  double dscr[32];
-  float tops[kFzMaxFrames];
+  double wstat[kFzWarps][4];
+  float tops[2][kFzMaxFrames];            // double-buffered frame maxima (see the despike loop)
   float fscr[40];
-  int iscr[32];
+  int iscr[64];
   int ctrl[4];
-  float xs[kFzStageWords];
+  int decision[2];                        // (active, worst) broadcast by warp 0
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void mv4_set(const double* __restrict__ m, const double (&v)[4], double (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double a = m[r * 4] * v[0];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) a = fma(m[r * 4 + c], v[c], a);
+    out[r] = a;
+  }
+}
+
+// acc += (M^lane) v with the element-major table: element (r, c) of lane's matrix sits at tab[r*4+c][lane].
+__device__ __forceinline__ void mv4_lane_acc(const double (*tab)[32], int lane, const double (&v)[4], double (&acc)[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double a = acc[r];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a = fma(tab[r * 4 + c][lane], v[c], a);
+    acc[r] = a;
+  }
+}
+
+struct FzCoef {
+  double b00, b01, b02, a01, a02, b10, b11, b12, a11, a12;
+};
+// One sample through both sections (transposed direct form II).
+__device__ __forceinline__ double fz_step(const FzCoef& k, double (&z)[4], double xv) {
+  const double y0 = fma(k.b00, xv, z[0]);
+  z[0] = fma(-k.a01, y0, fma(k.b01, xv, z[1]));
+  z[1] = fma(-k.a02, y0, k.b02 * xv);
+  const double y1 = fma(k.b10, y0, z[2]);
+  z[2] = fma(-k.a11, y1, fma(k.b11, y0, z[3]));
+  z[3] = fma(-k.a12, y1, k.b12 * y0);
+  return y1;
+}
+__device__ __forceinline__ float fz_round(double y, bool fix_nan) {
+  float v = (float)y;
+  if (fix_nan && !(fabsf(v) <= FLT_MAX)) v = (v != v) ? 0.f : (v > 0.f ? FLT_MAX : -FLT_MAX);
+  return v;
+}
+
 template <int UP, int DOWN, int D, int FR, int PS>
-__global__ void __launch_bounds__(kFzThreads, 2)
+__global__ void __launch_bounds__(kFzThreads, MPCG_FZ_MINBLOCKS)
 fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   extern __shared__ __align__(16) unsigned char fz_raw[];
   FzShared& sm = *reinterpret_cast<FzShared*>(fz_raw);
@@ -94,36 +154,18 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   const long long row = blockIdx.x / P.ncl;
   const int ch = (int)(row % P.channels);
   const long long rec = row / P.channels;
-  const FzKind& K = P.kind[P.kind_of_channel[ch]];
+  const FzKind* __restrict__ Kg = P.kinds + P.kind_of_channel[ch];
+  const int k_despike = Kg->despike;
   const int s0 = rank * P.S;
   int n = (rank == P.ncl - 1) ? (P.t - s0) : P.S;
   if (n < 0) n = 0;
-
-  // ---------------------------------------------------------------- M^lane table (warp 0), overlaps the loads
-  if (tid < 32) {
-    double acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = (i % 5 == 0) ? 1.0 : 0.0;
-#pragma unroll
-    for (int d = 0; d < 5; ++d) {
-      if ((tid >> d) & 1) {
-        double nxt[16];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a = fma(K.mp[d][r * 4 + k], acc[k * 4 + c], a);
-            nxt[r * 4 + c] = a;
-          }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = nxt[i];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sm.mtab[tid][i] = acc[i];
-  }
+  const int L = P.L;
+  int dbg_k = 0;
+  auto stamp = [&]() {
+    if (P.dbg && tid == 0) P.dbg[(long long)blockIdx.x * 16 + dbg_k] = clock64();
+    ++dbg_k;
+  };
+  stamp();                                                // 0: start
 
   // ---------------------------------------------------------------- 1. resample my slice into shared memory
   const float* xr = P.x + row * (long long)P.t_in;
@@ -133,24 +175,40 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     using T = RsTile<UP, DOWN, D, FR, PS, kFzThreads>;
     static_assert(T::IN_WORDS <= kFzStageWords, "staging buffer too small for this resampler instance");
     const int f_lo = s0 / UP, f_hi = (s0 + n - 1) / UP;
+    float pre[T::NPRE];
+    T::fetch(pre, xr, (long long)f_lo * DOWN + P.off, P.t_in);
     for (int fb = f_lo; fb <= f_hi; fb += T::NF) {
-      T::stage(sm.xs, xr, (long long)fb * DOWN + P.off, P.t_in);
+      T::commit(sm.xs, pre);
       __syncthreads();
+      if (fb + T::NF <= f_hi) T::fetch(pre, xr, (long long)(fb + T::NF) * DOWN + P.off, P.t_in);   // next tile in flight
       const int obase = fb * UP - s0;
       auto sink = [&](int frame, int p, float v) {
         const int o = obase + frame * UP + p;
-        if (o >= 0 && o < n) sig[o] = v;
+        if ((unsigned)o < (unsigned)n) sig[o] = v;
       };
       T::compute(sm.xs, sink);
       __syncthreads();
     }
   }
+  stamp();                                                // 1: slice resampled
   for (int i = n + tid; i < P.cap; i += kFzThreads) sig[i] = 0.f;      // chunk grid beyond the slice
+
+  // ---------------------------------------------------------------- filter tables (independent of the samples)
+  // recipe tables: global (L2-resident, ~11 KB) -> shared, coalesced; everything below reads shared memory
+  for (int i = tid; i < 512; i += kFzThreads) sm.f.mtab[i & 15][i >> 4] = (&Kg->mlane[0][0])[i];
+  for (int i = tid; i < L * 4; i += kFzThreads) (&sm.f.wt[0][0])[i] = (&Kg->wt[0][0])[i];
+  for (int i = tid; i < 160; i += kFzThreads) (&sm.f.mp[0][0])[i] = (&Kg->mp[0][0])[i];
+  if (tid < 16) { sm.f.prop_slice[tid] = Kg->prop_slice[tid]; sm.f.prop_part[tid] = Kg->prop_part[tid]; }
+  if (tid < 10) (&sm.f.c[0][0])[tid] = (&Kg->c[0][0])[tid];
   __syncthreads();
 
+  stamp();                                                // 2: tables ready
   // ---------------------------------------------------------------- 2. Schmidt despike (cluster-wide)
+  // Every CTA keeps two copies of all frame maxima.  Pass k reads copy k&1; the owner of the worst frame
+  // flattens it in its own shared memory and writes the frame's new maximum (and a "changed" flag) into copy
+  // (k+1)&1 of every CTA while each CTA carries the other entries over locally: one cluster barrier per pass.
   int passes = 0;
-  if (K.despike && P.nframes > 0) {
+  if (k_despike && P.nframes > 0) {
     const int gf0 = rank * P.fpc;
     int nloc = P.nframes - gf0;
     nloc = nloc < 0 ? 0 : (nloc > P.fpc ? P.fpc : nloc);
@@ -159,35 +217,44 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
       float m = 0.f;
       for (int i = lane; i < P.win_d; i += 32) m = fmaxf(m, fabsf(p[i]));
       m = warp_max(m);
-      if (lane < P.ncl) *cluster.map_shared_rank(&sm.tops[gf0 + f], lane) = m;
+      if (lane < P.ncl) *cluster.map_shared_rank(&sm.tops[0][gf0 + f], lane) = m;
     }
     cluster_arrive();
     cluster_wait();
     for (; passes < P.max_iter; ++passes) {
-      const SpikeDecision dec =
-          spike_decide<kFzThreads>(sm.tops, P.nframes, P.threshold, P.median_mode, sm.fscr, sm.iscr);
+      const float* cur = sm.tops[passes & 1];
+      float* nxt = sm.tops[(passes + 1) & 1];
+      SpikeDecision dec;
+      if (warp == 0) {                                    // one warp decides, the CTA reads the verdict
+        dec = (P.nframes <= 64) ? spike_decide_sort64(cur, P.nframes, P.threshold, P.median_mode)
+                                : spike_decide_warp(cur, P.nframes, P.threshold, P.median_mode);
+        if (lane == 0) { sm.decision[0] = dec.active ? 1 : 0; sm.decision[1] = dec.worst; }
+      }
+      __syncthreads();
+      dec.active = sm.decision[0] != 0;
+      dec.worst = sm.decision[1];
       if (!dec.active) break;
       const int owner = dec.worst / P.fpc;
-      cluster_arrive();                                   // every CTA has finished reading tops
-      int peak = 0, lo = 0, hi = 0;
-      bool changed = false;
-      float new_top = 0.f;
+      for (int i = tid; i < P.nframes; i += kFzThreads)
+        if (i != dec.worst) nxt[i] = cur[i];
       if (rank == owner) {
+        int peak, lo, hi;
+        bool changed;
+        float new_top;
         spike_flatten<kFzThreads>(sig + (dec.worst - gf0) * P.win_d, P.win_d, peak, lo, hi, changed, new_top,
                                   sm.fscr, sm.iscr);
         if (tid == 0 && P.trace && passes < P.trace_cap) {
           int* tr = P.trace + (row * P.trace_cap + passes) * 4;
           tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
         }
-      }
-      cluster_wait();
-      if (rank == owner && tid < P.ncl) {
-        *cluster.map_shared_rank(&sm.tops[dec.worst], tid) = new_top;
-        *cluster.map_shared_rank(&sm.ctrl[0], tid) = changed ? 1 : 0;
+        if (tid < P.ncl) {
+          *cluster.map_shared_rank(&nxt[dec.worst], tid) = new_top;
+          *cluster.map_shared_rank(&sm.ctrl[(passes + 1) & 1], tid) = changed ? 1 : 0;
+        }
       }
       cluster_arrive();
       cluster_wait();
-      if (!sm.ctrl[0]) { ++passes; break; }               // fixed point: the reference would only repeat it
+      if (!sm.ctrl[(passes + 1) & 1]) { ++passes; break; }   // fixed point: the reference would only repeat it
     }
     if (P.edits && rank == 0 && tid == 0) P.edits[row] = passes;
     __syncthreads();
@@ -195,16 +262,21 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     P.edits[row] = 0;
   }
 
+  stamp();                                                // 3: despiked
   // ---------------------------------------------------------------- 3. low-pass + high-pass as one 4-state scan
-  const int L = P.L;
   float* mine = sig + tid * L;
   double p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
   for (int j = 0; j < L; ++j) {
+    const double2 w01 = *reinterpret_cast<const double2*>(&sm.f.wt[j][0]);
+    const double2 w23 = *reinterpret_cast<const double2*>(&sm.f.wt[j][2]);
     const double xv = (double)mine[j];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) p[s] = fma(K.wt[j][s], xv, p[s]);
+    p[0] = fma(w01.x, xv, p[0]);
+    p[1] = fma(w01.y, xv, p[1]);
+    p[2] = fma(w23.x, xv, p[2]);
+    p[3] = fma(w23.y, xv, p[3]);
   }
+  stamp();                                                // 4: pass 1 done
   const bool exporter = (P.ncl > 1) && (rank < P.ncl - 1) && (tid == P.q);
   double pp[4] = {0.0, 0.0, 0.0, 0.0};
   if (exporter) {                                         // zero-state response of the partial last chunk
@@ -212,33 +284,40 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     for (int j = 0; j < P.nq; ++j) {
       const double xv = (double)mine[j];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) pp[s] = fma(K.wt[j + shift][s], xv, pp[s]);
+      for (int s = 0; s < 4; ++s) pp[s] = fma(sm.f.wt[j + shift][s], xv, pp[s]);
     }
   }
 #pragma unroll
-  for (int d = 0; d < 5; ++d) {
+  for (int d = 0; d < 5; ++d) {                           // inclusive scan inside the warp
     double u[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, p[s], 1 << d);
-    if (lane >= (1 << d)) mv4_acc(K.mp[d], u, p);
+    if (lane >= (1 << d)) mv4_acc(sm.f.mp[d], u, p);
   }
   if (lane == 31) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) sm.wagg[warp][s] = p[s];
+    for (int s = 0; s < 4; ++s) sm.f.wagg[warp][s] = p[s];
   }
   __syncthreads();
-  if (tid == 0) {                                         // chain the warp aggregates from a zero slice start
-    double c[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int w = 0; w < kFzWarps; ++w) {
-      double nx[4];
+  if (warp == 0) {                                        // scan the warp aggregates in one warp
+    double v[4];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) { sm.wcar[w][s] = c[s]; nx[s] = sm.wagg[w][s]; }
-      mv4_acc(K.mp[5], c, nx);
+    for (int s = 0; s < 4; ++s) v[s] = (lane < kFzWarps) ? sm.f.wagg[lane][s] : 0.0;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) c[s] = nx[s];
+    for (int d = 0; d < 5; ++d) {
+      double u[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, v[s], 1 << d);
+      if (lane >= (1 << d)) mv4_acc(sm.f.mp[5 + d], u, v);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const double e = __shfl_up_sync(kFull, v[s], 1);
+      if (lane < kFzWarps) sm.f.wcar[lane][s] = lane ? e : 0.0;
     }
   }
   __syncthreads();
+  stamp();                                                // 5: intra-CTA scan done
   double z[4];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
@@ -248,13 +327,13 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   {
     double wc[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) wc[s] = sm.wcar[warp][s];
-    mv4_acc(sm.mtab[lane], wc, z);                       // start state of my chunk for a zero slice start
+    for (int s = 0; s < 4; ++s) wc[s] = sm.f.wcar[warp][s];
+    mv4_lane_acc(sm.f.mtab, lane, wc, z);                     // chunk start state for a zero slice start
   }
   if (P.ncl > 1) {
     if (exporter) {
       double e[4] = {pp[0], pp[1], pp[2], pp[3]};
-      mv4_acc(K.prop_part, z, e);                         // E = A^nq * start_q + partial response
+      mv4_acc(sm.f.prop_part, z, e);                         // E = A^nq start_q + partial response
       for (int rk = 0; rk < P.ncl; ++rk) {
         double* dst = cluster.map_shared_rank(&sm.xE[rank][0], rk);
 #pragma unroll
@@ -263,66 +342,64 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     }
     cluster_arrive();
     cluster_wait();
-    // true slice start state: c_(r+1) = A^S c_r + E_r ; then move it to my chunk: M^(32*warp + lane)
+    // true slice start state c_(r+1) = A^S c_r + E_r, then carried to my chunk: M^(32*warp + lane)
     double c[4] = {0.0, 0.0, 0.0, 0.0};
     for (int r = 0; r < rank; ++r) {
       double nx[4];
 #pragma unroll
       for (int s = 0; s < 4; ++s) nx[s] = sm.xE[r][s];
-      mv4_acc(K.prop_slice, c, nx);
+      mv4_acc(sm.f.prop_slice, c, nx);
 #pragma unroll
       for (int s = 0; s < 4; ++s) c[s] = nx[s];
     }
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {                         // whole warps: M^(32 * 2^d)
+    for (int d = 0; d < 5; ++d) {
       if ((warp >> d) & 1) {
-        double nx[4] = {0.0, 0.0, 0.0, 0.0};
-        mv4_acc(K.mp[5 + d], c, nx);
+        double nx[4];
+        mv4_set(sm.f.mp[5 + d], c, nx);
 #pragma unroll
         for (int s = 0; s < 4; ++s) c[s] = nx[s];
       }
     }
-    mv4_acc(sm.mtab[lane], c, z);
+    mv4_lane_acc(sm.f.mtab, lane, c, z);
   }
-  // pass 2: transposed direct form II; statistics of the valid outputs ride along
+  stamp();                                                // 6: cluster carry applied
+  // pass 2; statistics of the valid outputs ride along
   double lsum = 0.0;
   float lmin = INFINITY, lmax = -INFINITY;
   {
-    const double b00 = K.c[0][0], b01 = K.c[0][1], b02 = K.c[0][2], a01 = K.c[0][3], a02 = K.c[0][4];
-    const double b10 = K.c[1][0], b11 = K.c[1][1], b12 = K.c[1][2], a11 = K.c[1][3], a12 = K.c[1][4];
+    FzCoef kc;
+    kc.b00 = sm.f.c[0][0]; kc.b01 = sm.f.c[0][1]; kc.b02 = sm.f.c[0][2]; kc.a01 = sm.f.c[0][3]; kc.a02 = sm.f.c[0][4];
+    kc.b10 = sm.f.c[1][0]; kc.b11 = sm.f.c[1][1]; kc.b12 = sm.f.c[1][2]; kc.a11 = sm.f.c[1][3]; kc.a12 = sm.f.c[1][4];
     const bool fix_nan = (P.norm_flags & MPCG_NORM_NAN_TO_NUM) != 0;
-    const int valid = n - tid * L;                        // samples of my chunk that belong to the row
+    int lim = n - tid * L;
+    lim = lim < 0 ? 0 : (lim > L ? L : lim);
+    float sacc = 0.f;
 #pragma unroll 4
-    for (int j = 0; j < L; ++j) {
-      const double xv = (double)mine[j];
-      const double y0 = fma(b00, xv, z[0]);
-      z[0] = fma(-a01, y0, fma(b01, xv, z[1]));
-      z[1] = fma(-a02, y0, b02 * xv);
-      const double y1 = fma(b10, y0, z[2]);
-      z[2] = fma(-a11, y1, fma(b11, y0, z[3]));
-      z[3] = fma(-a12, y1, b12 * y0);
-      float v = (float)y1;
-      if (fix_nan) {
-        if (v != v) v = 0.f;
-        else if (v == INFINITY) v = FLT_MAX;
-        else if (v == -INFINITY) v = -FLT_MAX;
-      }
+    for (int j = 0; j < lim; ++j) {
+      const float v = fz_round(fz_step(kc, z, (double)mine[j]), fix_nan);
       mine[j] = v;
-      if (j < valid) {
-        lsum += (double)v;
-        lmin = fminf(lmin, v);
-        lmax = fmaxf(lmax, v);
-      }
+      sacc += v;
+      lmin = fminf(lmin, v);
+      lmax = fmaxf(lmax, v);
+      if ((j & 7) == 7) { lsum += (double)sacc; sacc = 0.f; }
     }
+    lsum += (double)sacc;
   }
 
+  stamp();                                                // 7: pass 2 done
   // ---------------------------------------------------------------- 4. row statistics across the cluster
-  lsum = block_sum<kFzThreads>(lsum, sm.dscr);
-  lmin = block_min<kFzThreads>(lmin, sm.fscr);
-  lmax = block_max<kFzThreads>(lmax, sm.fscr);
+  lsum = warp_sum(lsum);
+  lmin = warp_min(lmin);
+  lmax = warp_max(lmax);
+  if (lane == 0) { sm.wstat[warp][0] = lsum; sm.wstat[warp][1] = (double)lmin; sm.wstat[warp][2] = (double)lmax; }
+  __syncthreads();
   if (tid < P.ncl) {
+    double a = 0.0, b = INFINITY, c = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kFzWarps; ++w) { a += sm.wstat[w][0]; b = fmin(b, sm.wstat[w][1]); c = fmax(c, sm.wstat[w][2]); }
     double* dst = cluster.map_shared_rank(&sm.xstat[rank][0], tid);
-    dst[0] = lsum; dst[1] = (double)lmin; dst[2] = (double)lmax;
+    dst[0] = a; dst[1] = b; dst[2] = c;
   }
   cluster_arrive();
   cluster_wait();
@@ -337,7 +414,10 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   double inv_peak;
   if (P.norm_flags & MPCG_NORM_PEAK_GT0) inv_peak = (peak > 0.0) ? 1.0 / peak : 1.0;
   else inv_peak = 1.0 / fmax(peak, 1e-12);
+  // fp32 map: the mean is split hi + lo so (s - hi) - lo carries no cancellation error
+  const float mean_hi = (float)mean, mean_lo = (float)(mean - (double)mean_hi), inv_f = (float)inv_peak;
 
+  stamp();                                                // 8: statistics exchanged
   // ---------------------------------------------------------------- 5. normalise + write my share of every window
   float* obase = P.out + rec * P.so_b + ch * P.so_c;
   const int s1 = s0 + n;
@@ -349,13 +429,13 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     float* dst = obase + k * P.so_k;
     if (P.so_j == 1) {
       for (int i = a + tid; i < b; i += kFzThreads) {
-        const double u = ((double)sig[i - s0] - mean) * inv_peak;
-        st_stream(dst + (i - w0), (float)fmin(fmax(u, -1.0), 1.0));
+        const float u = ((sig[i - s0] - mean_hi) - mean_lo) * inv_f;
+        st_stream(dst + (i - w0), fminf(fmaxf(u, -1.f), 1.f));
       }
     } else {
       for (int i = a + tid; i < b; i += kFzThreads) {
-        const double u = ((double)sig[i - s0] - mean) * inv_peak;
-        dst[(long long)(i - w0) * P.so_j] = (float)fmin(fmax(u, -1.0), 1.0);
+        const float u = ((sig[i - s0] - mean_hi) - mean_lo) * inv_f;
+        dst[(long long)(i - w0) * P.so_j] = fminf(fmaxf(u, -1.f), 1.f);
       }
     }
     if (rank == P.ncl - 1 && w1 > P.t) {                  // short recording: zero-fill past its end
@@ -363,10 +443,10 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
       for (int i = z0 + tid; i < w1; i += kFzThreads) dst[(long long)(i - w0) * P.so_j] = 0.f;
     }
   }
-  cluster_arrive();                                       // peers may still be reading my shared memory
-  cluster_wait();
+  stamp();                                                // 9: windows stored (issued)
+  // No trailing cluster barrier: every remote shared-memory access of this kernel happens before the
+  // statistics barrier above, so a CTA may retire while its peers are still storing their windows.
 }
-
 
 template <int UP, int DOWN, int D, int FR, int PS>
 int fz_launch(const FzParams& P, size_t smem, long long rows, cudaStream_t stream) {

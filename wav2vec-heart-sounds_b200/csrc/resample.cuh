@@ -33,17 +33,47 @@ struct RsTile {
     }
   }
 
+  // PB outputs are accumulated side by side so four independent FFMA chains are always in flight.
+  static constexpr int PB = 4;
   template <int P0, int P1, class Sink>
   __device__ static __forceinline__ void phases(const float (&in)[PER_THREAD_IN], int frame0, Sink& sink) {
 #pragma unroll
     for (int fr = 0; fr < FR; ++fr) {
 #pragma unroll
-      for (int p = P0; p < P1; ++p) {
-        float acc = 0.f;
+      for (int p = P0; p < P1; p += PB) {
+        float acc[PB];
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc = fmaf(in[fr * DOWN + d], Taps::tap(p, d), acc);
-        sink(frame0 + fr, p, acc);
+        for (int k = 0; k < PB; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+          for (int k = 0; k < PB; ++k)
+            if (p + k < P1) acc[k] = fmaf(in[fr * DOWN + d], Taps::tap(p + k < UP ? p + k : 0, d), acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < PB; ++k)
+          if (p + k < P1) sink(frame0 + fr, p + k, acc[k]);
       }
+    }
+  }
+
+  // Register-prefetched staging: issue the global loads for a tile early (fetch), park them in registers
+  // while the previous tile is being computed, then drop them into shared memory (commit).
+  static constexpr int NPRE = (NIN + THREADS - 1) / THREADS;
+  __device__ static __forceinline__ void fetch(float (&pre)[NPRE], const float* __restrict__ x_row, long long in0,
+                                               long long t_in) {
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int m = threadIdx.x + k * THREADS;
+      const long long src = in0 + m;
+      pre[k] = (m < NIN && src >= 0 && src < t_in) ? ld_stream(x_row + src) : 0.f;
+    }
+  }
+  __device__ static __forceinline__ void commit(float* xs, const float (&pre)[NPRE]) {
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int m = threadIdx.x + k * THREADS;
+      if (m < NIN) xs[rs_skew(m, SIN)] = pre[k];
     }
   }
 
