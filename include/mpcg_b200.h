@@ -50,6 +50,11 @@ const char* mpcg_error_string(int code);
 int mpcg_biquad_cascade_f32(const float* x, float* y, int64_t rows, int64_t t, const double* sos, int n_sections,
                             void* stream);
 
+/* Same, but rows whose row_mask[r] == 0 are skipped (their y is not written); row_mask: device [rows] or NULL.
+ * Used by the EQ stage of augment_pcg_batch, where only the Bernoulli-selected rows need the coloured signal. */
+int mpcg_biquad_cascade_masked_f32(const float* x, float* y, int64_t rows, int64_t t, const double* sos,
+                                   int n_sections, const float* row_mask, void* stream);
+
 /* Rational polyphase resampler in dense frame form:
  *   y[i*up + p] = sum_{d<taps_per_phase} x[i*down + offset + d] * taps[p*taps_per_phase + d],  x = 0 outside [0, t_in)
  * for 0 <= i*up + p < t_out.  The host shim builds `taps` for either oracle:
@@ -120,6 +125,48 @@ typedef struct mpcg_chain_desc {
 int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t recordings, int channels,
                                 const mpcg_chain_desc* desc, int32_t* edits, int32_t* trace, int trace_cap,
                                 void* stream);
+
+/* ---- augmentation (augment/torchaug.py) ----------------------------------------------------------
+ * Random draws are made by the caller (the Python mirror draws them with torch in the reference's call
+ * order) and handed in; `noise == NULL` selects an in-kernel counter-based Philox stream instead. */
+#define MPCG_AUG_IDENTITY 0 /* plain _normalise (torchaug.py:24-27)                                          */
+#define MPCG_AUG_NOISE 1    /* x + rowp[0] * z,  rowp[0] = scale*std (add_white_noise, torchaug.py:39-42)     */
+#define MPCG_AUG_SINE_MUL 2 /* x * (1 + sum_k a_k sin(2 pi (f_k i/fs + p_k)))  (sinusoidal_envelope, :45-54)  */
+#define MPCG_AUG_SINE_ADD 3 /* x + sum_k a_k sin(...)                          (baseline_wander, :57-66)      */
+#define MPCG_AUG_SELECT 4   /* take the sample from `noise` (a second tensor): the blend of _apply (:34-36)   */
+
+/* One stage: w = transform(x) on rows whose mask is non-zero (mask NULL: every row), w = x elsewhere; then
+ * y = w, or with normalise != 0  y = _normalise(w)  -- i.e. torchaug._apply (torchaug.py:34-36) with the
+ * Bernoulli mask given.  rowp: device [rows, 8] floats = (a0, f0, p0, a1, f1, p1, -, -) for the sine ops,
+ * (scale*std, ...) for noise.  noise: device [rows, t] standard normals or NULL (Philox keyed by seed/stream_id). */
+int mpcg_aug_stage_f32(const float* x, float* y, int64_t rows, int64_t t, int op, float fs, const float* rowp,
+                       const float* noise, const float* mask, int normalise, uint64_t seed, uint64_t stream_id,
+                       void* stream);
+
+/* amplitude_warp (torchaug.py:69-85): y[r, i] = sum_k curves[r, k] * xpad[r, i + k], xpad = reflect pad ntaps/2.
+ * curves: device [rows, ntaps] (ntaps odd, <= 257), built by the caller from the control gains. */
+int mpcg_aug_warp_f32(const float* x, float* y, int64_t rows, int64_t t, const float* curves, int ntaps,
+                      void* stream);
+
+/* Tail of parametric_eq (torchaug.py:100) after the five band-pass sections produced `coloured`
+ * (mpcg_biquad_cascade_f32):  e = N(N(coloured)/50 + N(x)).  mix_only != 0: y = e.  Otherwise the stage of
+ * augment_pcg_batch (torchaug.py:109): y = N(mask ? e : x). */
+int mpcg_aug_eq_mix_f32(const float* x, const float* coloured, float* y, int64_t rows, int64_t t, const float* mask,
+                        int mix_only, void* stream);
+
+/* ---- mel conditioning (signalproc/spectrogram.py:13-45) -------------------------------------------
+ * x [rows, t] -> out [rows, n_mels, frames], frames = 1 + t / hop (centred, reflect-padded frames).
+ * basis: device [n_hi - n_lo][2][kpad], fp64 (basis_f64 != 0: exact path, fp64 accumulation) or fp32 (fast path)
+ * = w[n] cos(2 pi k n / n_fft) / sqrt(sum w^2)  |  -w[n] sin(...) / ...  for
+ * the nbins DFT bins k0 .. k0+nbins-1 that carry mel weight (zero-padded to kpad, a multiple of 32) and the
+ * window's non-zero span [n_lo, n_hi); fb: device [nbins][n_mels] HTK triangles of those bins.  Both are built
+ * once per MelConfig by the host mirror.  log_map != 0 fuses log_mel's dB map (spectrogram.py:44-45). */
+int mpcg_mel_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int n_lo, int n_hi, int nbins,
+                 int kpad, const void* basis, int basis_f64, const float* fb, int n_mels, int64_t frames, int log_map,
+                 void* stream);
+
+/* y = clamp((20 log10(max(x, 1e-5)) - 20 + 100) / 100, 0, 1) elementwise (log_mel on a foreign transform's output). */
+int mpcg_logmap_f32(const float* x, float* y, int64_t n, void* stream);
 
 /* Profiling aid (tools/ only): device buffer [ctas, 16] of int64 that the fused kernel fills with clock64 stamps at
  * its phase boundaries; NULL switches it off.  Not part of the data path. */

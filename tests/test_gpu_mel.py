@@ -1,0 +1,95 @@
+"""Mel conditioning parity: against the reference's own outputs (tests/golden/mel_presets.npz, produced by running
+MelConfig.build() / log_mel of the reference) and the oracle in float64.  Tolerance 1e-5 absolute on the [0, 1]
+log-mel scale and 1e-5 of the largest value on the linear mel."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_path as otp
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+PRESETS = {"dw4k": dict(sample_rate=4000, n_fft=1024, hop_length=256, n_mels=80, f_max=500.0),
+           "c4_16k": dict(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500.0),
+           "wg4k": dict(sample_rate=4000, n_fft=2048, win_length=1200, hop_length=300, n_mels=128, f_max=500.0)}
+
+
+@pytest.fixture(scope="module")
+def pkg(built_lib):
+    import wav2vec_heart_sounds_b200 as m
+    return m
+
+
+@pytest.mark.parametrize("tag", list(PRESETS))
+def test_presets_vs_reference_outputs(pkg, golden, tag):
+    g = golden("mel_presets.npz")
+    x = torch.from_numpy(g["x"]).cuda()
+    tr = pkg.MelConfig(**PRESETS[tag]).build()
+    mel = tr(x).cpu().numpy()
+    assert mel.shape == g[f"{tag}_mel"].shape
+    assert rel_err(mel, g[f"{tag}_mel"]) < 1e-5
+    lm = pkg.log_mel(x, tr).cpu().numpy()
+    assert lm.min() >= 0.0 and lm.max() <= 1.0
+    assert np.abs(lm - g[f"{tag}_logmel64"]).max() < 1e-5          # reference run in float64
+    assert np.abs(lm - g[f"{tag}_logmel"]).max() < 2e-5            # and its float32 run
+
+
+def test_frame_count_and_shapes(pkg):
+    """Reference tests/test_generative.py:52, test_heart_cycles.py:51-52: crop_frames*hop samples give
+    crop_frames + 1 frames before the dataset crops."""
+    tr = pkg.MelConfig(sample_rate=4000, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build()
+    x = torch.randn(3, 96 * 256, device="cuda")
+    assert tr(x).shape == (3, 80, 97)
+    assert tr(x[0]).shape == (80, 97)
+    assert tr(x.reshape(3, 1, -1)).shape == (3, 1, 80, 97)
+    lm = pkg.log_mel(x[0], tr)
+    assert lm.shape == (80, 97) and float(lm.min()) >= 0 and float(lm.max()) <= 1
+    with pytest.raises(ValueError):
+        tr(torch.randn(2, 400, device="cuda"))                      # shorter than the reflect pad: torch raises too
+
+
+def test_vs_oracle_on_noise_and_tones(pkg):
+    rng = np.random.default_rng(3)
+    t = np.arange(24576) / 4000.0
+    x = np.stack([rng.standard_normal(24576), np.sin(2 * np.pi * 100 * t), 0.01 * np.sin(2 * np.pi * 37.5 * t),
+                  np.zeros(24576)]).astype(np.float32)
+    kw = PRESETS["dw4k"]
+    tr = pkg.MelConfig(**kw).build()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = otp.mel_transform(**kw).double()
+    want = otp.log_mel(torch.from_numpy(x).double(), ref).numpy()
+    got = pkg.log_mel(torch.from_numpy(x).cuda(), tr).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-5
+    assert got[3].max() == 0.0                                      # silence clamps to 0
+    fast = pkg.log_mel(torch.from_numpy(x).cuda(), pkg.MelConfig(**kw).build(fast=True)).cpu().numpy()
+    assert np.abs(fast[0] - want[0]).max() < 1e-5                  # broadband input: float32 DFT is enough
+    assert np.abs(fast - want).max() < 5e-3                        # tones: only the skirts near the clamp differ
+
+
+def test_log_mel_with_foreign_transform(pkg):
+    import torchaudio
+    kw = PRESETS["dw4k"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ta_tr = otp.mel_transform(**kw).cuda()
+    x = torch.randn(2, 8192, device="cuda")
+    a = pkg.log_mel(x, ta_tr)
+    b = otp.log_mel(x, ta_tr)
+    assert float((a - b).abs().max()) < 1e-6
+
+
+def test_config4_size_properties(pkg):
+    """8192 windows of 64 000 samples at 16 kHz (BASELINE config 4): shape, range, and time-shift covariance:
+    shifting the signal by k hops shifts the interior frames by k."""
+    tr = pkg.MelConfig(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build()
+    x = torch.randn(8192, 64000, device="cuda")
+    m = pkg.log_mel(x, tr)
+    assert m.shape == (8192, 80, 251) and float(m.min()) >= 0 and float(m.max()) <= 1
+    empty = (tr._fb_host.abs().sum(dim=0) == 0)                     # at 16 kHz 18 of the 80 filters have no bin
+    assert int(empty.sum()) == 18 and float(m[:, empty.cuda()].abs().max()) == 0.0
+    y = torch.roll(x[:64], shifts=3 * 256, dims=1)
+    my = pkg.log_mel(y, tr)
+    assert torch.equal(my[:, :, 8:240], m[:64, :, 5:237])

@@ -1,0 +1,138 @@
+"""Parity of the augmentation kernels with the reference's torchaug (golden vectors produced by running the
+reference with a replayed RNG, tests/golden/torchaug_replay.npz) and with the oracle in float64.
+Tolerance 1e-5 of the output scale (outputs are normalised to [-1, 1])."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_path as otp
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ta(built_lib):
+    from wav2vec_heart_sounds_b200 import torchaug
+    return torchaug
+
+
+def _dev(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+
+
+def test_normalise_matches_reference(ta, golden):
+    g = golden("torchaug_replay.npz")
+    x = torch.from_numpy(g["x"]) * 3.0 + 0.7
+    got = ta._normalise(x.cuda()).cpu().numpy()
+    assert rel_err(got, otp.renormalise(x.double()).numpy()) < TOL
+
+
+def test_noise_sine_wander_warp_vs_reference_outputs(ta, golden):
+    g = golden("torchaug_replay.npz")
+    x = _dev(g["x"])
+    fs = int(g["fs"])
+    got = ta.add_white_noise(x, std=float(g["noise_std"]), scale=g["noise_scale"], noise=_dev(g["noise_noise"]))
+    assert rel_err(got.cpu().numpy(), g["noise_out"]) < TOL
+    got = ta.sinusoidal_envelope(x, fs, amp=g["sine_amp"], freq=g["sine_freq"], phase=g["sine_phase"])
+    assert rel_err(got.cpu().numpy(), g["sine_out"]) < TOL
+    got = ta.baseline_wander(x, fs, amp=g["wander_amp"], freq=g["wander_freq"], phase=g["wander_phase"])
+    assert rel_err(got.cpu().numpy(), g["wander_out"]) < TOL
+    got = ta.amplitude_warp(x, amps=g["warp_amps"])
+    assert rel_err(got.cpu().numpy(), g["warp_out"]) < TOL
+
+
+def test_parametric_eq_vs_float64_reference(ta, golden):
+    g = golden("torchaug_replay.npz")
+    x = _dev(g["x"])
+    bands = [tuple(b) for b in g["eq_bands"]]
+    got = ta.parametric_eq(x, int(g["fs"]), 2, 500, bands=bands).cpu().numpy()
+    assert rel_err(got, g["eq_out64"]) < TOL                 # the reference run in float64 is the target
+    assert rel_err(got, g["eq_out"]) < 5e-3                  # its own float32 run is only this close to it
+
+
+def test_whole_chain_vs_reference_and_oracle(ta, golden):
+    g = golden("torchaug_replay.npz")
+    from wav2vec_heart_sounds_b200 import AugmentConfig
+    x = torch.from_numpy(g["x"])
+    draws = {}
+    for k in g.files:
+        if k.startswith("chain_") and k != "chain_out":
+            v = g[k]
+            key = k[len("chain_"):]
+            draws[key] = float(v) if key.startswith("std") else ([tuple(b) for b in v] if key == "bands" else v)
+    cfg = AugmentConfig(prob_noise=2.0, prob_wandering_volume=0.75, prob_banding=0.6)
+    dev_draws = {k: (_dev(v) if isinstance(v, np.ndarray) and v.dtype != object and k not in ("bands",) else v)
+                 for k, v in draws.items()}
+    got = ta.augment_pcg_batch(x.cuda(), int(g["fs"]), cfg, draws=dev_draws).cpu().numpy()
+    assert got.shape == x.shape and np.isfinite(got).all() and np.abs(got).max() <= 1.0 + 1e-6
+    odraws = {k: (torch.from_numpy(np.asarray(v)) if isinstance(v, np.ndarray) else v) for k, v in draws.items()}
+    want64 = otp.augment_pcg_batch(x.double(), int(g["fs"]), odraws).numpy()
+    assert rel_err(got, want64) < TOL
+    assert rel_err(got, g["chain_out"]) < 5e-3               # the reference's float32 EQ is the noisy party
+    masks = [draws[f"mask{i}"].reshape(-1) for i in (1, 2, 3, 4)]
+    assert any(m.any() for m in masks) and not all(m.all() for m in masks)   # both branches exercised
+
+
+def test_apply_blend_and_masks(ta):
+    x = torch.randn(6, 3001, device="cuda")
+    tr = torch.randn(6, 3001, device="cuda")
+    m = torch.tensor([1, 0, 1, 1, 0, 0.0]).reshape(6, 1)
+    got = ta._apply(x, tr, 0.5, mask=m).cpu()
+    want = otp.blend(x.cpu().double(), tr.cpu().double(), m.double())
+    assert rel_err(got.numpy(), want.numpy()) < TOL
+
+
+def test_reference_property_test_default_rng(ta):
+    """The reference's own test (tests/test_torchaug.py:9-15) with the default random draws."""
+    from wav2vec_heart_sounds_b200 import AugmentConfig, augment_pcg_batch
+    x = torch.randn(8, 4125, device="cuda")
+    torch.manual_seed(0); np.random.seed(0)
+    out = augment_pcg_batch(x, fs=4125, cfg=AugmentConfig(prob_hpss=0.0, prob_real_noise=0.0))
+    assert out.shape == x.shape and torch.isfinite(out).all() and float(out.abs().max()) <= 1.0 + 1e-5
+    torch.manual_seed(0); np.random.seed(0)
+    again = augment_pcg_batch(x, fs=4125, cfg=AugmentConfig(prob_hpss=0.0, prob_real_noise=0.0))
+    assert torch.equal(out, again)                           # seeded runs repeat
+
+
+def test_default_draw_order_equals_reference_stream(ta):
+    """With the same seeds the default path consumes numpy's and torch's CUDA generators like the reference:
+    replay the reference's call order on the device and inject it -- results must be identical."""
+    x = ta._normalise(torch.randn(5, 2048, device="cuda"))
+    np.random.seed(7); torch.manual_seed(7)
+    a = ta.add_white_noise(x)
+    np.random.seed(7); torch.manual_seed(7)
+    std = float(np.random.choice((0.0001, 0.001, 0.01)))
+    scale = torch.rand(5, 1, device="cuda") * 0.1
+    noise = torch.randn_like(x)
+    assert torch.equal(a, ta.add_white_noise(x, std=std, scale=scale, noise=noise))
+    assert torch.equal(a, x + scale * std * noise)           # and that IS the reference's expression
+
+
+def test_philox_noise_statistics_and_repeatability(ta):
+    x = torch.zeros(64, 64000, device="cuda")
+    torch.manual_seed(3)
+    a = ta.add_white_noise(x, std=0.01, scale=torch.full((64, 1), 0.1), noise="philox")
+    z = (a / (0.1 * 0.01)).double()
+    assert abs(float(z.mean())) < 3e-3 and abs(float(z.std()) - 1.0) < 3e-3
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.05          # Gaussian kurtosis
+    c = torch.corrcoef(torch.stack([z[0], z[1], z[0].roll(1)]))
+    assert float(c[0, 1].abs()) < 0.02 and float(c[0, 2].abs()) < 0.02
+    torch.manual_seed(3)
+    b = ta.add_white_noise(x, std=0.01, scale=torch.full((64, 1), 0.1), noise="philox")
+    assert torch.equal(a, b)
+
+
+def test_edge_shapes(ta):
+    x = torch.randn(3, 1001, device="cuda")                 # odd length: tail group of the 4-sample loop
+    out = ta.sinusoidal_envelope(x, 1000, amp=np.full((3, 2), 0.1), freq=np.full((3, 2), 0.3), phase=np.zeros((3, 2)))
+    want = otp.sinusoidal_envelope(x.cpu(), 1000, torch.full((3, 2), 0.1), torch.full((3, 2), 0.3), torch.zeros(3, 2))
+    assert rel_err(out.cpu().numpy(), want.numpy()) < TOL
+    assert ta._normalise(torch.zeros(0, 16, device="cuda")).shape == (0, 16)
+    with pytest.raises(ValueError):
+        ta._normalise(torch.zeros(16, device="cuda"))
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        ta.add_white_noise(torch.zeros(2, 16))
+    w = ta.amplitude_warp(torch.randn(2, 5000, device="cuda"), amps=np.ones((2, 12)))    # flat gains = 65-tap mean
+    assert w.shape == (2, 5000)

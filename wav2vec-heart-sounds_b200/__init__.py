@@ -6,7 +6,9 @@ name; the importable alias package next to it redirects here).
 """
 from . import design, segment as _segment_mod  # noqa: F401
 from .segment import WINDOWS, WindowSpec, default_window
-from . import torchproc
+from . import torchproc, torchaug
+from .torchaug import AugmentConfig, augment_pcg_batch
 from .pipeline import preprocess_segment
+from .spectrogram import MelConfig, log_mel
 
-__all__ = ["torchproc", "preprocess_segment", "WindowSpec", "WINDOWS", "default_window", "design"]
+__all__ = ["torchproc", "MelConfig", "log_mel", "torchaug", "AugmentConfig", "augment_pcg_batch", "preprocess_segment", "WindowSpec", "WINDOWS", "default_window", "design"]

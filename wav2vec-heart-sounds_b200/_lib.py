@@ -24,6 +24,8 @@ _SIGNATURES = {
     "mpcg_abi_version": (c_int, []),
     "mpcg_error_string": (ctypes.c_char_p, [c_int]),
     "mpcg_biquad_cascade_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_biquad_cascade_masked_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, c_f32p,
+                                               ctypes.c_void_p]),
     "mpcg_resample_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, ctypes.c_void_p, c_int, c_int, c_int, c_i64,
                                   ctypes.c_void_p]),
     "mpcg_despike_f32": (c_int, [c_f32p, c_i64, c_i64, c_i64, ctypes.c_double, c_int, c_int, ctypes.c_void_p,
@@ -35,6 +37,13 @@ _SIGNATURES = {
     "mpcg_preprocess_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p, c_int, ctypes.c_void_p]),
     "mpcg_debug_set_phase_clock_buffer": (None, [ctypes.c_void_p]),
+    "mpcg_mel_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p,
+                             c_int, c_f32p, c_int, c_i64, c_int, ctypes.c_void_p]),
+    "mpcg_logmap_f32": (c_int, [c_f32p, c_f32p, c_i64, ctypes.c_void_p]),
+    "mpcg_aug_stage_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, ctypes.c_float, c_f32p, c_f32p, c_f32p, c_int,
+                                   ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]),
+    "mpcg_aug_warp_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_int, ctypes.c_void_p]),
+    "mpcg_aug_eq_mix_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_int, ctypes.c_void_p]),
 }
 EUNSUPPORTED = -3
 
@@ -55,6 +64,7 @@ class ChainDesc(ctypes.Structure):
 
 MEDIAN_LOWER, MEDIAN_MEAN = 0, 1
 NORM_NAN_TO_NUM, NORM_PEAK_GT0 = 1, 2
+AUG_IDENTITY, AUG_NOISE, AUG_SINE_MUL, AUG_SINE_ADD, AUG_SELECT = 0, 1, 2, 3, 4
 
 
 def build(verbose: bool = False) -> pathlib.Path:

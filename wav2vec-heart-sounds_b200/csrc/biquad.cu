@@ -127,10 +127,11 @@ struct BqSmem {
 
 __global__ void __launch_bounds__(kBqThreads)
 biquad_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long t,
-                   const __grid_constant__ BqPlan plan) {
+                   const float* __restrict__ row_mask, const __grid_constant__ BqPlan plan) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BqSmem& sm = *reinterpret_cast<BqSmem*>(smem_raw);
   const long long row = blockIdx.x;
+  if (row_mask && row_mask[row] == 0.f) return;              // rows not selected are left untouched in y
   const float* xr = x + row * t;
   float* yr = y + row * t;
   bq_init_scratch<kBqThreads>(sm.sc, plan);
@@ -156,8 +157,16 @@ biquad_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long
 
 }  // namespace mpcg
 
+extern "C" int mpcg_biquad_cascade_masked_f32(const float* x, float* y, int64_t rows, int64_t t, const double* sos,
+                                              int n_sections, const float* row_mask, void* stream);
+
 extern "C" int mpcg_biquad_cascade_f32(const float* x, float* y, int64_t rows, int64_t t, const double* sos,
                                        int n_sections, void* stream) {
+  return mpcg_biquad_cascade_masked_f32(x, y, rows, t, sos, n_sections, nullptr, stream);
+}
+
+extern "C" int mpcg_biquad_cascade_masked_f32(const float* x, float* y, int64_t rows, int64_t t, const double* sos,
+                                              int n_sections, const float* row_mask, void* stream) {
   using namespace mpcg;
   if (rows < 0 || t < 0) return MPCG_EINVAL;
   BqPlan plan;
@@ -169,7 +178,7 @@ extern "C" int mpcg_biquad_cascade_f32(const float* x, float* y, int64_t rows, i
   cudaError_t e = cudaFuncSetAttribute(biquad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(BqSmem));
   if (e != cudaSuccess) return (int)e;
-  biquad_rows_kernel<<<(unsigned)rows, kBqThreads, sizeof(BqSmem), (cudaStream_t)stream>>>(x, y, (long long)t, plan);
+  biquad_rows_kernel<<<(unsigned)rows, kBqThreads, sizeof(BqSmem), (cudaStream_t)stream>>>(x, y, (long long)t, row_mask, plan);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }

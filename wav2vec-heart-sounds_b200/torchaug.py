@@ -1,0 +1,220 @@
+"""Drop-in for ``mpcg_wav2vec.augment.torchaug`` on B200 (reference ``augment/torchaug.py:24-111``): same names,
+argument order and ``[B, T]`` layout, every transform a CUDA kernel behind ``libmpcg_b200.so``.
+
+Randomness.  By default each function draws its parameters exactly as the reference does -- same calls, same
+order (``np.random.choice`` for the noise level, ``torch.rand(B, 1, device=...)`` per row, ``torch.randn_like``
+for the noise, ``np.random.uniform`` for the EQ band edges) -- so a seeded run consumes the RNG streams like
+the reference and can be compared with it.  Every function also accepts its draws as keyword arguments
+("injected-parameter mode", what the parity tests use), and ``noise="philox"`` replaces the materialised
+``randn_like`` tensor by an in-kernel counter-based Philox stream (one HBM read and write less per noise stage).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, design
+
+_NOISE_STDS = (0.0001, 0.001, 0.01)
+_SINE_BANDS = ((0.05, 0.5), (0.001, 0.05))
+
+
+@dataclass
+class AugmentConfig:
+    """Mirror of the reference's ``augment/pipelines.py:26-36`` (any object with these attributes works)."""
+    ephnogram_dir: str = ""
+    mit_dir: str = ""
+    prob_hpss: float = 0.75
+    prob_noise: float = 0.30
+    prob_time_warp: float = 0.25
+    prob_wandering_volume: float = 0.75
+    prob_banding: float = 0.25
+    prob_baseline_wander: float = 0.30
+    prob_real_noise: float = 0.5
+
+
+def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    x = _lib.require_cuda_f32(x)
+    if x.dim() != 2:
+        raise ValueError("torchaug functions take a [B, T] batch")
+    return x
+
+
+def _dev_f32(v, device, shape=None) -> torch.Tensor:
+    t = torch.as_tensor(v, dtype=torch.float32, device=device)
+    return t.reshape(shape).contiguous() if shape is not None else t.contiguous()
+
+
+def _stage(x, op, *, fs=1.0, rowp=None, noise=None, mask=None, normalise=False, seed=0, stream_id=0):
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mpcg_aug_stage_f32(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], op, float(fs),
+                                             _lib.ptr(rowp), _lib.ptr(noise), _lib.ptr(mask), 1 if normalise else 0,
+                                             int(seed), int(stream_id), _lib.stream_ptr(x)), "augmentation stage")
+    return out
+
+
+def _normalise(x: torch.Tensor) -> torch.Tensor:
+    """Row-wise zero-mean, peak-normalise, clamp (reference torchaug.py:24-27)."""
+    return _stage(_rows2d(x), _lib.AUG_IDENTITY, normalise=True)
+
+
+def _mask(batch: int, prob: float, device) -> torch.Tensor:
+    return (torch.rand(batch, 1, device=device) < prob).float()
+
+
+def _apply(x: torch.Tensor, transformed: torch.Tensor, prob: float, *, mask=None) -> torch.Tensor:
+    """``_normalise(m * transformed + (1 - m) * x)`` with ``m ~ Bernoulli(prob)`` per row (reference :34-36)."""
+    x = _rows2d(x)
+    m = _mask(x.shape[0], prob, x.device) if mask is None else _dev_f32(mask, x.device, (x.shape[0], 1))
+    return _stage(x, _lib.AUG_SELECT, noise=_rows2d(transformed), mask=m.reshape(-1).contiguous(), normalise=True)
+
+
+# ------------------------------------------------------------------------------------------------ draws
+def _draw_noise(x, std=None, scale=None, noise=None):
+    b = x.shape[0]
+    std = float(np.random.choice(_NOISE_STDS)) if std is None else float(std)
+    scale = torch.rand(b, 1, device=x.device) * 0.1 if scale is None else _dev_f32(scale, x.device, (b, 1))
+    if noise is None:
+        noise = torch.randn_like(x)
+    elif isinstance(noise, str):
+        if noise != "philox":
+            raise ValueError("noise must be a tensor, None or 'philox'")
+        noise = None
+    else:
+        noise = _rows2d(noise)
+    rowp = torch.zeros(b, 8, device=x.device)
+    rowp[:, 0:1] = scale * std                      # fp32 product, as the reference forms it
+    return rowp, noise
+
+
+def _draw_sines(x, span, amp=None, freq=None, phase=None):
+    b, dev = x.shape[0], x.device
+    cols = []
+    for k, (lo, hi) in enumerate(_SINE_BANDS):
+        a = 0.01 + torch.rand(b, 1, device=dev) * span if amp is None else _dev_f32(amp, dev)[:, k:k + 1]
+        f = lo + torch.rand(b, 1, device=dev) * (hi - lo) if freq is None else _dev_f32(freq, dev)[:, k:k + 1]
+        p = torch.rand(b, 1, device=dev) if phase is None else _dev_f32(phase, dev)[:, k:k + 1]
+        cols += [a, f, p]
+    rowp = torch.zeros(b, 8, device=dev)
+    rowp[:, :6] = torch.cat(cols, dim=1)
+    return rowp
+
+
+def _draw_bands(low, high, num_bands, bands=None):
+    if bands is not None:
+        return [tuple(map(float, b)) for b in bands]
+    out = []
+    for _ in range(num_bands):
+        lo = float(np.random.uniform(low, 0.95 * high))
+        hi = float(np.random.uniform(lo + 0.05 * (high - low), high))
+        out.append((lo, hi))
+    return out
+
+
+def _philox_key():
+    """A fresh (seed, stream) pair drawn from torch's CPU generator so torch.manual_seed controls it."""
+    v = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
+    return int(v[0]), int(v[1])
+
+
+# ------------------------------------------------------------------------------------------------ transforms
+def add_white_noise(x: torch.Tensor, *, std=None, scale=None, noise=None) -> torch.Tensor:
+    """``x + scale * std * randn`` (reference torchaug.py:39-42): one ``std`` per call, one ``scale`` per row."""
+    x = _rows2d(x)
+    rowp, nz = _draw_noise(x, std, scale, noise)
+    seed, sid = _philox_key() if nz is None else (0, 0)
+    return _stage(x, _lib.AUG_NOISE, rowp=rowp, noise=nz, seed=seed, stream_id=sid)
+
+
+def sinusoidal_envelope(x: torch.Tensor, fs: int, *, amp=None, freq=None, phase=None) -> torch.Tensor:
+    """``x * (1 + fast + slow)`` sinusoidal volume modulation (reference torchaug.py:45-54)."""
+    x = _rows2d(x)
+    return _stage(x, _lib.AUG_SINE_MUL, fs=fs, rowp=_draw_sines(x, 0.24, amp, freq, phase))
+
+
+def baseline_wander(x: torch.Tensor, fs: int, *, amp=None, freq=None, phase=None) -> torch.Tensor:
+    """``x + fast + slow`` sinusoidal drift (reference torchaug.py:57-66)."""
+    x = _rows2d(x)
+    return _stage(x, _lib.AUG_SINE_ADD, fs=fs, rowp=_draw_sines(x, 0.19, amp, freq, phase))
+
+
+def _warp_curves(amps: torch.Tensor, kernel: int) -> torch.Tensor:
+    """[B, P] control gains -> [B, kernel] unit-sum taps by linear interpolation (reference :75-81, on the host
+    exactly as the reference does it)."""
+    p = amps.shape[1]
+    grid = torch.arange(kernel).float()
+    idx = torch.clamp(grid / (kernel - 1) * (p - 1), max=p - 1)
+    lo, hi = idx.floor().long(), idx.ceil().long()
+    curve = amps[:, lo] + (amps[:, hi] - amps[:, lo]) * (idx - lo).unsqueeze(0)
+    return curve / curve.sum(dim=-1, keepdim=True)
+
+
+def amplitude_warp(x: torch.Tensor, num_points: int = 12, kernel: int = 65, *, amps=None) -> torch.Tensor:
+    """Per-row smooth gain curve applied as a depthwise FIR over the reflect-padded row (reference :69-85)."""
+    x = _rows2d(x)
+    b, t = x.shape
+    amps = 0.7 + torch.rand(b, num_points) * 0.6 if amps is None else torch.as_tensor(amps, dtype=torch.float32).cpu()
+    curves = _warp_curves(amps, kernel).to(x.device).contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mpcg_aug_warp_f32(x.data_ptr(), out.data_ptr(), b, t, curves.data_ptr(), kernel,
+                                            _lib.stream_ptr(x)), "amplitude warp")
+    return out
+
+
+def _coloured(x: torch.Tensor, fs: float, bands, mask=None) -> torch.Tensor:
+    """The five cascaded band-pass sections; with a row mask only the selected rows are computed (the others are
+    never read by the mix kernel)."""
+    sos = np.ascontiguousarray(design.eq_band_sos(fs, bands), dtype=np.float64)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mpcg_biquad_cascade_masked_f32(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                                                         sos.ctypes.data, sos.shape[0], _lib.ptr(mask),
+                                                         _lib.stream_ptr(x)), "EQ cascade")
+    return out
+
+
+def _eq_mix(x, coloured, mask, mix_only):
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mpcg_aug_eq_mix_f32(x.data_ptr(), coloured.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1],
+                                              _lib.ptr(mask), 1 if mix_only else 0, _lib.stream_ptr(x)), "EQ mix")
+    return out
+
+
+def parametric_eq(x: torch.Tensor, fs: float, low: float, high: float, num_bands: int = 5, *, bands=None) -> torch.Tensor:
+    """Blend with a stack of random first-order band-pass sections, bands shared by the batch (reference :88-100)."""
+    x = _rows2d(x)
+    bands = _draw_bands(low, high, num_bands, bands)
+    if len(bands) > 6:
+        raise ValueError("at most 6 EQ bands per call")
+    return _eq_mix(x, _coloured(x, fs, bands), None, True)
+
+
+def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None, *, draws: dict | None = None,
+                      noise: str | None = None) -> torch.Tensor:
+    """Noise -> wandering volume -> EQ -> noise, each behind a per-row Bernoulli mask, every row re-normalised
+    after every stage (reference torchaug.py:103-111).  Each stage is one fused kernel (transform + blend +
+    normalise).  ``draws`` injects every random quantity (keys as in ``oracle.torch_path.augment_pcg_batch``)."""
+    cfg = cfg or AugmentConfig()
+    x = _normalise(_rows2d(x))
+    b, dev = x.shape[0], x.device
+    d = draws or {}
+
+    def mask_of(key, prob):
+        m = d.get(key)
+        return _mask(b, prob, dev).reshape(b) if m is None else _dev_f32(m, dev, (b,))
+
+    def noise_stage(x, i, mask_key):
+        rowp, nz = _draw_noise(x, d.get(f"std{i}"), d.get(f"scale{i}"), d.get(f"noise{i}", noise))
+        seed, sid = _philox_key() if nz is None else (0, 0)
+        return _stage(x, _lib.AUG_NOISE, rowp=rowp, noise=nz, mask=mask_of(mask_key, cfg.prob_noise / 4),
+                      normalise=True, seed=seed, stream_id=sid)
+
+    x = noise_stage(x, 1, "mask1")
+    rowp = _draw_sines(x, 0.24, d.get("amp"), d.get("freq"), d.get("phase"))
+    x = _stage(x, _lib.AUG_SINE_MUL, fs=fs, rowp=rowp, mask=mask_of("mask2", cfg.prob_wandering_volume), normalise=True)
+    bands = _draw_bands(2, 500, 5, d.get("bands"))
+    m3 = mask_of("mask3", cfg.prob_banding)
+    x = _eq_mix(x, _coloured(x, fs, bands, m3), m3, False)
+    x = noise_stage(x, 2, "mask4")
+    return x
