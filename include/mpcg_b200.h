@@ -168,6 +168,29 @@ int mpcg_mel_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft,
 /* y = clamp((20 log10(max(x, 1e-5)) - 20 + 100) / 100, 0, 1) elementwise (log_mel on a foreign transform's output). */
 int mpcg_logmap_f32(const float* x, float* y, int64_t n, void* stream);
 
+/* ---- HPSS augmentation (augment/primitives.py:88-123; librosa stft / decompose.hpss / softmask / istft) -------
+ * Spectra are frame-major complex64: spec[row][frame][bin], bins = n_fft/2 + 1, frames = 1 + t/hop.
+ * window: device [n_fft] periodic Hann; twiddle: device [n_fft/2] complex64 exp(-2 pi i k / n_fft). n_fft = 2^m. */
+int mpcg_hpss_stft_f32(const float* x, float* spec, int64_t rows, int64_t t, int n_fft, int hop, int64_t frames,
+                       const float* window, const float* twiddle, void* stream);
+/* out[row][frame][bin] = median of |spec| over k neighbours along time (along_time != 0: librosa's harmonic
+ * filter, size (1, k)) or along frequency (percussive, size (k, 1)); scipy.ndimage 'reflect' boundary, rank k/2. */
+int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows, int64_t frames, int bins, int k, int along_time,
+                         void* stream);
+/* Soft masks (power 2, margins as in decompose.hpss) -> harmonic / percussive / residual spectra -> inverse FFT ->
+ * windowed overlap-add into acc[row][3][n_fft + hop*(frames-1)] (zeroed here). */
+int mpcg_hpss_istft_f32(const float* spec, const float* harm, const float* perc, float* acc, int64_t rows, int n_fft,
+                        int hop, int64_t frames, float margin_h, float margin_p, const float* window,
+                        const float* twiddle, void* stream);
+/* y[line][i] = acc[line][i + n_fft/2] / wsum[i + n_fft/2] (where wsum > tiny), i < hop*(frames-1): istft's
+ * normalisation and centre trim.  wsum: device [n_fft + hop*(frames-1)] window sum-of-squares. */
+int mpcg_hpss_finish_f32(const float* acc, const float* wsum, float* y, int64_t lines, int n_fft, int hop,
+                         int64_t frames, void* stream);
+/* hpss_recombine's tail (primitives.py:117-123): out = N(N(sum w1_p part_p) + wmix * N(sum w2_p N(part_p))), N =
+ * NumPy abs_max_normalise.  parts: device [nparts][rows][n]; w1, w2: HOST [nparts]. */
+int mpcg_hpss_mix_f32(const float* parts, float* out, int64_t rows, int64_t n, int nparts, const float* w1,
+                      const float* w2, float wmix, void* stream);
+
 /* Profiling aid (tools/ only): device buffer [ctas, 16] of int64 that the fused kernel fills with clock64 stamps at
  * its phase boundaries; NULL switches it off.  Not part of the data path. */
 void mpcg_debug_set_phase_clock_buffer(void* dev_ptr);

@@ -1,0 +1,349 @@
+// extern "C" entries of the HPSS augmentation (augment/primitives.py:88-123, whose arithmetic is librosa 0.11's
+// stft / decompose.hpss / softmask / istft and scipy.ndimage.median_filter underneath):
+//   mpcg_hpss_stft_f32        frames -> one-sided complex spectrum (periodic Hann, centred, zero padded)
+//   mpcg_hpss_median_f32      running median of |S| along time (harmonic) or along frequency (percussive)
+//   mpcg_hpss_istft_f32       soft masks -> H / P / R spectra -> inverse FFT -> windowed overlap-add
+//   mpcg_hpss_finish_f32      divide by the window sum-of-squares, trim n_fft/2 on both sides
+//   mpcg_hpss_mix_f32         the random re-weighting tail of hpss_recombine (two mixes, three normalisations)
+//
+// Layout: spectra are frame-major, S[row][frame][bin] (bin contiguous), so FFT output and the frequency median are
+// unit-stride and the time median is coalesced across bins.  FFTs are radix-2 in shared memory, one frame per
+// CTA; medians keep a sorted window per thread in shared memory and slide it (remove oldest, insert newest),
+// O(k) per output instead of a fresh selection.  Median results are bit-exact functions of the magnitudes:
+// window [i - k/2, i - k/2 + k - 1], half-sample-symmetric reflection, rank k/2 (upper median for even k).
+#include "common.cuh"
+
+namespace mpcg {
+
+constexpr int kFftThreads = 256;
+
+__device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
+
+// In-place radix-2 decimation-in-time FFT over a[0..n) (input already bit-reversed).  tw[k] = exp(-2 pi i k / n).
+__device__ __forceinline__ void fft_shared(float2* a, int n, int log2n, bool inverse, const float2* __restrict__ tw) {
+  for (int s = 1; s <= log2n; ++s) {
+    const int half = 1 << (s - 1);
+    const int tstep = n >> s;
+    for (int j = threadIdx.x; j < (n >> 1); j += kFftThreads) {
+      const int k = j & (half - 1);
+      const int i0 = ((j >> (s - 1)) << s) + k;
+      const int i1 = i0 + half;
+      float2 w = __ldg(tw + k * tstep);
+      if (inverse) w.y = -w.y;
+      const float2 b = a[i1], u = a[i0];
+      const float2 t = make_float2(w.x * b.x - w.y * b.y, w.x * b.y + w.y * b.x);
+      a[i0] = make_float2(u.x + t.x, u.y + t.y);
+      a[i1] = make_float2(u.x - t.x, u.y - t.y);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- STFT
+__global__ void __launch_bounds__(kFftThreads)
+hpss_stft_kernel(const float* __restrict__ x, float2* __restrict__ spec, long long t, int n_fft, int log2n, int hop,
+                 int frames, const float* __restrict__ window, const float2* __restrict__ tw) {
+  extern __shared__ float2 fft_buf[];
+  const int frame = blockIdx.x;
+  const long long row = blockIdx.y;
+  const float* xr = x + row * t;
+  const long long base = (long long)frame * hop - n_fft / 2;
+  for (int i = threadIdx.x; i < n_fft; i += kFftThreads) {
+    const long long j = base + i;
+    const float v = (j >= 0 && j < t) ? xr[j] * __ldg(window + i) : 0.f;
+    fft_buf[bitrev((unsigned)i, log2n)] = make_float2(v, 0.f);
+  }
+  __syncthreads();
+  fft_shared(fft_buf, n_fft, log2n, false, tw);
+  const int bins = n_fft / 2 + 1;
+  float2* out = spec + ((long long)row * frames + frame) * bins;
+  for (int k = threadIdx.x; k < bins; k += kFftThreads) out[k] = fft_buf[k];
+}
+
+// ---------------------------------------------------------------------------------------------- medians
+constexpr int kMedThreads = 128;
+constexpr int kMedMaxK = 64;
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {       // d c b a | a b c d | d c b a
+  if (n == 1) return 0;
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+// Each thread owns one line (a bin for the time median, a frame for the frequency median) and walks along it.
+// sorted[kk][thread] (shared, column per thread) holds the current window in ascending order.
+__global__ void __launch_bounds__(kMedThreads)
+hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time) {
+  extern __shared__ float med_sorted[];                          // [k][kMedThreads]
+  const long long row = blockIdx.y;
+  const int line = blockIdx.x * kMedThreads + threadIdx.x;
+  const int nlines = along_time ? bins : frames;
+  if (line >= nlines) return;
+  const int len = along_time ? frames : bins;
+  const long long stride = along_time ? bins : 1;
+  const float2* src = spec + (long long)row * frames * bins + (along_time ? line : (long long)line * bins);
+  float* dst = out + (long long)row * frames * bins + (along_time ? line : (long long)line * bins);
+  float* sw = med_sorted + threadIdx.x;
+  auto mag_at = [&](int i) {
+    const float2 v = src[(long long)reflect_idx(i, len) * stride];
+    return sqrtf(v.x * v.x + v.y * v.y);
+  };
+  const int left = k / 2;
+  // initial window for output 0: indices -left .. -left + k - 1, insertion sort
+  for (int q = 0; q < k; ++q) {
+    const float v = mag_at(q - left);
+    int p = q;
+    while (p > 0 && sw[(p - 1) * kMedThreads] > v) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
+    sw[p * kMedThreads] = v;
+  }
+  dst[0] = sw[left * kMedThreads];
+  for (int i = 1; i < len; ++i) {
+    const float gone = mag_at(i - 1 - left);                     // leaves the window
+    const float come = mag_at(i - left + k - 1);                 // enters it
+    if (gone != come) {
+      // remove one occurrence of `gone`, then insert `come`, keeping the array sorted
+      int p = 0;
+      while (p < k - 1 && sw[p * kMedThreads] != gone) ++p;      // present by construction (bounded for NaNs)
+      if (come > gone) {
+        while (p + 1 < k && sw[(p + 1) * kMedThreads] < come) { sw[p * kMedThreads] = sw[(p + 1) * kMedThreads]; ++p; }
+      } else {
+        while (p > 0 && sw[(p - 1) * kMedThreads] > come) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
+      }
+      sw[p * kMedThreads] = come;
+    }
+    dst[(long long)i * stride] = sw[left * kMedThreads];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- masks + ISTFT
+__device__ __forceinline__ float softmask2(float x, float ref, bool split_zeros) {
+  const float z = fmaxf(x, ref);
+  if (z < FLT_MIN) return split_zeros ? 0.5f : 0.f;
+  const float a = x / z, b = ref / z;
+  const float m = a * a, r = b * b;
+  return m / (m + r);
+}
+
+__global__ void __launch_bounds__(kFftThreads)
+hpss_istft_kernel(const float2* __restrict__ spec, const float* __restrict__ harm, const float* __restrict__ perc,
+                  float* __restrict__ acc, int n_fft, int log2n, int hop, int frames, long long acc_len,
+                  float margin_h, float margin_p, const float* __restrict__ window, const float2* __restrict__ tw) {
+  extern __shared__ float2 fft_buf[];                            // [n_fft] work + [bins] frame spectrum + 2*[bins] masks
+  const int bins = n_fft / 2 + 1;
+  float2* sp = fft_buf + n_fft;
+  float* mh = reinterpret_cast<float*>(sp + bins);
+  float* mp = mh + bins;
+  const int frame = blockIdx.x;
+  const long long row = blockIdx.y;
+  const long long off = ((long long)row * frames + frame) * bins;
+  const bool split = (margin_h == 1.f && margin_p == 1.f);
+  for (int k = threadIdx.x; k < bins; k += kFftThreads) {
+    sp[k] = spec[off + k];
+    const float h = harm[off + k], p = perc[off + k];
+    mh[k] = softmask2(h, p * margin_h, split);
+    mp[k] = softmask2(p, h * margin_p, split);
+  }
+  __syncthreads();
+  const float scale = 1.f / (float)n_fft;
+  for (int comp = 0; comp < 3; ++comp) {
+    for (int k = threadIdx.x; k < bins; k += kFftThreads) {
+      const float g = comp == 0 ? mh[k] : (comp == 1 ? mp[k] : 1.f - (mh[k] + mp[k]));
+      const float2 v = make_float2(sp[k].x * g, sp[k].y * g);
+      fft_buf[bitrev((unsigned)k, log2n)] = v;
+      if (k > 0 && k < n_fft / 2) fft_buf[bitrev((unsigned)(n_fft - k), log2n)] = make_float2(v.x, -v.y);
+    }
+    __syncthreads();
+    fft_shared(fft_buf, n_fft, log2n, true, tw);
+    float* dst = acc + ((long long)row * 3 + comp) * acc_len + (long long)frame * hop;
+    for (int i = threadIdx.x; i < n_fft; i += kFftThreads)
+      atomicAdd(dst + i, fft_buf[i].x * scale * __ldg(window + i));
+    __syncthreads();
+  }
+}
+
+__global__ void hpss_finish_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, float* __restrict__ y,
+                                   long long acc_len, long long n_out, int pad, long long lines) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long line = blockIdx.y;
+  if (i >= n_out || line >= lines) return;
+  const float w = __ldg(wsum + i + pad);
+  const float v = acc[line * acc_len + i + pad];
+  y[line * n_out + i] = (w > FLT_MIN) ? v / w : v;
+}
+
+// ---------------------------------------------------------------------------------------------- recombination
+constexpr int kMixThreads = 512;
+constexpr int kMixMaxParts = 8;
+struct MixArgs {
+  const float* parts;        // [nparts][rows][n]
+  float* out;                // [rows][n]
+  long long rows, n;
+  int nparts;
+  float w1[kMixMaxParts], w2[kMixMaxParts], wmix;
+};
+struct MixStat {
+  double sum;
+  float lo, hi;
+};
+__device__ __forceinline__ void mix_finish(MixStat s, long long n, double& mean, double& inv, double* dscr, float* fscr) {
+  const double tot = block_sum<kMixThreads>(s.sum, dscr);
+  const float lo = block_min<kMixThreads>(s.lo, fscr);
+  const float hi = block_max<kMixThreads>(s.hi, fscr);
+  mean = tot / (double)n;
+  const double peak = fmax((double)hi - mean, mean - (double)lo);
+  inv = peak > 0.0 ? 1.0 / peak : 1.0;                          // NumPy rule: divide only when the peak is positive
+}
+__device__ __forceinline__ float mix_norm(float v, double mean, double inv) {
+  return fminf(fmaxf((float)(((double)v - mean) * inv), -1.f), 1.f);
+}
+
+__global__ void __launch_bounds__(kMixThreads)
+hpss_mix_kernel(const MixArgs a) {
+  __shared__ double dscr[32];
+  __shared__ float fscr[32];
+  const long long row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* base = a.parts + row * a.n;
+  const long long pstride = a.rows * a.n;
+  double pm[kMixMaxParts], pi[kMixMaxParts];
+  for (int p = 0; p < a.nparts; ++p) {                           // statistics of every part
+    MixStat s{0.0, INFINITY, -INFINITY};
+    for (long long i = tid; i < a.n; i += kMixThreads) {
+      const float v = base[p * pstride + i];
+      s.sum += (double)v; s.lo = fminf(s.lo, v); s.hi = fmaxf(s.hi, v);
+    }
+    mix_finish(s, a.n, pm[p], pi[p], dscr, fscr);
+  }
+  auto raw = [&](long long i, float& m1, float& m2) {
+    m1 = 0.f; m2 = 0.f;
+    for (int p = 0; p < a.nparts; ++p) {
+      const float v = base[p * pstride + i];
+      m1 = fmaf(a.w1[p], v, m1);
+      m2 = fmaf(a.w2[p], mix_norm(v, pm[p], pi[p]), m2);
+    }
+  };
+  MixStat s1{0.0, INFINITY, -INFINITY}, s2{0.0, INFINITY, -INFINITY};
+  for (long long i = tid; i < a.n; i += kMixThreads) {
+    float m1, m2;
+    raw(i, m1, m2);
+    s1.sum += (double)m1; s1.lo = fminf(s1.lo, m1); s1.hi = fmaxf(s1.hi, m1);
+    s2.sum += (double)m2; s2.lo = fminf(s2.lo, m2); s2.hi = fmaxf(s2.hi, m2);
+  }
+  double mean1, inv1, mean2, inv2, mean3, inv3;
+  mix_finish(s1, a.n, mean1, inv1, dscr, fscr);
+  mix_finish(s2, a.n, mean2, inv2, dscr, fscr);
+  MixStat s3{0.0, INFINITY, -INFINITY};
+  for (long long i = tid; i < a.n; i += kMixThreads) {
+    float m1, m2;
+    raw(i, m1, m2);
+    const float v = mix_norm(m1, mean1, inv1) + a.wmix * mix_norm(m2, mean2, inv2);
+    s3.sum += (double)v; s3.lo = fminf(s3.lo, v); s3.hi = fmaxf(s3.hi, v);
+  }
+  mix_finish(s3, a.n, mean3, inv3, dscr, fscr);
+  for (long long i = tid; i < a.n; i += kMixThreads) {
+    float m1, m2;
+    raw(i, m1, m2);
+    const float v = mix_norm(m1, mean1, inv1) + a.wmix * mix_norm(m2, mean2, inv2);
+    a.out[row * a.n + i] = mix_norm(v, mean3, inv3);
+  }
+}
+
+static int log2_exact(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return (1 << l) == n ? l : -1;
+}
+
+}  // namespace mpcg
+
+extern "C" int mpcg_hpss_stft_f32(const float* x, float* spec, int64_t rows, int64_t t, int n_fft, int hop,
+                                  int64_t frames, const float* window, const float* twiddle, void* stream) {
+  using namespace mpcg;
+  const int l2 = log2_exact(n_fft);
+  if (rows < 0 || t < 0 || l2 < 1 || n_fft > 8192 || hop < 1 || frames != 1 + t / hop) return MPCG_EINVAL;
+  if (rows == 0) return MPCG_OK;
+  if (!x || !spec || !window || !twiddle) return MPCG_EINVAL;
+  if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
+  const size_t smem = (size_t)n_fft * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(hpss_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)frames, (unsigned)rows);
+  hpss_stft_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream>>>(x, (float2*)spec, (long long)t, n_fft, l2, hop,
+                                                                    (int)frames, window, (const float2*)twiddle);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
+
+extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows, int64_t frames, int bins, int k,
+                                    int along_time, void* stream) {
+  using namespace mpcg;
+  if (rows < 0 || frames < 1 || bins < 1 || k < 1) return MPCG_EINVAL;
+  if (k > kMedMaxK) return MPCG_ERANGE;
+  if (rows == 0) return MPCG_OK;
+  if (!spec || !out) return MPCG_EINVAL;
+  if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
+  const int64_t nlines = along_time ? bins : frames;
+  const size_t smem = (size_t)k * kMedThreads * sizeof(float);
+  dim3 grid((unsigned)((nlines + kMedThreads - 1) / kMedThreads), (unsigned)rows);
+  hpss_median_kernel<<<grid, kMedThreads, smem, (cudaStream_t)stream>>>((const float2*)spec, out, (int)frames, bins, k,
+                                                                      along_time);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
+
+extern "C" int mpcg_hpss_istft_f32(const float* spec, const float* harm, const float* perc, float* acc, int64_t rows,
+                                   int n_fft, int hop, int64_t frames, float margin_h, float margin_p,
+                                   const float* window, const float* twiddle, void* stream) {
+  using namespace mpcg;
+  const int l2 = log2_exact(n_fft);
+  if (rows < 0 || l2 < 1 || n_fft > 8192 || hop < 1 || frames < 1) return MPCG_EINVAL;
+  if (rows == 0) return MPCG_OK;
+  if (!spec || !harm || !perc || !acc || !window || !twiddle) return MPCG_EINVAL;
+  if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
+  const int bins = n_fft / 2 + 1;
+  const long long acc_len = (long long)n_fft + (long long)hop * (frames - 1);
+  const size_t smem = (size_t)n_fft * sizeof(float2) + (size_t)bins * (sizeof(float2) + 2 * sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(hpss_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)rows * 3 * acc_len, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)frames, (unsigned)rows);
+  hpss_istft_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream>>>((const float2*)spec, harm, perc, acc, n_fft, l2,
+                                                                     hop, (int)frames, acc_len, margin_h, margin_p,
+                                                                     window, (const float2*)twiddle);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
+
+extern "C" int mpcg_hpss_finish_f32(const float* acc, const float* wsum, float* y, int64_t lines, int n_fft, int hop,
+                                    int64_t frames, void* stream) {
+  using namespace mpcg;
+  if (lines < 0 || n_fft < 2 || hop < 1 || frames < 1) return MPCG_EINVAL;
+  const long long acc_len = (long long)n_fft + (long long)hop * (frames - 1);
+  const long long n_out = (long long)hop * (frames - 1);
+  if (lines == 0 || n_out == 0) return MPCG_OK;
+  if (!acc || !wsum || !y) return MPCG_EINVAL;
+  if (lines > 65535) return MPCG_ERANGE;
+  dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)lines);
+  hpss_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, wsum, y, acc_len, n_out, n_fft / 2, (long long)lines);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
+
+extern "C" int mpcg_hpss_mix_f32(const float* parts, float* out, int64_t rows, int64_t n, int nparts, const float* w1,
+                                 const float* w2, float wmix, void* stream) {
+  using namespace mpcg;
+  if (rows < 0 || n < 0 || nparts < 1 || !w1 || !w2) return MPCG_EINVAL;
+  if (nparts > kMixMaxParts) return MPCG_ERANGE;
+  if (rows == 0 || n == 0) return MPCG_OK;
+  if (!parts || !out) return MPCG_EINVAL;
+  if (rows > 0x7fffffffLL) return MPCG_ERANGE;
+  MixArgs a;
+  a.parts = parts; a.out = out; a.rows = rows; a.n = n; a.nparts = nparts; a.wmix = wmix;
+  for (int p = 0; p < kMixMaxParts; ++p) { a.w1[p] = p < nparts ? w1[p] : 0.f; a.w2[p] = p < nparts ? w2[p] : 0.f; }
+  hpss_mix_kernel<<<(unsigned)rows, kMixThreads, 0, (cudaStream_t)stream>>>(a);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
