@@ -191,6 +191,17 @@ int mpcg_hpss_finish_f32(const float* acc, const float* wsum, float* y, int64_t 
 int mpcg_hpss_mix_f32(const float* parts, float* out, int64_t rows, int64_t n, int nparts, const float* w1,
                       const float* w2, float wmix, void* stream);
 
+/* ---- time warp and recorded-noise mixing (NumPy-only in the reference; parity unpinned) ------------------------
+ * y[r, j] = x_r(j * rate), 4-point Catmull-Rom, edges clamped; n_out is chosen by the caller (round(t / rate)).
+ * Stands in for primitives.time_stretch (augment/primitives.py:30-34), whose rubberband arithmetic is external. */
+int mpcg_time_warp_f32(const float* x, float* y, int64_t rows, int64_t t, int64_t n_out, double rate, void* stream);
+/* y[r] = N(x[r] + scale[r] * N(bank[src_row[r], src_start[r] : src_start[r] + t])), N = NumPy abs_max_normalise
+ * (noise_sources.py:53-64 + pipelines.py:59-60).  bank: device [bank_rows, bank_len]; src_row / src_start: device
+ * int64 [rows]; scale: device [rows].  The caller guarantees src_start + t <= bank_len. */
+int mpcg_mix_noise_f32(const float* x, const float* bank, float* y, int64_t rows, int64_t t, int64_t bank_rows,
+                       int64_t bank_len, const int64_t* src_row, const int64_t* src_start, const float* scale,
+                       void* stream);
+
 /* Profiling aid (tools/ only): device buffer [ctas, 16] of int64 that the fused kernel fills with clock64 stamps at
  * its phase boundaries; NULL switches it off.  Not part of the data path. */
 void mpcg_debug_set_phase_clock_buffer(void* dev_ptr);

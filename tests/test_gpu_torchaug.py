@@ -136,3 +136,39 @@ def test_edge_shapes(ta):
         ta.add_white_noise(torch.zeros(2, 16))
     w = ta.amplitude_warp(torch.randn(2, 5000, device="cuda"), amps=np.ones((2, 12)))    # flat gains = 65-tap mean
     assert w.shape == (2, 5000)
+
+
+def test_time_warp_definition(ta):
+    """y[j] = x(j * rate) with Catmull-Rom interpolation (this build's definition; parity with rubberband unpinned)."""
+    rng = np.random.default_rng(9)
+    t = 5000
+    x = np.cumsum(rng.standard_normal((2, t)), axis=1).astype(np.float32) * 0.05
+    for rate in (1.005, 0.8, 1.3):
+        got = ta.time_warp(torch.from_numpy(x).cuda(), 4125, rate).cpu().numpy()
+        n = int(round(t / rate))
+        assert got.shape == (2, n)
+        pos = np.arange(n) * rate
+        i = np.floor(pos).astype(int); u = (pos - i).astype(np.float32)
+        at = lambda k: x[:, np.clip(k, 0, t - 1)]
+        p0, p1, p2, p3 = at(i - 1), at(i), at(i + 1), at(i + 2)
+        want = ((( -0.5 * p0 + 1.5 * p1 - 1.5 * p2 + 0.5 * p3) * u + (p0 - 2.5 * p1 + 2 * p2 - 0.5 * p3)) * u
+                + (-0.5 * p0 + 0.5 * p2)) * u + p1
+        assert rel_err(got, want) < 1e-5
+    same = ta.time_warp(torch.from_numpy(x).cuda(), 4125, 1.0).cpu().numpy()
+    np.testing.assert_array_equal(same, x)                                     # rate 1 is the identity
+    assert ta.time_warp(torch.from_numpy(x).cuda(), 4125, 0.7, keep_length=True).shape == (2, t)
+
+
+def test_mix_noise_arithmetic(ta):
+    from oracle import numpy_path as onp
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((3, 4000)).astype(np.float32)
+    bank = (rng.standard_normal((2, 9000)) * 3 + 1).astype(np.float32)
+    rows, starts, scale = [1, 0, 1], [0, 5000, 1234], [0.3, 0.0, 0.11]
+    got = ta.mix_noise(torch.from_numpy(x).cuda(), torch.from_numpy(bank).cuda(), rows=rows, starts=starts, scale=scale)
+    for r in range(3):
+        crop = onp.abs_max_normalise(bank[rows[r], starts[r]:starts[r] + 4000])
+        want = onp.abs_max_normalise(x[r].astype(np.float64) + scale[r] * crop)
+        assert rel_err(got[r].cpu().numpy(), want) < 1e-5
+    out = ta.mix_noise(torch.from_numpy(x).cuda(), torch.from_numpy(bank).cuda())          # random draws
+    assert out.shape == (3, 4000) and float(out.abs().max()) <= 1.0

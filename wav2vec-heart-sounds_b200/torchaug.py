@@ -218,3 +218,42 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
     x = _eq_mix(x, _coloured(x, fs, bands, m3), m3, False)
     x = noise_stage(x, 2, "mask4")
     return x
+
+
+# ------------------------------------------------------------------------------------------------ NumPy-only rows
+def time_warp(x: torch.Tensor, fs: int, rate: float, keep_length: bool = False) -> torch.Tensor:
+    """Device stand-in for ``primitives.time_stretch(x, fs, rate, keep_length)`` (reference primitives.py:30-34).
+    The reference calls the rubberband phase vocoder through a subprocess, which has no reproducible arithmetic;
+    this is a DEFINED resampling warp ``y[j] = x(j * rate)`` (Catmull-Rom), length ``round(T / rate)``, cut to ``T``
+    with ``keep_length``.  Parity with the reference is unpinned."""
+    x = _rows2d(x)
+    b, t = x.shape
+    n = int(round(t / float(rate)))
+    out = torch.empty((b, n), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().mpcg_time_warp_f32(x.data_ptr(), out.data_ptr(), b, t, n, float(rate), _lib.stream_ptr(x)),
+               "time warp")
+    return out[:, :t].contiguous() if keep_length and n > t else out
+
+
+def mix_noise(x: torch.Tensor, bank: torch.Tensor, *, rows=None, starts=None, scale=None, hi: float = 0.5) -> torch.Tensor:
+    """``abs_max_normalise(x + scale * abs_max_normalise(crop))`` with ``crop`` a random ``T``-sample span of a
+    random record of the device-resident noise ``bank [K, Tn]`` (reference noise_sources.py:53-64 and
+    pipelines.py:59-60; record loading stays on the host).  ``scale`` defaults to the reference's
+    ``choice([0, U(0, hi)])`` per row."""
+    x = _rows2d(x)
+    bank = _lib.require_cuda_f32(bank, "bank")
+    b, t = x.shape
+    k, tn = bank.shape
+    if tn < t:
+        raise ValueError("noise records must be at least as long as the signals")
+    dev = x.device
+    rows = torch.randint(0, k, (b,), device=dev) if rows is None else torch.as_tensor(rows, device=dev)
+    starts = (torch.rand(b, device=dev) * (tn - t + 1)).long().clamp_(0, tn - t) if starts is None else torch.as_tensor(starts, device=dev)
+    if scale is None:
+        scale = torch.where(torch.rand(b, device=dev) < 0.5, torch.zeros(b, device=dev), torch.rand(b, device=dev) * hi)
+    rows, starts = rows.long().contiguous(), starts.long().contiguous()
+    scale = _dev_f32(scale, dev, (b,))
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mpcg_mix_noise_f32(x.data_ptr(), bank.data_ptr(), out.data_ptr(), b, t, k, tn, rows.data_ptr(),
+                                             starts.data_ptr(), scale.data_ptr(), _lib.stream_ptr(x)), "noise mix")
+    return out
