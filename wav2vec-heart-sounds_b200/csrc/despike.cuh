@@ -155,6 +155,140 @@ __device__ __forceinline__ SpikeDecision spike_decide_sort64(const float* tops, 
   return d;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast path for frames resident in shared memory, driven by ONE warp with no block barrier.
+//   * per-frame maxima of 32-sample blocks (bmax) make "first arg-max" and "maximum after the edit" O(blocks);
+//   * sign flips are searched outward from the peak in 32-sample ballots;
+//   * the frame maxima of the whole recording are kept as a sorted array of 64-bit keys
+//     (value bits << 32 | ~index), updated by one insertion per pass instead of a fresh sort.
+// Every step reproduces the reference's rules: first maximum, strict +/- flips, [lo, hi) fill, median rank.
+struct SpikeSorted {                                  // lives in shared memory, owned by warp 0
+  unsigned long long key[64];
+};
+__device__ __forceinline__ unsigned long long spike_key(float top, int frame) {
+  return ((unsigned long long)__float_as_uint(top) << 32) | (0xffffffffu - (unsigned)frame);
+}
+// Sort the (<= 64) frame maxima into sk (ascending, zero keys pad the bottom).
+__device__ __forceinline__ void spike_sort_init(SpikeSorted& sk, const float* tops, int nframes) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long k0 = (2 * lane < nframes) ? spike_key(tops[2 * lane], 2 * lane) : 0ull;
+  unsigned long long k1 = (2 * lane + 1 < nframes) ? spike_key(tops[2 * lane + 1], 2 * lane + 1) : 0ull;
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const bool up = ((2 * lane) & size) == 0;
+      if (stride == 1) {
+        const unsigned long long lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+        k0 = up ? lo : hi;
+        k1 = up ? hi : lo;
+      } else {
+        const int pl = stride >> 1;
+        const unsigned long long o0 = __shfl_xor_sync(kFull, k0, pl), o1 = __shfl_xor_sync(kFull, k1, pl);
+        const bool take_min = (up == ((lane & pl) == 0));
+        k0 = take_min ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+        k1 = take_min ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+      }
+    }
+  }
+  sk.key[2 * lane] = k0;
+  sk.key[2 * lane + 1] = k1;
+  __syncwarp();
+}
+// Frame `frame` dropped from old_top to new_top (new <= old): move its key down to its new place.
+__device__ __forceinline__ void spike_sort_update(SpikeSorted& sk, int frame, float old_top, float new_top) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long ko = spike_key(old_top, frame), kn = spike_key(new_top, frame);
+  if (ko == kn) return;
+  const unsigned long long a = sk.key[2 * lane], b = sk.key[2 * lane + 1];
+  const unsigned m0 = __ballot_sync(kFull, a == ko), m1 = __ballot_sync(kFull, b == ko);
+  const int pos_old = m0 ? 2 * (__ffs(m0) - 1) : 2 * (__ffs(m1) - 1) + 1;
+  const int below = __popc(__ballot_sync(kFull, a < kn)) + __popc(__ballot_sync(kFull, b < kn));   // insertion point
+  unsigned long long na, nb;
+  {
+    const int i = 2 * lane;
+    na = (i == below) ? kn : ((i > below && i <= pos_old) ? sk.key[i - 1] : a);
+    const int j = i + 1;
+    nb = (j == below) ? kn : ((j > below && j <= pos_old) ? a : b);
+  }
+  __syncwarp();
+  sk.key[2 * lane] = na;
+  sk.key[2 * lane + 1] = nb;
+  __syncwarp();
+}
+__device__ __forceinline__ SpikeDecision spike_sort_decide(const SpikeSorted& sk, int nframes, double threshold,
+                                                          int median_mode) {
+  const int base = 64 - nframes;
+  const unsigned long long top = sk.key[63];
+  SpikeDecision d;
+  d.worst = (int)(0xffffffffu - (unsigned)(top & 0xffffffffu));
+  const float bv = __uint_as_float((unsigned)(top >> 32));
+  const float lo_mid = __uint_as_float((unsigned)(sk.key[base + ((nframes - 1) >> 1)] >> 32));
+  if (median_mode == MPCG_MEDIAN_LOWER) {
+    d.active = bv > __fmul_rn((float)threshold, lo_mid);
+  } else {
+    const float hi_mid = __uint_as_float((unsigned)(sk.key[base + (nframes >> 1)] >> 32));
+    const double med = ((double)lo_mid + (double)hi_mid) * 0.5;
+    d.active = (med != 0.0) && ((double)bv > threshold * med);
+  }
+  return d;
+}
+
+// One flattening pass on a shared-memory frame by one warp.  bm[0..nblk) are the maxima of its 32-sample blocks
+// and frame_top == max(bm).  Updates fr and bm, returns the integer decisions, whether anything moved, and the
+// frame's new maximum.
+__device__ __forceinline__ void spike_pass_warp(float* fr, int win, float* bm, int nblk, float frame_top, int& peak,
+                                                int& lo, int& hi, bool& changed, float& new_top) {
+  const int lane = threadIdx.x & 31;
+  // first block holding the maximum, then the first sample inside it
+  int blk = -1;
+  for (int b0 = 0; b0 < nblk && blk < 0; b0 += 32) {
+    const int b = b0 + lane;
+    const unsigned m = __ballot_sync(kFull, b < nblk && bm[b] == frame_top);
+    if (m) blk = b0 + __ffs(m) - 1;
+  }
+  {
+    const int i = blk * 32 + lane;
+    const unsigned m = __ballot_sync(kFull, i < win && fabsf(fr[i]) == frame_top);
+    peak = blk * 32 + __ffs(m) - 1;
+  }
+  auto flip = [&](int i) {                               // strict sign change between samples i and i + 1
+    if (i < 0 || i > win - 2) return false;
+    const float a = fr[i], b = fr[i + 1];
+    return (a > 0.f && b < 0.f) || (a < 0.f && b > 0.f);
+  };
+  int last_before = -1;
+  for (int c = peak - 1; c >= 0; c -= 32) {              // candidates c-31 .. c, highest first
+    const unsigned m = __ballot_sync(kFull, flip(c - 31 + lane));
+    if (m) { last_before = c - 31 + (31 - __clz(m)); break; }
+  }
+  int first_after = 0x7fffffff;
+  for (int c = peak; c <= win - 2; c += 32) {            // candidates c .. c+31, lowest first
+    const unsigned m = __ballot_sync(kFull, flip(c + lane));
+    if (m) { first_after = c + __ffs(m) - 1; break; }
+  }
+  lo = last_before + 1;
+  hi = (first_after == 0x7fffffff) ? win - 1 : first_after;
+  int moved = 0;
+  for (int i = lo + lane; i < hi; i += 32) {
+    moved |= (fr[i] != kSpikeFill);
+    fr[i] = kSpikeFill;
+  }
+  changed = __any_sync(kFull, moved != 0);
+  __syncwarp();
+  if (hi > lo) {                                         // refresh the maxima of the blocks the span touched
+    for (int b = lo >> 5; b <= ((hi - 1) >> 5); ++b) {
+      const int i = b * 32 + lane;
+      const float m = warp_max(i < win ? fabsf(fr[i]) : 0.f);
+      if (lane == 0) bm[b] = m;
+    }
+    __syncwarp();
+  }
+  float m = 0.f;
+  for (int b = lane; b < nblk; b += 32) m = fmaxf(m, bm[b]);
+  new_top = warp_max(m);
+}
+
 // Flatten the spike in one frame held in shared memory.  Returns (through refs) the integer decisions;
 // `changed` tells whether any sample actually moved (an unchanged pass is a fixed point: every later
 // pass of the reference would repeat it, so the caller may stop).  All threads call.

@@ -37,7 +37,7 @@ constexpr int kFzThreads = MPCG_FZ_THREADS;
 constexpr int kFzWarps = kFzThreads / 32;
 constexpr int kFzChunks = kFzThreads;     // one filter chunk per thread
 constexpr int kFzLmax = 81;               // longest chunk (odd)
-constexpr int kFzMaxFrames = 256;        // despike frames per row the fused kernel accepts
+constexpr int kFzMaxFrames = 64;         // despike frames per row the fused kernel accepts
 constexpr int kFzMaxCluster = 8;
 constexpr int kFzStageWords = 4400;       // resampler input staging (largest instance: 4116 + skew)
 
@@ -84,10 +84,16 @@ struct FzFilterScratch {                  // this row's recipe, copied from glob
   double wagg[kFzWarps][4];               // warp aggregates
   double wcar[kFzWarps][4];               // state at the start of each warp's first chunk (zero slice start)
 };
+constexpr int kFzMaxBlocks = 1344;        // 32-sample blocks in one slice (kFzLmax * kFzChunks / 32 + frames)
+struct FzDespikeScratch {
+  SpikeSorted sorted;
+  float bmax[kFzMaxBlocks];
+};
 struct FzShared {
-  union {                                 // the resampler's input staging is dead once the slice is in `sig`
-    float xs[kFzStageWords];
-    FzFilterScratch f;
+  union {                                 // three phases, one after the other, share this space:
+    float xs[kFzStageWords];              //   resampler input staging
+    FzDespikeScratch d;                   //   despike: block maxima of my frames + sorted frame maxima
+    FzFilterScratch f;                    //   filter recipe tables and scan scratch
   };
   double xE[kFzMaxCluster][4];            // end states exported by each rank
   double xstat[kFzMaxCluster][4];         // (sum, min, max, -) exported by each rank
@@ -95,7 +101,7 @@ struct FzShared {
   float tops[2][kFzMaxFrames];            // double-buffered frame maxima (see the despike loop)
   float fscr[40];
   int iscr[64];
-  int ctrl[4];
+  int ctrl[4];                            // (passes, done) published by the round owner, double-buffered
   int decision[2];                        // (active, worst) broadcast by warp 0
 };
 
@@ -194,67 +200,98 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   for (int i = n + tid; i < P.cap; i += kFzThreads) sig[i] = 0.f;      // chunk grid beyond the slice
 
   // ---------------------------------------------------------------- filter tables (independent of the samples)
-  // recipe tables: global (L2-resident, ~11 KB) -> shared, coalesced; everything below reads shared memory
-  for (int i = tid; i < 512; i += kFzThreads) sm.f.mtab[i & 15][i >> 4] = (&Kg->mlane[0][0])[i];
-  for (int i = tid; i < L * 4; i += kFzThreads) (&sm.f.wt[0][0])[i] = (&Kg->wt[0][0])[i];
-  for (int i = tid; i < 160; i += kFzThreads) (&sm.f.mp[0][0])[i] = (&Kg->mp[0][0])[i];
-  if (tid < 16) { sm.f.prop_slice[tid] = Kg->prop_slice[tid]; sm.f.prop_part[tid] = Kg->prop_part[tid]; }
-  if (tid < 10) (&sm.f.c[0][0])[tid] = (&Kg->c[0][0])[tid];
   __syncthreads();
 
   stamp();                                                // 2: tables ready
   // ---------------------------------------------------------------- 2. Schmidt despike (cluster-wide)
-  // Every CTA keeps two copies of all frame maxima.  Pass k reads copy k&1; the owner of the worst frame
-  // flattens it in its own shared memory and writes the frame's new maximum (and a "changed" flag) into copy
-  // (k+1)&1 of every CTA while each CTA carries the other entries over locally: one cluster barrier per pass.
+  // Every CTA keeps two copies of all frame maxima.  Round k reads copy k&1.  Warp 0 of every CTA sorts the
+  // maxima (identical data, identical verdict).  The CTA owning the worst frame then keeps going ON ITS OWN:
+  // flatten, update its local maxima, decide again -- pass after pass with no barrier at all, as long as the
+  // worst frame stays one of its own (a burst is flattened half-cycle by half-cycle, so it usually does).  When
+  // ownership moves (or nothing is left to do) it publishes its frames' maxima and the pass counter into copy
+  // (k+1)&1 of every CTA; the other CTAs carried the remaining entries over locally; one cluster barrier per round.
+  // All other warps only wait at that barrier.
   int passes = 0;
   if (k_despike && P.nframes > 0) {
     const int gf0 = rank * P.fpc;
     int nloc = P.nframes - gf0;
     nloc = nloc < 0 ? 0 : (nloc > P.fpc ? P.fpc : nloc);
-    for (int f = warp; f < nloc; f += kFzWarps) {
-      const float* p = sig + f * P.win_d;
+    const int nblk = (P.win_d + 31) >> 5;                   // 32-sample blocks per frame
+    for (int q = warp; q < nloc * nblk; q += kFzWarps) {    // block maxima of my frames
+      const int f = q / nblk, b = q - f * nblk;
+      const int i = b * 32 + lane;
+      const float m = warp_max(i < P.win_d ? fabsf(sig[f * P.win_d + i]) : 0.f);
+      if (lane == 0) sm.d.bmax[q] = m;
+    }
+    __syncthreads();
+    for (int f = warp; f < nloc; f += kFzWarps) {           // frame maxima -> every CTA's copy 0
       float m = 0.f;
-      for (int i = lane; i < P.win_d; i += 32) m = fmaxf(m, fabsf(p[i]));
+      for (int b = lane; b < nblk; b += 32) m = fmaxf(m, sm.d.bmax[f * nblk + b]);
       m = warp_max(m);
       if (lane < P.ncl) *cluster.map_shared_rank(&sm.tops[0][gf0 + f], lane) = m;
     }
     cluster_arrive();
     cluster_wait();
-    for (; passes < P.max_iter; ++passes) {
-      const float* cur = sm.tops[passes & 1];
-      float* nxt = sm.tops[(passes + 1) & 1];
-      SpikeDecision dec;
-      if (warp == 0) {                                    // one warp decides, the CTA reads the verdict
-        dec = (P.nframes <= 64) ? spike_decide_sort64(cur, P.nframes, P.threshold, P.median_mode)
-                                : spike_decide_warp(cur, P.nframes, P.threshold, P.median_mode);
-        if (lane == 0) { sm.decision[0] = dec.active ? 1 : 0; sm.decision[1] = dec.worst; }
-      }
-      __syncthreads();
-      dec.active = sm.decision[0] != 0;
-      dec.worst = sm.decision[1];
-      if (!dec.active) break;
-      const int owner = dec.worst / P.fpc;
-      for (int i = tid; i < P.nframes; i += kFzThreads)
-        if (i != dec.worst) nxt[i] = cur[i];
-      if (rank == owner) {
-        int peak, lo, hi;
-        bool changed;
-        float new_top;
-        spike_flatten<kFzThreads>(sig + (dec.worst - gf0) * P.win_d, P.win_d, peak, lo, hi, changed, new_top,
-                                  sm.fscr, sm.iscr);
-        if (tid == 0 && P.trace && passes < P.trace_cap) {
-          int* tr = P.trace + (row * P.trace_cap + passes) * 4;
-          tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
+    for (int round = 0;; ++round) {
+      float* cur = sm.tops[round & 1];
+      float* nxt = sm.tops[(round + 1) & 1];
+      if (warp == 0) {
+        bool idle = passes >= P.max_iter;                   // budget spent, or (below) nothing exceeds the threshold
+        SpikeDecision dec;
+        dec.active = false; dec.worst = 0;
+        if (!idle) {
+          spike_sort_init(sm.d.sorted, cur, P.nframes);
+          dec = spike_sort_decide(sm.d.sorted, P.nframes, P.threshold, P.median_mode);
+          idle = !dec.active;
         }
-        if (tid < P.ncl) {
-          *cluster.map_shared_rank(&nxt[dec.worst], tid) = new_top;
-          *cluster.map_shared_rank(&sm.ctrl[(passes + 1) & 1], tid) = changed ? 1 : 0;
+        if (lane == 0) sm.decision[round & 1] = idle ? 1 : 0;   // same verdict in every CTA
+        if (!idle) {
+          const int owner = dec.worst / P.fpc;
+          const int of0 = owner * P.fpc;
+          for (int i = lane; i < P.nframes; i += 32)        // carry the other CTAs' entries over locally
+            if (i < of0 || i >= of0 + P.fpc) nxt[i] = cur[i];
+          if (rank == owner) {
+            bool done = false;
+            while (true) {                                  // local passes on my own frames, no barrier
+              const int fl = dec.worst - gf0;
+              const float old_top = cur[dec.worst];
+              int peak, lo, hi;
+              bool changed;
+              float new_top;
+              spike_pass_warp(sig + fl * P.win_d, P.win_d, sm.d.bmax + fl * nblk, nblk, old_top, peak, lo, hi, changed,
+                              new_top);
+              if (lane == 0) {
+                cur[dec.worst] = new_top;
+                if (P.trace && passes < P.trace_cap) {
+                  int* tr = P.trace + (row * P.trace_cap + passes) * 4;
+                  tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
+                }
+              }
+              __syncwarp();
+              ++passes;
+              if (!changed || passes >= P.max_iter) { done = true; break; }   // fixed point / budget
+              spike_sort_update(sm.d.sorted, dec.worst, old_top, new_top);
+              dec = spike_sort_decide(sm.d.sorted, P.nframes, P.threshold, P.median_mode);
+              if (!dec.active) { done = true; break; }
+              if (dec.worst / P.fpc != rank) break;         // somebody else's frame: hand over
+            }
+            for (int f = lane; f < nloc * P.ncl; f += 32) { // publish my frames' maxima to every CTA
+              const int fi = f % nloc, rk = f / nloc;
+              *cluster.map_shared_rank(&nxt[gf0 + fi], rk) = cur[gf0 + fi];
+            }
+            if (lane < P.ncl) {
+              int* c = cluster.map_shared_rank(&sm.ctrl[2 * ((round + 1) & 1)], lane);
+              c[0] = passes;
+              c[1] = done ? 1 : 0;
+            }
+          }
         }
       }
       cluster_arrive();
       cluster_wait();
-      if (!sm.ctrl[(passes + 1) & 1]) { ++passes; break; }   // fixed point: the reference would only repeat it
+      if (sm.decision[round & 1]) break;                    // nothing to do this round: every CTA stops together
+      passes = sm.ctrl[2 * ((round + 1) & 1)];
+      if (sm.ctrl[2 * ((round + 1) & 1) + 1]) break;
     }
     if (P.edits && rank == 0 && tid == 0) P.edits[row] = passes;
     __syncthreads();
@@ -263,6 +300,13 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   }
 
   stamp();                                                // 3: despiked
+  // recipe tables: global (L2-resident, ~11 KB) -> shared, coalesced; everything below reads shared memory
+  for (int i = tid; i < 512; i += kFzThreads) sm.f.mtab[i & 15][i >> 4] = (&Kg->mlane[0][0])[i];
+  for (int i = tid; i < L * 4; i += kFzThreads) (&sm.f.wt[0][0])[i] = (&Kg->wt[0][0])[i];
+  for (int i = tid; i < 160; i += kFzThreads) (&sm.f.mp[0][0])[i] = (&Kg->mp[0][0])[i];
+  if (tid < 16) { sm.f.prop_slice[tid] = Kg->prop_slice[tid]; sm.f.prop_part[tid] = Kg->prop_part[tid]; }
+  if (tid < 10) (&sm.f.c[0][0])[tid] = (&Kg->c[0][0])[tid];
+  __syncthreads();
   // ---------------------------------------------------------------- 3. low-pass + high-pass as one 4-state scan
   float* mine = sig + tid * L;
   double p[4] = {0.0, 0.0, 0.0, 0.0};
