@@ -264,7 +264,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "matches_device_run": same},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": recorded_traffic(), "algorithmic_bytes_per_launch": algo_bytes,
-                             "kernel": "fused_preprocess_kernel<33,16,30,1,1>", "peak_source": peak_src},
+                             "kernel": "fused_preprocess_kernel<33,16,30,1,2>", "peak_source": peak_src},
                 "clocks": clocks.summary()}
         if world == 1 and not args.no_cpu:
             cores = host_cores()
