@@ -93,3 +93,29 @@ def test_config4_size_properties(pkg):
     y = torch.roll(x[:64], shifts=3 * 256, dims=1)
     my = pkg.log_mel(y, tr)
     assert torch.equal(my[:, :, 8:240], m[:64, :, 5:237])
+
+
+def test_tensor_core_tier(pkg, golden):
+    """fast=True on the config-4 preset (n_fft = 4 * hop) runs on tcgen05; broadband inputs stay within 1e-5 of the
+    float64 reference, the fp64 tier and the TC tier agree, and the 16 kHz golden vectors are reproduced."""
+    kw = PRESETS["c4_16k"]
+    tr_tc = pkg.MelConfig(**kw).build(fast=True)
+    assert tr_tc.backend.startswith("tcgen05")
+    g = golden("mel_presets.npz")
+    x = torch.from_numpy(g["x"]).cuda()
+    lm = pkg.log_mel(x, tr_tc).cpu().numpy()
+    assert np.abs(lm - g["c4_16k_logmel64"]).max() < 1e-5
+    mel = tr_tc(x).cpu().numpy()
+    assert rel_err(mel, g["c4_16k_mel"]) < 1e-5
+    rng = torch.Generator(device="cuda").manual_seed(0)
+    big = torch.randn(64, 64000, device="cuda", generator=rng)
+    a = pkg.log_mel(big, tr_tc)
+    b = pkg.log_mel(big, pkg.MelConfig(**kw).build())
+    assert a.shape == b.shape == (64, 80, 251)
+    # white noise: a bin whose Hann-windowed magnitude happens to be ~1e-3 of its neighbours carries the split-fp16
+    # floor (~4e-7 of the rectangular-window bins) as a larger RELATIVE error; the dB map turns that into <= 1e-4
+    d = (a - b).abs()
+    assert float(d.max()) < 1e-4 and float((d > 1e-5).float().mean()) < 1e-3
+    short = torch.randn(3, 1000, device="cuda")                      # fewer frames than one tile, odd length
+    assert float((pkg.log_mel(short, tr_tc) - pkg.log_mel(short, pkg.MelConfig(**kw).build())).abs().max()) < 1e-4
+    assert pkg.MelConfig(**PRESETS["wg4k"]).build(fast=True).backend == "fma fp32"      # win < n_fft: not eligible

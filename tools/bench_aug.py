@@ -28,4 +28,4 @@ import wav2vec_heart_sounds_b200 as pkg
 xm = torch.randn(8192, 64000, device="cuda")
 for fast in (False, True):
     tr = pkg.MelConfig(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build(fast=fast)
-    timeit(f"log_mel config 4 (8192 x 64000 @16k), fast={fast}", lambda: pkg.log_mel(xm, tr), 8192 * 64000 * 4 + 8192 * 80 * 251 * 4)
+    timeit(f"log_mel config 4 (8192 x 64000 @16k), {tr.backend}", lambda: pkg.log_mel(xm, tr), 8192 * 64000 * 4 + 8192 * 80 * 251 * 4)

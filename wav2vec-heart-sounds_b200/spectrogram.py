@@ -54,12 +54,44 @@ class MelTransform:
         self._basis_host = torch.from_numpy(basis.astype(np.float32) if self.fast else basis)
         self._fb_host = fb[k0:k1].contiguous()
         self._dev = {}
+        # tensor-core tier (fast only): n_fft = Q * hop, full-length window, few enough weighted bins
+        self._tc = None
+        q = self.n_fft // self.hop_length if self.hop_length else 0
+        ncols = (2 * (self.nbins + 2) + 15) // 16 * 16
+        if (self.fast and self.win_length == self.n_fft and q * self.hop_length == self.n_fft and 1 <= q <= 8
+                and self.hop_length % 16 == 0 and ncols <= 256
+                and 2 * 128 * self.hop_length * 2 + 2 * ncols * self.hop_length * 2 + 256 <= 227 * 1024
+                and 128 * (ncols + 1) * 4 + 128 * (self.nbins + 1) * 4 <= 2 * 128 * self.hop_length * 2):
+            hop, nb2 = self.hop_length, self.nbins + 2
+            j = np.arange(hop, dtype=np.float64)[None, :]
+            kk = (k0 - 1 + np.arange(nb2, dtype=np.float64))[:, None]
+            ang = 2.0 * np.pi * ((kk * j) % self.n_fft) / self.n_fft
+            e = np.zeros((ncols, hop), dtype=np.float64)
+            e[:nb2] = np.cos(ang)
+            e[nb2:2 * nb2] = -np.sin(ang)
+            hi = e.astype(np.float16)
+            lo = (e - hi.astype(np.float64)).astype(np.float16)
+            packed = np.zeros((2, ncols * hop), dtype=np.float16)
+            n_idx, j_idx = np.meshgrid(np.arange(ncols), np.arange(hop), indexing="ij")
+            off = ((n_idx >> 3) * hop * 16 + (j_idx >> 3) * 128 + (n_idx & 7) * 16 + (j_idx & 7) * 2) // 2
+            packed[0, off.ravel()] = hi.ravel()
+            packed[1, off.ravel()] = lo.ravel()
+            m = np.arange(q, dtype=np.float64)
+            twq = np.stack([np.cos(-2 * np.pi * m / q), np.sin(-2 * np.pi * m / q)], axis=1).astype(np.float32)
+            wf = torch.hann_window(self.win_length, periodic=True).double().numpy()
+            self._tc = dict(q=q, ncols=ncols, basis=torch.from_numpy(packed), twq=torch.from_numpy(twq),
+                            inv_norm=float(1.0 / math.sqrt(float(np.sum(wf ** 2)))))
 
     def _tables(self, device):
         key = str(device)
         if key not in self._dev:
-            self._dev[key] = (self._basis_host.to(device), self._fb_host.to(device))
+            tc = None if self._tc is None else (self._tc["basis"].to(device), self._tc["twq"].to(device))
+            self._dev[key] = (self._basis_host.to(device), self._fb_host.to(device), tc)
         return self._dev[key]
+
+    @property
+    def backend(self) -> str:
+        return "tcgen05 split-fp16" if self._tc is not None else ("fma fp32" if self.fast else "fma fp64")
 
     def num_frames(self, t: int) -> int:
         return 1 + t // self.hop_length
@@ -71,8 +103,16 @@ class MelTransform:
         if t <= self.n_fft // 2:
             raise ValueError(f"signal of {t} samples is too short for reflect padding of {self.n_fft // 2}")
         frames = self.num_frames(t)
-        basis, fb = self._tables(x.device)
+        basis, fb, tc = self._tables(x.device)
         out = torch.empty((rows.shape[0], self.n_mels, frames), device=x.device, dtype=torch.float32)
+        if tc is not None:
+            rc = _lib.lib().mpcg_mel_tc_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
+                                            self.k0, self.nbins, self._tc["ncols"], tc[0].data_ptr(), fb.data_ptr(),
+                                            tc[1].data_ptr(), self._tc["inv_norm"], self.n_mels, frames,
+                                            1 if log_map else 0, _lib.stream_ptr(x))
+            if rc != _lib.EUNSUPPORTED:
+                _lib.check(rc, "mel (tensor cores)")
+                return out.reshape(*lead, self.n_mels, frames)
         _lib.check(_lib.lib().mpcg_mel_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
                                            self.n_lo, self.n_hi, self.nbins, self.kpad, basis.data_ptr(),
                                            0 if self.fast else 1, fb.data_ptr(),
@@ -98,9 +138,11 @@ class MelConfig:
     f_max: float = 500.0
 
     def build(self, fast: bool = False) -> MelTransform:
-        """``fast=True`` runs the DFT in float32 (about twice the throughput; error ~1e-7 of a frame's largest
-        bin, which only shows in leakage skirts near the dB map's 1e-5 floor).  The default keeps the contraction
-        in float64 and stays within 1e-5 of the float64 reference on any input."""
+        """``fast=True`` trades exactness in leakage skirts for speed: when ``n_fft`` is a multiple of ``hop_length``
+        and the window spans ``n_fft`` the DFT runs on the tensor cores (tcgen05, split-fp16 operands, fp32
+        accumulation; see csrc/mel_tc.cu), otherwise on the fp32 FMA pipe.  Both resolve a frame's spectrum down to
+        ~1e-6 of its largest bin, which only shows near the dB map's 1e-5 floor on tonal inputs.  The default keeps
+        the contraction in float64 and stays within 1e-5 of the float64 reference on any input."""
         return MelTransform(self.sample_rate, self.n_fft, self.hop_length, self.win_length or self.n_fft, self.n_mels,
                             self.f_min, self.f_max, fast=fast)
 
