@@ -149,3 +149,25 @@ def test_fused_full_size_properties(pkg):
     # unaffected by the other rows: recompute 3 rows alone
     sub = pkg.preprocess_segment(x[5:8].contiguous(), 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True)
     assert torch.equal(sub, w[5:8])
+
+
+@pytest.mark.parametrize("mode", ["torch", "numpy"])
+def test_fast_despike_equals_reference_order(pkg, mode, monkeypatch):
+    """The fused kernel's fast despike path (parallel frames, logged passes, exact handling of stuck frames) must
+    leave exactly the samples and pass counts of its serial path, which replays the reference's order pass by
+    pass (and is the one the trace tests pin to the oracle).  Synthetic PCG rows end stuck about 40 % of the time."""
+    from wav2vec_heart_sounds_b200.synth import synth_pcg
+    spec = pkg.WindowSpec(4.0)
+    for seed, rows, n, fs_in in ((1234, 192, 60000, 2000), (77, 64, 32000, 4000), (5, 32, 9000, 2000)):
+        x = synth_pcg(rows, n, float(fs_in), seed=seed, device="cuda")
+        x[1, 500] += 40.0                                    # one-sample spike: the classic stuck frame
+        x[2, 700:703] -= 35.0
+        x[2, n // 2] += 30.0
+        monkeypatch.delenv("MPCG_FZ_DESPIKE_SERIAL", raising=False)
+        fast, e_fast = pkg.preprocess_segment(x, fs_in, 4125, spec, mode=mode, fused=True, return_edits=True)
+        monkeypatch.setenv("MPCG_FZ_DESPIKE_SERIAL", "1")
+        ser, e_ser = pkg.preprocess_segment(x, fs_in, 4125, spec, mode=mode, fused=True, return_edits=True)
+        monkeypatch.delenv("MPCG_FZ_DESPIKE_SERIAL", raising=False)
+        assert int(e_ser.sum()) > rows                       # the despiker really worked
+        assert torch.equal(e_fast, e_ser)
+        assert torch.equal(fast, ser)

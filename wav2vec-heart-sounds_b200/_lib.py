@@ -7,6 +7,7 @@ library is missing, or a tensor is not a CUDA float32 tensor, the call raises.
 from __future__ import annotations
 
 import ctypes
+import os
 import pathlib
 import subprocess
 
@@ -101,7 +102,8 @@ def lib() -> ctypes.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU or PyTorch fallback for this path)")
-        handle = ctypes.CDLL(str(LIB_PATH))
+        # MPCG_B200_LIB: tools/ only -- load an experimental build of the same ABI (A/B timing of kernel variants)
+        handle = ctypes.CDLL(os.environ.get("MPCG_B200_LIB", str(LIB_PATH)))
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)           # AttributeError here = header and library disagree
             fn.restype = res

@@ -7,9 +7,9 @@
 namespace mpcg {
 #include "fused_instances.h"
 #define MPCG_FZ_EXTERN_(...) MPCG_FZ_EXTERN(__VA_ARGS__)
-#define MPCG_FZ_EXTERN(U, DN, DD, FR, PS) \
-  extern template int fz_launch<U, DN, DD, FR, PS>(const FzParams&, size_t, long long, cudaStream_t);
-MPCG_FZ_EXTERN_(1, 1, 1, 1, 1)
+#define MPCG_FZ_EXTERN(U, DN, DD, PS) \
+  extern template int fz_launch<U, DN, DD, PS>(const FzParams&, size_t, long long, cudaStream_t);
+MPCG_FZ_EXTERN_(1, 1, 1, 1)
 MPCG_FZ_EXTERN_(FZ_I8)
 MPCG_FZ_EXTERN_(FZ_I16)
 MPCG_FZ_EXTERN_(FZ_I32)
@@ -59,7 +59,7 @@ static bool fz_plan_geometry(int t, int win_d, bool frames, FzGeometry* g) {
     c.cap = L * kFzChunks;
     c.q = (c.S - 1) / L;
     c.nq = c.S - c.q * L;
-    c.smem = sizeof(FzShared) + (size_t)(c.cap + 8) * sizeof(float);
+    c.smem = sizeof(FzShared) + (size_t)(c.cap + 2 * kFzGuard + 8) * sizeof(float);
     if (c.smem > 225 * 1024) continue;
     if (c.smem <= fz_smem_target()) { *g = c; return true; }
     if (!have) { best = c; have = true; }
@@ -172,6 +172,10 @@ extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t r
   P.win_d = frames ? (int)d->despike_win : 1; P.nframes = frames ? g.nframes : 0; P.fpc = g.fpc;
   P.threshold = d->despike_threshold; P.max_iter = d->despike_max_iterations; P.median_mode = d->median_mode;
   P.norm_flags = d->norm_flags;
+  {
+    const char* e = getenv("MPCG_FZ_DESPIKE_SERIAL");       // tests: force the reference-order despike path
+    P.serial_despike = (e && atoi(e) != 0) ? 1 : 0;
+  }
   P.start = (int)d->seg_start; P.win = (int)d->seg_win; P.hop = (int)d->seg_hop; P.n = (int)d->seg_n;
   if (d->channels_last) {
     P.so_j = channels; P.so_c = 1; P.so_k = (long long)d->seg_win * channels;
@@ -193,12 +197,12 @@ extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t r
   }
   if (P.max_iter < 0 || (P.median_mode != MPCG_MEDIAN_LOWER && P.median_mode != MPCG_MEDIAN_MEAN)) return MPCG_EINVAL;
 
-  if (identity) return fz_launch<1, 1, 1, 1, 1>(P, g.smem, rows, stream);
+  if (identity) return fz_launch<1, 1, 1, 1>(P, g.smem, rows, stream);
   const int D = d->taps_per_phase;
 #define MPCG_FZ_CASE_(...) MPCG_FZ_CASE(__VA_ARGS__)
-#define MPCG_FZ_CASE(U, DN, DD, FR, PS)                                                              \
+#define MPCG_FZ_CASE(U, DN, DD, PS)                                                                  \
   if (d->up == U && d->down == DN && D == DD && rs_taps_match<U, DN, DD>(d->taps, d->offset))       \
-    return fz_launch<U, DN, DD, FR, PS>(P, g.smem, rows, stream);
+    return fz_launch<U, DN, DD, PS>(P, g.smem, rows, stream);
   MPCG_FZ_CASE_(FZ_I8)
   MPCG_FZ_CASE_(FZ_I16)
   MPCG_FZ_CASE_(FZ_I32)

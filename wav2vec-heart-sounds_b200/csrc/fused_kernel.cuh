@@ -33,13 +33,25 @@ namespace mpcg {
 #ifndef MPCG_FZ_MINBLOCKS
 #define MPCG_FZ_MINBLOCKS 2              // CTAs per SM the register allocation is sized for
 #endif
+#ifndef MPCG_FZ_FILTER_THREADS
+#define MPCG_FZ_FILTER_THREADS 512       // threads that own a filter chunk (the rest idle through the fp64 phases)
+#endif
 constexpr int kFzThreads = MPCG_FZ_THREADS;
 constexpr int kFzWarps = kFzThreads / 32;
-constexpr int kFzChunks = kFzThreads;     // one filter chunk per thread
-constexpr int kFzLmax = 81;               // longest chunk (odd)
+constexpr int kFzChunks = MPCG_FZ_FILTER_THREADS;   // one filter chunk per filter thread
+constexpr int kFzFW = kFzChunks / 32;               // filter warps
+constexpr int kFzLmax = 81 * (512 / kFzChunks) + (512 / kFzChunks - 1);   // longest chunk (odd): 81 / 163
 constexpr int kFzMaxFrames = 64;         // despike frames per row the fused kernel accepts
 constexpr int kFzMaxCluster = 8;
-constexpr int kFzStageWords = 4400;       // resampler input staging (largest instance: 4116 + skew)
+constexpr int kFzStageWords = 4608;       // resampler input staging: teams x buffers x block (largest: 8 x 565)
+constexpr int kFzGuard = 40;              // floats before and after the slice that edge frames may spill into
+// fast despike path (see the kernel): scratch copies of the frames being flattened + per-pass logs
+constexpr int kFzScr = 2;                 // frames in flight per CTA
+constexpr int kFzScrWords = 2112;         // longest despike frame the fast path takes
+constexpr int kFzLogCap = 16;             // passes per frame and round it logs before handing over to the serial path
+constexpr int kFzFastLocal = 16;          // frames per CTA the fast path takes
+static_assert(kFzChunks == 512 || kFzChunks == 256, "filter threads: 512 or 256");
+static_assert(kFzChunks <= kFzThreads, "filter threads are a subset of the CTA");
 
 struct FzKind {                           // per channel kind (PCG / ECG): despike on/off + its filter
   int despike;
@@ -68,6 +80,7 @@ struct FzParams {
   int win_d, nframes, fpc;                // despike frame length, frames per row, frames per CTA
   double threshold;
   int max_iter, median_mode, norm_flags;
+  int serial_despike;                     // 1: always take the serial (reference-order) despike path
   int start, win, hop, n;                 // window geometry
   long long so_b, so_c, so_k, so_j;       // output strides (elements): recording, channel, window, sample
   unsigned char kind_of_channel[8];
@@ -81,24 +94,40 @@ struct FzFilterScratch {                  // this row's recipe, copied from glob
   double prop_slice[16];
   double prop_part[16];
   double c[2][5];
-  double wagg[kFzWarps][4];               // warp aggregates
-  double wcar[kFzWarps][4];               // state at the start of each warp's first chunk (zero slice start)
+  double wagg[kFzFW][4];                  // warp aggregates
+  double wcar[kFzFW][4];                  // state at the start of each warp's first chunk (zero slice start)
 };
 constexpr int kFzMaxBlocks = 1344;        // 32-sample blocks in one slice (kFzLmax * kFzChunks / 32 + frames)
-struct FzDespikeScratch {
+struct FzDespikeScratch {                 // serial path
   SpikeSorted sorted;
   float bmax[kFzMaxBlocks];
 };
+struct FzFastScratch {                    // fast path
+  float scr[kFzScr][kFzScrWords];         // working copies of the frames being flattened
+  float bm[kFzScr][kFzScrWords / 32 + 2]; // their 32-sample block maxima
+  float seq[kFzFastLocal][kFzLogCap + 1];            // MY frames: maximum after j logged passes
+  unsigned short span[kFzFastLocal][kFzLogCap][2];   // MY frames: [lo, hi) of every logged pass
+  float xtop[2][kFzMaxFrames];            // [round parity][slot] maximum the owner ended with   (owner -> every CTA)
+  int xmeta[2][kFzMaxFrames];             // passes | stuck << 8 | log full << 9                 (owner -> every CTA)
+  int xj[kFzMaxFrames];                   // passes that count, per slot, after a stuck round    (owner -> rank 0)
+  unsigned char act_frame[kFzMaxFrames];  // slot -> frame (identical in every CTA)
+  int nact, verdict, total;
+  float cutf;
+  double cutd;
+  unsigned long long kstar;
+};
 struct FzShared {
-  union {                                 // three phases, one after the other, share this space:
+  union {                                 // phases that follow one another share this space:
     float xs[kFzStageWords];              //   resampler input staging
-    FzDespikeScratch d;                   //   despike: block maxima of my frames + sorted frame maxima
+    FzFastScratch df;                     //   despike, fast path
+    FzDespikeScratch d;                   //   despike, serial path: block maxima of my frames + sorted frame maxima
     FzFilterScratch f;                    //   filter recipe tables and scan scratch
   };
   double xE[kFzMaxCluster][4];            // end states exported by each rank
   double xstat[kFzMaxCluster][4];         // (sum, min, max, -) exported by each rank
   double wstat[kFzWarps][4];
-  float tops[2][kFzMaxFrames];            // double-buffered frame maxima (see the despike loop)
+  float tops[2][kFzMaxFrames];            // serial path: double-buffered frame maxima
+  float ftops[kFzMaxFrames];              // fast path: committed frame maxima (identical in every CTA)
   float fscr[40];
   int iscr[64];
   int ctrl[4];                            // (passes, done) published by the round owner, double-buffered
@@ -148,12 +177,75 @@ __device__ __forceinline__ float fz_round(double y, bool fix_nan) {
   return v;
 }
 
-template <int UP, int DOWN, int D, int FR, int PS>
+__device__ __forceinline__ void fz_team_sync(int team, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(count) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long u = __shfl_xor_sync(kFull, v, o);
+    v = u > v ? u : v;
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast despike path, one frame by one warp.  The frame is COPIED to scratch and flattened there pass after pass
+// while its maximum exceeds the round's threshold; every pass logs its span and the maximum it leaves behind.
+// Nothing touches the resident signal here: which of the logged passes the reference's serial order really
+// performs is decided after the cluster has exchanged the logs (see the kernel).
+struct FzCut {                             // "frame maximum exceeds threshold * median" in the oracle's arithmetic
+  int mode;
+  float cutf;                              // tensor path: fp32 product, fp32 compare
+  double cutd;                             // NumPy path: float64 product and compare
+  __device__ __forceinline__ bool exceeds(float top) const {
+    return mode == MPCG_MEDIAN_LOWER ? (top > cutf) : ((double)top > cutd);
+  }
+};
+__device__ __forceinline__ void fz_fast_frame(FzShared& sm, cg::cluster_group& cluster, const float* src, int win,
+                                              int fl, int gframe, int slot, int par, int sidx, int ncl, const FzCut& cut) {
+  const int lane = threadIdx.x & 31;
+  float* scr = sm.df.scr[sidx];
+  float* bm = sm.df.bm[sidx];
+  const int nblk = (win + 31) >> 5;
+  for (int b = 0; b < nblk; ++b) {
+    const int i = b * 32 + lane;
+    const float v = i < win ? src[i] : 0.f;
+    if (i < win) scr[i] = v;
+    const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fabsf(v), 0.f)));   // fmaxf drops NaN
+    if (lane == 0) bm[b] = __uint_as_float(m);
+  }
+  __syncwarp();
+  float top = sm.ftops[gframe];
+  if (lane == 0) sm.df.seq[fl][0] = top;
+  int k = 0, stuck = 0, over = 0;
+  while (cut.exceeds(top)) {
+    if (k == kFzLogCap) { over = 1; break; }
+    int peak, lo, hi;
+    bool changed;
+    float new_top;
+    spike_pass_warp(scr, win, bm, nblk, top, peak, lo, hi, changed, new_top);
+    if (!changed) { stuck = 1; break; }      // a pass that moves nothing: the reference repeats it until max_iterations
+    ++k;
+    top = new_top;
+    if (lane == 0) {
+      sm.df.span[fl][k - 1][0] = (unsigned short)lo;
+      sm.df.span[fl][k - 1][1] = (unsigned short)hi;
+      sm.df.seq[fl][k] = top;
+    }
+  }
+  if (lane < ncl) {
+    *cluster.map_shared_rank(&sm.df.xtop[par][slot], lane) = top;
+    *cluster.map_shared_rank(&sm.df.xmeta[par][slot], lane) = k | (stuck << 8) | (over << 9);
+  }
+}
+
+template <int UP, int DOWN, int D, int PS>
 __global__ void __launch_bounds__(kFzThreads, MPCG_FZ_MINBLOCKS)
 fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   extern __shared__ __align__(16) unsigned char fz_raw[];
   FzShared& sm = *reinterpret_cast<FzShared*>(fz_raw);
-  float* sig = reinterpret_cast<float*>(fz_raw + sizeof(FzShared));
+  float* sig = reinterpret_cast<float*>(fz_raw + sizeof(FzShared)) + kFzGuard;
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster.block_rank();
@@ -174,124 +266,284 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   stamp();                                                // 0: start
 
   // ---------------------------------------------------------------- 1. resample my slice into shared memory
+  // Teams of PS warps walk the slice in blocks of 32 frames: coalesced loads -> registers (prefetched one block
+  // ahead) -> skewed staging -> each warp of the team computes its phase group -> the slice.  Edge frames spill
+  // into the guard floats around the slice instead of being bounds-checked.
   const float* xr = P.x + row * (long long)P.t_in;
   if constexpr (UP == DOWN) {                             // no resampling: plain copy of my slice
     for (int i = tid; i < n; i += kFzThreads) sig[i] = ld_stream(xr + s0 + i);
   } else if (n > 0) {
-    using T = RsTile<UP, DOWN, D, FR, PS, kFzThreads>;
-    static_assert(T::IN_WORDS <= kFzStageWords, "staging buffer too small for this resampler instance");
+    using T = RsTeam<UP, DOWN, D, PS>;
+    constexpr int NTEAMS = kFzWarps / PS;
+    constexpr int NBUF = (NTEAMS * 2 * T::WORDS <= kFzStageWords) ? 2 : 1;
+    static_assert(kFzWarps % PS == 0 && (PS == 1 || NTEAMS <= 15), "teams map onto named barriers 1..15");
+    static_assert(NTEAMS * NBUF * T::WORDS <= kFzStageWords, "staging buffer too small for this resampler instance");
+    static_assert(UP - 1 <= kFzGuard, "guard too small");
+    const int team = warp / PS, grp = warp - team * PS, tt = tid - team * T::TEAM;
+    float* xs_team = sm.xs + team * (NBUF * T::WORDS);
     const int f_lo = s0 / UP, f_hi = (s0 + n - 1) / UP;
+    const int nblk = (f_hi - f_lo + T::FB) / T::FB;
     float pre[T::NPRE];
-    T::fetch(pre, xr, (long long)f_lo * DOWN + P.off, P.t_in);
-    for (int fb = f_lo; fb <= f_hi; fb += T::NF) {
-      T::commit(sm.xs, pre);
-      __syncthreads();
-      if (fb + T::NF <= f_hi) T::fetch(pre, xr, (long long)(fb + T::NF) * DOWN + P.off, P.t_in);   // next tile in flight
-      const int obase = fb * UP - s0;
-      auto sink = [&](int frame, int p, float v) {
-        const int o = obase + frame * UP + p;
-        if ((unsigned)o < (unsigned)n) sig[o] = v;
-      };
-      T::compute(sm.xs, sink);
-      __syncthreads();
+    int blk = team, buf = 0;
+    if (blk < nblk) T::fetch(pre, xr, (long long)(f_lo + blk * T::FB) * DOWN + P.off, P.t_in, tt);
+    for (; blk < nblk; blk += NTEAMS) {
+      float* xs = xs_team + buf * T::WORDS;
+      T::commit(xs, pre, tt);
+      if constexpr (PS == 1) __syncwarp(); else fz_team_sync(team, T::TEAM);
+      if (blk + NTEAMS < nblk)                            // next block's loads fly while this one is computed
+        T::fetch(pre, xr, (long long)(f_lo + (blk + NTEAMS) * T::FB) * DOWN + P.off, P.t_in, tt);
+      const int f = f_lo + blk * T::FB + lane;
+      if (f <= f_hi) T::template dispatch<0>(grp, xs, lane, sig + (f * UP - s0));
+      if constexpr (NBUF == 2) buf ^= 1;
+      else if constexpr (PS == 1) __syncwarp();
+      else fz_team_sync(team, T::TEAM);
     }
   }
-  stamp();                                                // 1: slice resampled
-  for (int i = n + tid; i < P.cap; i += kFzThreads) sig[i] = 0.f;      // chunk grid beyond the slice
-
-  // ---------------------------------------------------------------- filter tables (independent of the samples)
   __syncthreads();
+  stamp();                                                // 1: slice resampled
+  for (int i = n + tid; i < P.cap + kFzGuard; i += kFzThreads) sig[i] = 0.f;      // chunk grid beyond the slice
+  __syncthreads();
+  stamp();                                                // 2: tail cleared
 
-  stamp();                                                // 2: tables ready
   // ---------------------------------------------------------------- 2. Schmidt despike (cluster-wide)
-  // Every CTA keeps two copies of all frame maxima.  Round k reads copy k&1.  Warp 0 of every CTA sorts the
-  // maxima (identical data, identical verdict).  The CTA owning the worst frame then keeps going ON ITS OWN:
-  // flatten, update its local maxima, decide again -- pass after pass with no barrier at all, as long as the
-  // worst frame stays one of its own (a burst is flattened half-cycle by half-cycle, so it usually does).  When
-  // ownership moves (or nothing is left to do) it publishes its frames' maxima and the pass counter into copy
-  // (k+1)&1 of every CTA; the other CTAs carried the remaining entries over locally; one cluster barrier per round.
-  // All other warps only wait at that barrier.
   int passes = 0;
   if (k_despike && P.nframes > 0) {
     const int gf0 = rank * P.fpc;
     int nloc = P.nframes - gf0;
     nloc = nloc < 0 ? 0 : (nloc > P.fpc ? P.fpc : nloc);
-    const int nblk = (P.win_d + 31) >> 5;                   // 32-sample blocks per frame
-    for (int q = warp; q < nloc * nblk; q += kFzWarps) {    // block maxima of my frames
-      const int f = q / nblk, b = q - f * nblk;
-      const int i = b * 32 + lane;
-      const float m = warp_max(i < P.win_d ? fabsf(sig[f * P.win_d + i]) : 0.f);
-      if (lane == 0) sm.d.bmax[q] = m;
-    }
-    __syncthreads();
-    for (int f = warp; f < nloc; f += kFzWarps) {           // frame maxima -> every CTA's copy 0
-      float m = 0.f;
-      for (int b = lane; b < nblk; b += 32) m = fmaxf(m, sm.d.bmax[f * nblk + b]);
-      m = warp_max(m);
-      if (lane < P.ncl) *cluster.map_shared_rank(&sm.tops[0][gf0 + f], lane) = m;
-    }
-    cluster_arrive();
-    cluster_wait();
-    for (int round = 0;; ++round) {
-      float* cur = sm.tops[round & 1];
-      float* nxt = sm.tops[(round + 1) & 1];
-      if (warp == 0) {
-        bool idle = passes >= P.max_iter;                   // budget spent, or (below) nothing exceeds the threshold
-        SpikeDecision dec;
-        dec.active = false; dec.worst = 0;
-        if (!idle) {
-          spike_sort_init(sm.d.sorted, cur, P.nframes);
-          dec = spike_sort_decide(sm.d.sorted, P.nframes, P.threshold, P.median_mode);
-          idle = !dec.active;
+    bool serial = P.serial_despike || P.trace != nullptr || P.win_d > kFzScrWords || P.win_d < 2;
+    // ------------------------------------------------------------ 2a. fast path
+    // The reference flattens one span per pass, always in the frame holding the largest maximum, until no frame
+    // exceeds threshold * median.  A pass only changes its own frame, and the threshold can only fall, so the
+    // ORDER of the passes does not matter for the samples: every frame above the current threshold must be
+    // flattened until it is not, whatever happens elsewhere.  Rounds: (1) every CTA derives the threshold and the
+    // list of frames above it from its copy of the frame maxima; (2) the owners flatten those frames on scratch
+    // copies, in parallel, logging each pass; (3) the outcomes are exchanged (one cluster barrier) and the passes
+    // that the serial order really performs are committed to the signal.  All of them are, except when some frame
+    // got STUCK (a pass that moves nothing, e.g. a one-sample spike between two sign flips: the reference then
+    // repeats that pass until max_iterations): the serial order reaches the stuck state with the largest
+    // (maximum, first index) key K* and never leaves it, so exactly the logged passes that started from a key
+    // above K* happen, and the row is finished.  Anything the logs cannot settle exactly (pass budget in reach,
+    // log full) continues on the serial path from the committed state, which is always a state of the serial order.
+    if (!serial && P.fpc > kFzFastLocal) serial = true;
+    if (!serial) {
+      for (int f = warp; f < nloc; f += kFzWarps) {         // maxima of my frames -> every CTA
+        const float* fr = sig + f * P.win_d;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+        int i = lane;
+        for (; i + 96 < P.win_d; i += 128) {
+          m0 = fmaxf(m0, fabsf(fr[i])); m1 = fmaxf(m1, fabsf(fr[i + 32]));
+          m2 = fmaxf(m2, fabsf(fr[i + 64])); m3 = fmaxf(m3, fabsf(fr[i + 96]));
         }
-        if (lane == 0) sm.decision[round & 1] = idle ? 1 : 0;   // same verdict in every CTA
-        if (!idle) {
-          const int owner = dec.worst / P.fpc;
-          const int of0 = owner * P.fpc;
-          for (int i = lane; i < P.nframes; i += 32)        // carry the other CTAs' entries over locally
-            if (i < of0 || i >= of0 + P.fpc) nxt[i] = cur[i];
-          if (rank == owner) {
-            bool done = false;
-            while (true) {                                  // local passes on my own frames, no barrier
-              const int fl = dec.worst - gf0;
-              const float old_top = cur[dec.worst];
-              int peak, lo, hi;
-              bool changed;
-              float new_top;
-              spike_pass_warp(sig + fl * P.win_d, P.win_d, sm.d.bmax + fl * nblk, nblk, old_top, peak, lo, hi, changed,
-                              new_top);
-              if (lane == 0) {
-                cur[dec.worst] = new_top;
-                if (P.trace && passes < P.trace_cap) {
-                  int* tr = P.trace + (row * P.trace_cap + passes) * 4;
-                  tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
-                }
-              }
-              __syncwarp();
-              ++passes;
-              if (!changed || passes >= P.max_iter) { done = true; break; }   // fixed point / budget
-              spike_sort_update(sm.d.sorted, dec.worst, old_top, new_top);
-              dec = spike_sort_decide(sm.d.sorted, P.nframes, P.threshold, P.median_mode);
-              if (!dec.active) { done = true; break; }
-              if (dec.worst / P.fpc != rank) break;         // somebody else's frame: hand over
-            }
-            for (int f = lane; f < nloc * P.ncl; f += 32) { // publish my frames' maxima to every CTA
-              const int fi = f % nloc, rk = f / nloc;
-              *cluster.map_shared_rank(&nxt[gf0 + fi], rk) = cur[gf0 + fi];
-            }
-            if (lane < P.ncl) {
-              int* c = cluster.map_shared_rank(&sm.ctrl[2 * ((round + 1) & 1)], lane);
-              c[0] = passes;
-              c[1] = done ? 1 : 0;
-            }
-          }
-        }
+        for (; i < P.win_d; i += 32) m0 = fmaxf(m0, fabsf(fr[i]));
+        const float m = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)))));
+        if (lane < P.ncl) *cluster.map_shared_rank(&sm.ftops[gf0 + f], lane) = m;
       }
       cluster_arrive();
       cluster_wait();
-      if (sm.decision[round & 1]) break;                    // nothing to do this round: every CTA stops together
-      passes = sm.ctrl[2 * ((round + 1) & 1)];
-      if (sm.ctrl[2 * ((round + 1) & 1) + 1]) break;
+      for (int round = 0;; ++round) {
+        const int par = round & 1;
+        if (warp == 0) {                                    // threshold + frames above it (same bits in every CTA)
+          const int nf = P.nframes;
+          const float v0 = lane < nf ? sm.ftops[lane] : -1.f, v1 = lane + 32 < nf ? sm.ftops[lane + 32] : -1.f;
+          int less0 = 0, leq0 = 0, less1 = 0, leq1 = 0;
+#pragma unroll 4
+          for (int j = 0; j < nf; ++j) {
+            const float vj = sm.ftops[j];
+            less0 += (vj < v0); leq0 += (vj <= v0);
+            less1 += (vj < v1); leq1 += (vj <= v1);
+          }
+          const int k_lo = (nf - 1) >> 1, k_hi = nf >> 1;
+          float c_lo = -1.f, c_hi = -1.f;                   // maxima are >= 0, so -1 means "not mine"
+          if (lane < nf) {
+            if (less0 <= k_lo && k_lo < leq0) c_lo = v0;
+            if (less0 <= k_hi && k_hi < leq0) c_hi = v0;
+          }
+          if (lane + 32 < nf) {
+            if (less1 <= k_lo && k_lo < leq1) c_lo = fmaxf(c_lo, v1);
+            if (less1 <= k_hi && k_hi < leq1) c_hi = fmaxf(c_hi, v1);
+          }
+          const float lo_mid = warp_max(c_lo), hi_mid = warp_max(c_hi);
+          FzCut cut;
+          cut.mode = P.median_mode;
+          cut.cutf = __fmul_rn((float)P.threshold, lo_mid);
+          const double med = ((double)lo_mid + (double)hi_mid) * 0.5;
+          cut.cutd = P.threshold * med;
+          const bool open = passes < P.max_iter && (P.median_mode == MPCG_MEDIAN_LOWER || med != 0.0);
+          const bool a0 = open && lane < nf && cut.exceeds(v0), a1 = open && lane + 32 < nf && cut.exceeds(v1);
+          const unsigned m0 = __ballot_sync(kFull, a0), m1 = __ballot_sync(kFull, a1);
+          const unsigned below = (1u << lane) - 1u;
+          if (a0) sm.df.act_frame[__popc(m0 & below)] = (unsigned char)lane;
+          if (a1) sm.df.act_frame[__popc(m0) + __popc(m1 & below)] = (unsigned char)(lane + 32);
+          if (lane == 0) { sm.df.nact = __popc(m0) + __popc(m1); sm.df.cutf = cut.cutf; sm.df.cutd = cut.cutd; }
+        }
+        __syncthreads();
+        const int nact = sm.df.nact;
+        if (nact == 0) break;
+        if (warp < kFzScr) {                                // my frames of the list, kFzScr at a time
+          FzCut cut;
+          cut.mode = P.median_mode; cut.cutf = sm.df.cutf; cut.cutd = sm.df.cutd;
+          int ord = 0;
+          for (int slot = 0; slot < nact; ++slot) {
+            const int f = sm.df.act_frame[slot];
+            if (f < gf0 || f >= gf0 + nloc) continue;
+            if ((ord++ % kFzScr) != warp) continue;
+            fz_fast_frame(sm, cluster, sig + (f - gf0) * P.win_d, P.win_d, f - gf0, f, slot, par, warp, P.ncl, cut);
+          }
+        }
+        cluster_arrive();
+        cluster_wait();
+        if (warp == 0) {                                    // the round's outcome (same bits in every CTA)
+          const bool h0 = lane < nact, h1 = lane + 32 < nact;
+          const int me0 = h0 ? sm.df.xmeta[par][lane] : 0, me1 = h1 ? sm.df.xmeta[par][lane + 32] : 0;
+          const bool over = __any_sync(kFull, ((me0 | me1) >> 9) & 1);
+          unsigned long long ks = 0ull;
+          if ((me0 >> 8) & 1) ks = spike_key(sm.df.xtop[par][lane], sm.df.act_frame[lane]);
+          if ((me1 >> 8) & 1) {
+            const unsigned long long k1 = spike_key(sm.df.xtop[par][lane + 32], sm.df.act_frame[lane + 32]);
+            ks = k1 > ks ? k1 : ks;
+          }
+          const unsigned long long kstar = warp_max_u64(ks);
+          int total = (me0 & 0xff) + (me1 & 0xff);
+#pragma unroll
+          for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+          // (with a stuck frame fewer passes may count, plus the stuck pass itself: total + 1 bounds both cases)
+          const bool hand_over = over || (long long)passes + total + (kstar != 0ull ? 1 : 0) > (long long)P.max_iter;
+          if (!hand_over && kstar == 0ull) {
+            if (h0) sm.ftops[sm.df.act_frame[lane]] = sm.df.xtop[par][lane];
+            if (h1) sm.ftops[sm.df.act_frame[lane + 32]] = sm.df.xtop[par][lane + 32];
+          }
+          if (lane == 0) {
+            sm.df.verdict = hand_over ? 2 : (kstar != 0ull ? 1 : 0);
+            sm.df.total = total;
+            sm.df.kstar = kstar;
+          }
+        }
+        __syncthreads();
+        const int verdict = sm.df.verdict;
+        if (verdict == 2) { serial = true; break; }
+        const unsigned long long kstar = sm.df.kstar;
+        for (int slot = warp; slot < nact; slot += kFzWarps) {     // commit my frames' spans to the resident signal
+          const int f = sm.df.act_frame[slot];
+          if (f < gf0 || f >= gf0 + nloc) continue;
+          const int fl = f - gf0;
+          float* fr = sig + fl * P.win_d;
+          const int k = sm.df.xmeta[par][slot] & 0xff;
+          int jc = k;
+          if (verdict == 1) {                               // only passes that started above K* (all of the stuck frame's)
+            if (spike_key(sm.df.seq[fl][k], f) != kstar)
+              jc = __popc(__ballot_sync(kFull, lane < k && spike_key(sm.df.seq[fl][lane < k ? lane : 0], f) > kstar));
+            if (P.edits && lane == 0) *cluster.map_shared_rank(&sm.df.xj[slot], 0) = jc;
+          }
+          for (int j = 0; j < jc; ++j) {
+            const int lo = sm.df.span[fl][j][0], hi = sm.df.span[fl][j][1];
+            for (int i = lo + lane; i < hi; i += 32) fr[i] = kSpikeFill;
+          }
+        }
+        if (verdict == 1) {
+          if (P.edits) {                                    // exact pass count: rank 0 adds up what really counted
+            cluster_arrive();
+            cluster_wait();
+            if (rank == 0 && warp == 0) {
+              int t = (lane < nact ? sm.df.xj[lane] : 0) + (lane + 32 < nact ? sm.df.xj[lane + 32] : 0);
+#pragma unroll
+              for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+              if (lane == 0) sm.df.total = t + 1;           // + the pass that moves nothing
+            }
+            __syncthreads();
+            if (rank == 0) passes += sm.df.total;
+          }
+          break;
+        }
+        passes += sm.df.total;
+        __syncthreads();
+      }
+    }
+    // ------------------------------------------------------------ 2b. serial path (reference order, pass by pass)
+    // Every CTA keeps two copies of all frame maxima.  Round k reads copy k&1.  Warp 0 of every CTA sorts the
+    // maxima (identical data, identical verdict).  The CTA owning the worst frame then keeps going ON ITS OWN:
+    // flatten, update its local maxima, decide again -- pass after pass with no barrier at all, as long as the
+    // worst frame stays one of its own.  When ownership moves (or nothing is left to do) it publishes its frames'
+    // maxima and the pass counter into copy (k+1)&1 of every CTA; one cluster barrier per round.
+    if (serial) {
+      __syncthreads();
+      const int nblk = (P.win_d + 31) >> 5;                   // 32-sample blocks per frame
+      for (int q = warp; q < nloc * nblk; q += kFzWarps) {    // block maxima of my frames
+        const int f = q / nblk, b = q - f * nblk;
+        const int i = b * 32 + lane;
+        const float m = warp_max(i < P.win_d ? fabsf(sig[f * P.win_d + i]) : 0.f);
+        if (lane == 0) sm.d.bmax[q] = m;
+      }
+      __syncthreads();
+      for (int f = warp; f < nloc; f += kFzWarps) {           // frame maxima -> every CTA's copy 0
+        float m = 0.f;
+        for (int b = lane; b < nblk; b += 32) m = fmaxf(m, sm.d.bmax[f * nblk + b]);
+        m = warp_max(m);
+        if (lane < P.ncl) *cluster.map_shared_rank(&sm.tops[0][gf0 + f], lane) = m;
+      }
+      cluster_arrive();
+      cluster_wait();
+      for (int round = 0;; ++round) {
+        float* cur = sm.tops[round & 1];
+        float* nxt = sm.tops[(round + 1) & 1];
+        if (warp == 0) {
+          bool idle = passes >= P.max_iter;                   // budget spent, or (below) nothing exceeds the threshold
+          SpikeDecision dec;
+          dec.active = false; dec.worst = 0;
+          if (!idle) {
+            spike_sort_init(sm.d.sorted, cur, P.nframes);
+            dec = spike_sort_decide(sm.d.sorted, P.nframes, P.threshold, P.median_mode);
+            idle = !dec.active;
+          }
+          if (lane == 0) sm.decision[round & 1] = idle ? 1 : 0;   // same verdict in every CTA
+          if (!idle) {
+            const int owner = dec.worst / P.fpc;
+            const int of0 = owner * P.fpc;
+            for (int i = lane; i < P.nframes; i += 32)        // carry the other CTAs' entries over locally
+              if (i < of0 || i >= of0 + P.fpc) nxt[i] = cur[i];
+            if (rank == owner) {
+              bool done = false;
+              while (true) {                                  // local passes on my own frames, no barrier
+                const int fl = dec.worst - gf0;
+                const float old_top = cur[dec.worst];
+                int peak, lo, hi;
+                bool changed;
+                float new_top;
+                spike_pass_warp(sig + fl * P.win_d, P.win_d, sm.d.bmax + fl * nblk, nblk, old_top, peak, lo, hi, changed,
+                                new_top);
+                if (lane == 0) {
+                  cur[dec.worst] = new_top;
+                  if (P.trace && passes < P.trace_cap) {
+                    int* tr = P.trace + (row * P.trace_cap + passes) * 4;
+                    tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
+                  }
+                }
+                __syncwarp();
+                ++passes;
+                if (!changed || passes >= P.max_iter) { done = true; break; }   // fixed point / budget
+                spike_sort_update(sm.d.sorted, dec.worst, old_top, new_top);
+                dec = spike_sort_decide(sm.d.sorted, P.nframes, P.threshold, P.median_mode);
+                if (!dec.active) { done = true; break; }
+                if (dec.worst / P.fpc != rank) break;         // somebody else's frame: hand over
+              }
+              for (int f = lane; f < nloc * P.ncl; f += 32) { // publish my frames' maxima to every CTA
+                const int fi = f % nloc, rk = f / nloc;
+                *cluster.map_shared_rank(&nxt[gf0 + fi], rk) = cur[gf0 + fi];
+              }
+              if (lane < P.ncl) {
+                int* c = cluster.map_shared_rank(&sm.ctrl[2 * ((round + 1) & 1)], lane);
+                c[0] = passes;
+                c[1] = done ? 1 : 0;
+              }
+            }
+          }
+        }
+        cluster_arrive();
+        cluster_wait();
+        if (sm.decision[round & 1]) break;                    // nothing to do this round: every CTA stops together
+        passes = sm.ctrl[2 * ((round + 1) & 1)];
+        if (sm.ctrl[2 * ((round + 1) & 1) + 1]) break;
+      }
     }
     if (P.edits && rank == 0 && tid == 0) P.edits[row] = passes;
     __syncthreads();
@@ -308,10 +560,13 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   if (tid < 10) (&sm.f.c[0][0])[tid] = (&Kg->c[0][0])[tid];
   __syncthreads();
   // ---------------------------------------------------------------- 3. low-pass + high-pass as one 4-state scan
-  float* mine = sig + tid * L;
+  // (threads beyond kFzChunks own no chunk: their loops are empty and their scan inputs zero)
+  const bool filt = tid < kFzChunks;
+  float* mine = sig + (filt ? tid : 0) * L;
+  const int Lm = filt ? L : 0;
   double p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
-  for (int j = 0; j < L; ++j) {
+  for (int j = 0; j < Lm; ++j) {
     const double2 w01 = *reinterpret_cast<const double2*>(&sm.f.wt[j][0]);
     const double2 w23 = *reinterpret_cast<const double2*>(&sm.f.wt[j][2]);
     const double xv = (double)mine[j];
@@ -338,7 +593,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, p[s], 1 << d);
     if (lane >= (1 << d)) mv4_acc(sm.f.mp[d], u, p);
   }
-  if (lane == 31) {
+  if (lane == 31 && filt) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) sm.f.wagg[warp][s] = p[s];
   }
@@ -346,7 +601,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   if (warp == 0) {                                        // scan the warp aggregates in one warp
     double v[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) v[s] = (lane < kFzWarps) ? sm.f.wagg[lane][s] : 0.0;
+    for (int s = 0; s < 4; ++s) v[s] = (lane < kFzFW) ? sm.f.wagg[lane][s] : 0.0;
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
       double u[4];
@@ -357,7 +612,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const double e = __shfl_up_sync(kFull, v[s], 1);
-      if (lane < kFzWarps) sm.f.wcar[lane][s] = lane ? e : 0.0;
+      if (lane < kFzFW) sm.f.wcar[lane][s] = lane ? e : 0.0;
     }
   }
   __syncthreads();
@@ -371,7 +626,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   {
     double wc[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) wc[s] = sm.f.wcar[warp][s];
+    for (int s = 0; s < 4; ++s) wc[s] = sm.f.wcar[filt ? warp : 0][s];
     mv4_lane_acc(sm.f.mtab, lane, wc, z);                     // chunk start state for a zero slice start
   }
   if (P.ncl > 1) {
@@ -417,18 +672,47 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     kc.b10 = sm.f.c[1][0]; kc.b11 = sm.f.c[1][1]; kc.b12 = sm.f.c[1][2]; kc.a11 = sm.f.c[1][3]; kc.a12 = sm.f.c[1][4];
     const bool fix_nan = (P.norm_flags & MPCG_NORM_NAN_TO_NUM) != 0;
     int lim = n - tid * L;
-    lim = lim < 0 ? 0 : (lim > L ? L : lim);
-    float sacc = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < lim; ++j) {
-      const float v = fz_round(fz_step(kc, z, (double)mine[j]), fix_nan);
-      mine[j] = v;
-      sacc += v;
-      lmin = fminf(lmin, v);
-      lmax = fmaxf(lmax, v);
-      if ((j & 7) == 7) { lsum += (double)sacc; sacc = 0.f; }
+    lim = (lim < 0 || !filt) ? 0 : (lim > L ? L : lim);
+    // The non-finite fix-up of nan_to_num is kept out of the loop: a NaN or infinity anywhere in the chunk turns the
+    // chunk's sum non-finite, which sends this thread through a second sweep below.
+    int j = 0;
+    for (; j + 8 <= lim; j += 8) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float v = (float)fz_step(kc, z, (double)mine[j + u]);
+        mine[j + u] = v;
+        sacc += v;
+        lmin = fminf(lmin, v);
+        lmax = fmaxf(lmax, v);
+      }
+      lsum += (double)sacc;
     }
-    lsum += (double)sacc;
+    {
+      float sacc = 0.f;
+      for (; j < lim; ++j) {
+        const float v = (float)fz_step(kc, z, (double)mine[j]);
+        mine[j] = v;
+        sacc += v;
+        lmin = fminf(lmin, v);
+        lmax = fmaxf(lmax, v);
+      }
+      lsum += (double)sacc;
+    }
+    if (fix_nan && !(fabs(lsum) < (double)INFINITY)) {
+      lsum = 0.0; lmin = INFINITY; lmax = -INFINITY;
+      for (j = 0; j < lim; j += 8) {
+        float sacc = 0.f;
+        for (int u = 0; u < 8 && j + u < lim; ++u) {
+          const float v = fz_round((double)mine[j + u], true);
+          mine[j + u] = v;
+          sacc += v;
+          lmin = fminf(lmin, v);
+          lmax = fmaxf(lmax, v);
+        }
+        lsum += (double)sacc;
+      }
+    }
   }
 
   stamp();                                                // 7: pass 2 done
@@ -465,24 +749,42 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   // ---------------------------------------------------------------- 5. normalise + write my share of every window
   float* obase = P.out + rec * P.so_b + ch * P.so_c;
   const int s1 = s0 + n;
-  for (int k = 0; k < P.n; ++k) {
+  auto scaled = [&](float s) { return fminf(fmaxf(((s - mean_hi) - mean_lo) * inv_f, -1.f), 1.f); };
+  // windows that intersect my slice: k_first .. k_last
+  int k_first = s0 - P.start - P.win + 1;
+  k_first = k_first > 0 ? (k_first + P.hop - 1) / P.hop : 0;
+  int k_last = s1 - 1 - P.start;
+  k_last = k_last < 0 ? -1 : k_last / P.hop;
+  if (k_last > P.n - 1) k_last = P.n - 1;
+  for (int k = k_first; k <= k_last; ++k) {
     const int w0 = P.start + k * P.hop;
     const int a = w0 > s0 ? w0 : s0;
     const int w1 = w0 + P.win;
     const int b = w1 < s1 ? w1 : s1;
-    float* dst = obase + k * P.so_k;
+    const int len = b - a;
+    const float* sp = sig + (a - s0);
     if (P.so_j == 1) {
-      for (int i = a + tid; i < b; i += kFzThreads) {
-        const float u = ((sig[i - s0] - mean_hi) - mean_lo) * inv_f;
-        st_stream(dst + (i - w0), fminf(fmaxf(u, -1.f), 1.f));
+      float* dp = obase + k * P.so_k + (a - w0);
+      int i = tid;
+      for (; i + 3 * kFzThreads < len; i += 4 * kFzThreads) {
+        const float u0 = scaled(sp[i]), u1 = scaled(sp[i + kFzThreads]);
+        const float u2 = scaled(sp[i + 2 * kFzThreads]), u3 = scaled(sp[i + 3 * kFzThreads]);
+        st_stream(dp + i, u0);
+        st_stream(dp + i + kFzThreads, u1);
+        st_stream(dp + i + 2 * kFzThreads, u2);
+        st_stream(dp + i + 3 * kFzThreads, u3);
       }
+      for (; i < len; i += kFzThreads) st_stream(dp + i, scaled(sp[i]));
     } else {
-      for (int i = a + tid; i < b; i += kFzThreads) {
-        const float u = ((sig[i - s0] - mean_hi) - mean_lo) * inv_f;
-        dst[(long long)(i - w0) * P.so_j] = fminf(fmaxf(u, -1.f), 1.f);
-      }
+      float* dp = obase + k * P.so_k + (long long)(a - w0) * P.so_j;
+      for (int i = tid; i < len; i += kFzThreads) dp[(long long)i * P.so_j] = scaled(sp[i]);
     }
-    if (rank == P.ncl - 1 && w1 > P.t) {                  // short recording: zero-fill past its end
+  }
+  if (rank == P.ncl - 1 && P.n > 0 && P.start + (P.n - 1) * P.hop + P.win > P.t) {
+    for (int k = 0; k < P.n; ++k) {                       // short recording: zero-fill past its end
+      const int w0 = P.start + k * P.hop, w1 = w0 + P.win;
+      if (w1 <= P.t) continue;
+      float* dst = obase + k * P.so_k;
       const int z0 = (P.t > w0 ? P.t : w0);
       for (int i = z0 + tid; i < w1; i += kFzThreads) dst[(long long)(i - w0) * P.so_j] = 0.f;
     }
@@ -492,9 +794,9 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   // statistics barrier above, so a CTA may retire while its peers are still storing their windows.
 }
 
-template <int UP, int DOWN, int D, int FR, int PS>
+template <int UP, int DOWN, int D, int PS>
 int fz_launch(const FzParams& P, size_t smem, long long rows, cudaStream_t stream) {
-  auto kern = fused_preprocess_kernel<UP, DOWN, D, FR, PS>;
+  auto kern = fused_preprocess_kernel<UP, DOWN, D, PS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};

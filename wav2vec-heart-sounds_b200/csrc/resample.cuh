@@ -3,10 +3,21 @@
 //   y[i*UP + p] = sum_{d<D} x[i*DOWN + off + d] * G[p][d]
 // Taps are compile-time constants (resample_taps_gen.cuh), so the unrolled loops are FFMA-immediate.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "resample_taps_gen.cuh"
 
 namespace mpcg {
+
+// Compile-time counted loop: f(std::integral_constant<int, I>) for I in [I0, N).  Keeps tap indices constant
+// expressions, so every tap is an instruction immediate and zero taps vanish at compile time.
+template <int I, int N, class F>
+__device__ __forceinline__ void rs_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    rs_for<I + 1, N>(f);
+  }
+}
 
 __host__ __device__ constexpr int rs_skew(int idx, int stride) { return (stride & 1) ? idx : idx + idx / stride; }
 
@@ -37,24 +48,29 @@ struct RsTile {
   static constexpr int PB = 4;
   template <int P0, int P1, class Sink>
   __device__ static __forceinline__ void phases(const float (&in)[PER_THREAD_IN], int frame0, Sink& sink) {
-#pragma unroll
-    for (int fr = 0; fr < FR; ++fr) {
-#pragma unroll
-      for (int p = P0; p < P1; p += PB) {
+    rs_for<0, FR>([&](auto frc) {
+      constexpr int fr = decltype(frc)::value;
+      rs_for<0, (P1 - P0 + PB - 1) / PB>([&](auto gc) {
+        constexpr int p = P0 + decltype(gc)::value * PB;
         float acc[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-#pragma unroll
-          for (int k = 0; k < PB; ++k)
-            if (p + k < P1) acc[k] = fmaf(in[fr * DOWN + d], Taps::tap(p + k < UP ? p + k : 0, d), acc[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < PB; ++k)
-          if (p + k < P1) sink(frame0 + fr, p + k, acc[k]);
-      }
-    }
+        rs_for<0, D>([&](auto dc) {
+          constexpr int d = decltype(dc)::value;
+          rs_for<0, PB>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            if constexpr (p + k < P1) {
+              constexpr float t = Taps::g[p + k][d];
+              if constexpr (t != 0.f) acc[k] = fmaf(in[fr * DOWN + d], t, acc[k]);
+            }
+          });
+        });
+        rs_for<0, PB>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          if constexpr (p + k < P1) sink(frame0 + fr, p + k, acc[k]);
+        });
+      });
+    });
   }
 
   // Register-prefetched staging: issue the global loads for a tile early (fetch), park them in registers
@@ -95,6 +111,101 @@ struct RsTile {
 #pragma unroll
     for (int d = 0; d < PER_THREAD_IN; ++d) in[d] = xs[rs_skew(base + d, SIN)];
     dispatch<0>(grp, in, fi * FR, sink);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Team form used by the fused kernel: a TEAM of PS warps shares one staged block of 32 frames (coalesced global
+// loads -> skewed shared memory); warp g of the team computes phase group g (a contiguous 1/PS share of the UP
+// phases) for the 32 frames, one frame per lane.  Taps are instruction immediates and STRUCTURALLY ZERO TAPS ARE
+// SKIPPED: the Hann-windowed sinc (and the Kaiser polyphase bank) reaches only 12-13 (20-21) of the D columns of
+// the dense frame form per phase, the rest are +-0 in float32 (x * 0 contributes nothing for finite x).
+// Only the input columns a phase group really touches are read from shared memory.
+template <int UP, int DOWN, int D, int PS>
+struct RsTeam {
+  using Taps = BakedTaps<UP, DOWN, D>;
+  static constexpr int FB = 32;                         // frames per block (one per lane)
+  static constexpr int NIN = (FB - 1) * DOWN + D;       // staged inputs per block
+  static constexpr int WORDS = rs_skew(NIN - 1, DOWN) + 1;
+  static constexpr int TEAM = PS * 32;
+  static constexpr int NPRE = (NIN + TEAM - 1) / TEAM;
+  static constexpr int PB = 4;                          // outputs accumulated side by side
+
+  __host__ __device__ static constexpr int p_begin(int g) { return (g * UP) / PS; }
+  __host__ __device__ static constexpr int d_lo(int p0, int p1) {
+    int m = D - 1;
+    for (int p = p0; p < p1; ++p) m = Taps::first[p] < m ? Taps::first[p] : m;
+    return m;
+  }
+  __host__ __device__ static constexpr int d_hi(int p0, int p1) {
+    int m = 0;
+    for (int p = p0; p < p1; ++p) m = Taps::last[p] > m ? Taps::last[p] : m;
+    return m;
+  }
+
+  // inputs [in0, in0 + NIN) of the row -> registers (zero outside the row); tt = thread index inside the team
+  __device__ static __forceinline__ void fetch(float (&pre)[NPRE], const float* __restrict__ x_row, long long in0,
+                                               long long t_in, int tt) {
+    if (in0 >= 0 && in0 + NIN <= t_in) {                // block-uniform: interior block, no bounds checks
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        const int m = tt + k * TEAM;
+        pre[k] = (m < NIN) ? ld_stream(x_row + in0 + m) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        const int m = tt + k * TEAM;
+        const long long src = in0 + m;
+        pre[k] = (m < NIN && src >= 0 && src < t_in) ? ld_stream(x_row + src) : 0.f;
+      }
+    }
+  }
+  __device__ static __forceinline__ void commit(float* xs, const float (&pre)[NPRE], int tt) {
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int m = tt + k * TEAM;
+      if (m < NIN) xs[rs_skew(m, DOWN)] = pre[k];
+    }
+  }
+
+  // phases [P0, P1) of the frame staged at xs[skew(lane*DOWN + d)]; dst[p] receives phase p.
+  template <int P0, int P1>
+  __device__ static __forceinline__ void phases(const float* xs, int lane, float* dst) {
+    constexpr int DLO = d_lo(P0, P1), DHI = d_hi(P0, P1);
+    float in[DHI - DLO + 1];
+    const int base = (DOWN & 1) ? lane * DOWN : lane * (DOWN + 1);   // == rs_skew(lane * DOWN, DOWN)
+    rs_for<DLO, DHI + 1>([&](auto dc) {
+      constexpr int d = decltype(dc)::value;
+      in[d - DLO] = xs[base + rs_skew(d, DOWN)];
+    });
+    rs_for<0, (P1 - P0 + PB - 1) / PB>([&](auto gc) {
+      constexpr int p = P0 + decltype(gc)::value * PB;
+      float acc[PB];
+#pragma unroll
+      for (int k = 0; k < PB; ++k) acc[k] = 0.f;
+      rs_for<DLO, DHI + 1>([&](auto dc) {
+        constexpr int d = decltype(dc)::value;
+        rs_for<0, PB>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          if constexpr (p + k < P1) {
+            constexpr float t = Taps::g[p + k][d];
+            if constexpr (t != 0.f) acc[k] = fmaf(in[d - DLO], t, acc[k]);
+          }
+        });
+      });
+      rs_for<0, PB>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        if constexpr (p + k < P1) dst[p + k] = acc[k];
+      });
+    });
+  }
+  template <int G>
+  __device__ static __forceinline__ void dispatch(int grp, const float* xs, int lane, float* dst) {
+    if constexpr (G < PS) {
+      if (grp == G) phases<p_begin(G), p_begin(G + 1)>(xs, lane, dst);
+      else dispatch<G + 1>(grp, xs, lane, dst);
+    }
   }
 };
 

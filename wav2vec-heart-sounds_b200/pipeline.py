@@ -34,13 +34,17 @@ def _kind_struct(kind: str, fs_out: float, despike: bool) -> _lib.ChainKind:
 
 def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, kinds=None, despike: bool = True,
                        mode: str = "torch", channels_last: bool = False, return_trace: bool = False,
-                       trace_cap: int = 64, fused: bool | None = None, out: torch.Tensor | None = None):
+                       trace_cap: int = 64, fused: bool | None = None, out: torch.Tensor | None = None,
+                       return_edits: bool = False):
     """``[B, T]`` -> ``[B, N, win]``  or  ``[B, C, T]`` -> ``[B, C, N, win]`` (``[B, N, win, C]`` with
     ``channels_last``): resample, (PCG only) Schmidt despike, band-limit, abs-max normalise, segment.
 
     ``kinds``: one of ``"pcg"`` / ``"ecg"`` per channel (default: all ``"pcg"``), e.g. ``("pcg", "ecg")`` for the
     Training-A pair.  ``fused``: ``None`` = fused kernel when the geometry allows, ``True`` = require it,
     ``False`` = always chain the stand-alone kernels.  ``out``: optional preallocated result tensor.
+    ``return_trace``: also return ``(edits[B*C], trace[B*C, cap, 4])``, the despike passes in the reference's order
+    (this takes the fused kernel's serial despike path); ``return_edits``: also return the pass counts alone
+    (fused kernel only; the fast despike path stays on).
     """
     torchproc._check_mode(mode)
     x = _lib.require_cuda_f32(x)
@@ -72,6 +76,10 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
         edits = torch.zeros(b * c, dtype=torch.int32, device=x.device)
         trace = torch.full((b * c, trace_cap, 4), -1, dtype=torch.int32, device=x.device)
 
+    if return_edits and not return_trace:
+        if fused is False:
+            raise ValueError("return_edits without return_trace is a fused-kernel option")
+        edits = torch.zeros(b * c, dtype=torch.int32, device=x.device)
     if fused is not False and c <= 8:
         uniq = sorted(set(kinds))
         if len(uniq) <= 2:
@@ -99,8 +107,10 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
                                                         trace_cap if return_trace else 0, _lib.stream_ptr(v))
             if rc != _lib.EUNSUPPORTED:
                 _lib.check(rc, "fused preprocess+segment")
-                return (out, edits, trace) if return_trace else out
-    if fused is True:
+                if return_trace:
+                    return out, edits, trace
+                return (out, edits) if return_edits else out
+    if fused is True or (return_edits and not return_trace):
         raise ValueError("this geometry does not fit the fused kernel")
 
     # ---- chained stand-alone kernels (same arithmetic, more HBM traffic)
