@@ -35,6 +35,9 @@ __device__ __forceinline__ float4 ld_stream4(const float4* p) {
 __device__ __forceinline__ void st_stream4(float4* p, float4 v) {  // write-once data: evict first
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_stream2(float2* p, float2 v) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }

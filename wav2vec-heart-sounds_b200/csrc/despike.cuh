@@ -234,11 +234,13 @@ __device__ __forceinline__ SpikeDecision spike_sort_decide(const SpikeSorted& sk
   return d;
 }
 
-// One flattening pass on a shared-memory frame by one warp.  bm[0..nblk) are the maxima of its 32-sample blocks
-// and frame_top == max(bm).  Updates fr and bm, returns the integer decisions, whether anything moved, and the
-// frame's new maximum.
-__device__ __forceinline__ void spike_pass_warp(float* fr, int win, float* bm, int nblk, float frame_top, int& peak,
-                                                int& lo, int& hi, bool& changed, float& new_top) {
+// One flattening pass on a shared-memory frame by one warp, in two halves.  bm[0..nblk) are the maxima of the frame's
+// 32-sample blocks and frame_top == max(bm).
+//   spike_find_span: the reference's integer decisions (first arg-max, surrounding strict sign flips -> [lo, hi)).
+//   spike_fill_span: writes the fill, refreshes the touched block maxima, returns whether any sample moved and the
+//                    frame's new maximum.  `undo` (optional) first receives the hi - lo samples it overwrites.
+__device__ __forceinline__ void spike_find_span(const float* fr, int win, const float* bm, int nblk, float frame_top,
+                                                int& peak, int& lo, int& hi) {
   const int lane = threadIdx.x & 31;
   // first block holding the maximum, then the first sample inside it
   int blk = -1;
@@ -269,9 +271,15 @@ __device__ __forceinline__ void spike_pass_warp(float* fr, int win, float* bm, i
   }
   lo = last_before + 1;
   hi = (first_after == 0x7fffffff) ? win - 1 : first_after;
+}
+__device__ __forceinline__ void spike_fill_span(float* fr, int win, float* bm, int nblk, int lo, int hi, bool& changed,
+                                                float& new_top, float* undo = nullptr) {
+  const int lane = threadIdx.x & 31;
   int moved = 0;
   for (int i = lo + lane; i < hi; i += 32) {
-    moved |= (fr[i] != kSpikeFill);
+    const float v = fr[i];
+    if (undo) undo[i - lo] = v;
+    moved |= (v != kSpikeFill);
     fr[i] = kSpikeFill;
   }
   changed = __any_sync(kFull, moved != 0);
@@ -279,14 +287,19 @@ __device__ __forceinline__ void spike_pass_warp(float* fr, int win, float* bm, i
   if (hi > lo) {                                         // refresh the maxima of the blocks the span touched
     for (int b = lo >> 5; b <= ((hi - 1) >> 5); ++b) {
       const int i = b * 32 + lane;
-      const float m = warp_max(i < win ? fabsf(fr[i]) : 0.f);
-      if (lane == 0) bm[b] = m;
+      const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win ? fabsf(fr[i]) : 0.f, 0.f)));
+      if (lane == 0) bm[b] = __uint_as_float(m);
     }
     __syncwarp();
   }
   float m = 0.f;
   for (int b = lane; b < nblk; b += 32) m = fmaxf(m, bm[b]);
-  new_top = warp_max(m);
+  new_top = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(m)));
+}
+__device__ __forceinline__ void spike_pass_warp(float* fr, int win, float* bm, int nblk, float frame_top, int& peak,
+                                                int& lo, int& hi, bool& changed, float& new_top) {
+  spike_find_span(fr, win, bm, nblk, frame_top, peak, lo, hi);
+  spike_fill_span(fr, win, bm, nblk, lo, hi, changed, new_top);
 }
 
 // Flatten the spike in one frame held in shared memory.  Returns (through refs) the integer decisions;

@@ -85,7 +85,8 @@ static int fz_fill_kind(const mpcg_chain_kind& in, const FzGeometry& g, FzKind* 
   bq_mat_pow(A, g.L, k->mp[0]);
   for (int d = 1; d < 10; ++d) bq_mat_mul(k->mp[d - 1], k->mp[d - 1], k->mp[d]);
   for (int l = 0; l < 32; ++l) bq_mat_pow(k->mp[0], l, k->mlane[l]);
-  bq_mat_pow(A, g.S, k->prop_slice);
+  for (int j = 0; j < kFzMaxCluster; ++j) bq_mat_pow(A, (long long)g.S * j, k->prop_pow[j]);
+  for (int w = 0; w < kFzFW; ++w) bq_mat_pow(k->mp[0], 32LL * w, k->mwarp[w]);
   bq_mat_pow(A, g.nq, k->prop_part);
   return MPCG_OK;
 }

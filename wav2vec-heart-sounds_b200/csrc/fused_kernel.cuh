@@ -18,6 +18,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include "resample.cuh"
 #include "biquad.cuh"
@@ -46,8 +47,8 @@ constexpr int kFzMaxCluster = 8;
 constexpr int kFzStageWords = 4608;       // resampler input staging: teams x buffers x block (largest: 8 x 565)
 constexpr int kFzGuard = 40;              // floats before and after the slice that edge frames may spill into
 // fast despike path (see the kernel): scratch copies of the frames being flattened + per-pass logs
-constexpr int kFzScr = 2;                 // frames in flight per CTA
 constexpr int kFzScrWords = 2112;         // longest despike frame the fast path takes
+constexpr int kFzUndoWords = 3072;        // per-CTA pool for the samples the fast path's passes overwrite
 constexpr int kFzLogCap = 16;             // passes per frame and round it logs before handing over to the serial path
 constexpr int kFzFastLocal = 16;          // frames per CTA the fast path takes
 static_assert(kFzChunks == 512 || kFzChunks == 256, "filter threads: 512 or 256");
@@ -59,9 +60,10 @@ struct FzKind {                           // per channel kind (PCG / ECG): despi
   double c[2][5];                         // two sections, b0 b1 b2 a1 a2
   double wt[kFzLmax][4];                  // A^(L-1-j) B
   double mp[10][16];                      // M^(2^d), d = 0..9, M = A^L  (d >= 5 move whole warps)
-  double prop_slice[16];                  // A^S: state across one full slice
+  double prop_pow[kFzMaxCluster][16];     // (A^S)^j, j = 0..7: state across j full slices
   double prop_part[16];                   // A^nq: state across the valid part of the last chunk of a full slice
   double mlane[32][16];                   // M^lane, lane = 0..31
+  double mwarp[kFzFW][16];                // M^(32 w), w = filter warp
 };
 
 struct FzParams {
@@ -91,8 +93,9 @@ struct FzFilterScratch {                  // this row's recipe, copied from glob
   double mtab[16][32];                    // M^lane, element-major so a warp's loads are conflict-free
   double wt[kFzLmax][4];                  // pass-1 weights
   double mp[10][16];                      // M^(2^d)
-  double prop_slice[16];
+  double prop_pow[kFzMaxCluster][16];
   double prop_part[16];
+  double mwarp[kFzFW][16];
   double c[2][5];
   double wagg[kFzFW][4];                  // warp aggregates
   double wcar[kFzFW][4];                  // state at the start of each warp's first chunk (zero slice start)
@@ -103,18 +106,22 @@ struct FzDespikeScratch {                 // serial path
   float bmax[kFzMaxBlocks];
 };
 struct FzFastScratch {                    // fast path
-  float scr[kFzScr][kFzScrWords];         // working copies of the frames being flattened
-  float bm[kFzScr][kFzScrWords / 32 + 2]; // their 32-sample block maxima
+  float undo[kFzUndoWords];               // overwritten samples of this round's passes (so that passes can be taken back)
+  float bm[kFzFastLocal][kFzScrWords / 32 + 2];      // MY frames being flattened: 32-sample block maxima
   float seq[kFzFastLocal][kFzLogCap + 1];            // MY frames: maximum after j logged passes
-  unsigned short span[kFzFastLocal][kFzLogCap][2];   // MY frames: [lo, hi) of every logged pass
+  unsigned short span[kFzFastLocal][kFzLogCap][3];   // MY frames: [lo, hi) and undo offset of every logged pass
   float xtop[2][kFzMaxFrames];            // [round parity][slot] maximum the owner ended with   (owner -> every CTA)
   int xmeta[2][kFzMaxFrames];             // passes | stuck << 8 | log full << 9                 (owner -> every CTA)
   int xj[kFzMaxFrames];                   // passes that count, per slot, after a stuck round    (owner -> rank 0)
   unsigned char act_frame[kFzMaxFrames];  // slot -> frame (identical in every CTA)
-  int nact, verdict, total;
-  float cutf;
+  int nact, verdict, total, undo_used;
+  float cutf, lo_mid, hi_mid;
   double cutd;
   unsigned long long kstar;
+};
+struct FzWarpStat {
+  double sum;
+  float lo, hi;
 };
 struct FzShared {
   union {                                 // phases that follow one another share this space:
@@ -124,8 +131,7 @@ struct FzShared {
     FzFilterScratch f;                    //   filter recipe tables and scan scratch
   };
   double xE[kFzMaxCluster][4];            // end states exported by each rank
-  double xstat[kFzMaxCluster][4];         // (sum, min, max, -) exported by each rank
-  double wstat[kFzWarps][4];
+  FzWarpStat xstat[kFzMaxCluster][kFzWarps];   // (sum, min, max) of every warp of every rank (each rank holds a copy)
   float tops[2][kFzMaxFrames];            // serial path: double-buffered frame maxima
   float ftops[kFzMaxFrames];              // fast path: committed frame maxima (identical in every CTA)
   float fscr[40];
@@ -190,10 +196,10 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fast despike path, one frame by one warp.  The frame is COPIED to scratch and flattened there pass after pass
-// while its maximum exceeds the round's threshold; every pass logs its span and the maximum it leaves behind.
-// Nothing touches the resident signal here: which of the logged passes the reference's serial order really
-// performs is decided after the cluster has exchanged the logs (see the kernel).
+// Fast despike path, one frame by one warp.  The frame is flattened IN PLACE pass after pass while its maximum
+// exceeds the round's threshold; every pass logs its span, the maximum it leaves behind and the samples it
+// overwrote.  Which of the logged passes the reference's serial order really performs is decided after the
+// cluster has exchanged the outcomes (see the kernel); the others are taken back from the undo log.
 struct FzCut {                             // "frame maximum exceeds threshold * median" in the oracle's arithmetic
   int mode;
   float cutf;                              // tensor path: fp32 product, fp32 compare
@@ -202,18 +208,23 @@ struct FzCut {                             // "frame maximum exceeds threshold *
     return mode == MPCG_MEDIAN_LOWER ? (top > cutf) : ((double)top > cutd);
   }
 };
-__device__ __forceinline__ void fz_fast_frame(FzShared& sm, cg::cluster_group& cluster, const float* src, int win,
-                                              int fl, int gframe, int slot, int par, int sidx, int ncl, const FzCut& cut) {
+__device__ __forceinline__ void fz_fast_frame(FzShared& sm, cg::cluster_group& cluster, float* fr, int win, int fl,
+                                              int gframe, int slot, int par, int ncl, const FzCut& cut) {
   const int lane = threadIdx.x & 31;
-  float* scr = sm.df.scr[sidx];
-  float* bm = sm.df.bm[sidx];
+  float* bm = sm.df.bm[fl];
   const int nblk = (win + 31) >> 5;
-  for (int b = 0; b < nblk; ++b) {
-    const int i = b * 32 + lane;
-    const float v = i < win ? src[i] : 0.f;
-    if (i < win) scr[i] = v;
-    const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fabsf(v), 0.f)));   // fmaxf drops NaN
-    if (lane == 0) bm[b] = __uint_as_float(m);
+  for (int b0 = 0; b0 < nblk; b0 += 4) {                    // block maxima, four blocks in flight
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = (b0 + u) * 32 + lane;
+      v[u] = i < win ? fabsf(fr[i]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(v[u], 0.f)));   // fmaxf drops NaN
+      if (lane == 0 && b0 + u < nblk) bm[b0 + u] = __uint_as_float(m);
+    }
   }
   __syncwarp();
   float top = sm.ftops[gframe];
@@ -222,15 +233,21 @@ __device__ __forceinline__ void fz_fast_frame(FzShared& sm, cg::cluster_group& c
   while (cut.exceeds(top)) {
     if (k == kFzLogCap) { over = 1; break; }
     int peak, lo, hi;
+    spike_find_span(fr, win, bm, nblk, top, peak, lo, hi);
+    int off = 0;
+    if (lane == 0) off = atomicAdd(&sm.df.undo_used, hi - lo);
+    off = __shfl_sync(kFull, off, 0);
+    if (off + (hi - lo) > kFzUndoWords) { over = 1; break; }   // pool exhausted: the pass is not performed
     bool changed;
     float new_top;
-    spike_pass_warp(scr, win, bm, nblk, top, peak, lo, hi, changed, new_top);
+    spike_fill_span(fr, win, bm, nblk, lo, hi, changed, new_top, sm.df.undo + off);
     if (!changed) { stuck = 1; break; }      // a pass that moves nothing: the reference repeats it until max_iterations
     ++k;
     top = new_top;
     if (lane == 0) {
       sm.df.span[fl][k - 1][0] = (unsigned short)lo;
       sm.df.span[fl][k - 1][1] = (unsigned short)hi;
+      sm.df.span[fl][k - 1][2] = (unsigned short)off;
       sm.df.seq[fl][k] = top;
     }
   }
@@ -249,9 +266,9 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster.block_rank();
-  const long long row = blockIdx.x / P.ncl;
-  const int ch = (int)(row % P.channels);
-  const long long rec = row / P.channels;
+  const unsigned row = blockIdx.x / (unsigned)P.ncl;     // (the launcher keeps rows * cluster below 2^31)
+  const int ch = (int)(row % (unsigned)P.channels);
+  const long long rec = row / (unsigned)P.channels;
   const FzKind* __restrict__ Kg = P.kinds + P.kind_of_channel[ch];
   const int k_despike = Kg->despike;
   const int s0 = rank * P.S;
@@ -269,7 +286,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   // Teams of PS warps walk the slice in blocks of 32 frames: coalesced loads -> registers (prefetched one block
   // ahead) -> skewed staging -> each warp of the team computes its phase group -> the slice.  Edge frames spill
   // into the guard floats around the slice instead of being bounds-checked.
-  const float* xr = P.x + row * (long long)P.t_in;
+  const float* xr = P.x + (long long)row * P.t_in;
   if constexpr (UP == DOWN) {                             // no resampling: plain copy of my slice
     for (int i = tid; i < n; i += kFzThreads) sig[i] = ld_stream(xr + s0 + i);
   } else if (n > 0) {
@@ -375,20 +392,23 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
           const unsigned below = (1u << lane) - 1u;
           if (a0) sm.df.act_frame[__popc(m0 & below)] = (unsigned char)lane;
           if (a1) sm.df.act_frame[__popc(m0) + __popc(m1 & below)] = (unsigned char)(lane + 32);
-          if (lane == 0) { sm.df.nact = __popc(m0) + __popc(m1); sm.df.cutf = cut.cutf; sm.df.cutd = cut.cutd; }
+          if (lane == 0) {
+            sm.df.nact = __popc(m0) + __popc(m1); sm.df.cutf = cut.cutf; sm.df.cutd = cut.cutd;
+            sm.df.lo_mid = lo_mid; sm.df.hi_mid = hi_mid; sm.df.undo_used = 0;
+          }
         }
         __syncthreads();
         const int nact = sm.df.nact;
         if (nact == 0) break;
-        if (warp < kFzScr) {                                // my frames of the list, kFzScr at a time
+        {                                                   // my frames of the list, one warp each
           FzCut cut;
           cut.mode = P.median_mode; cut.cutf = sm.df.cutf; cut.cutd = sm.df.cutd;
           int ord = 0;
           for (int slot = 0; slot < nact; ++slot) {
             const int f = sm.df.act_frame[slot];
             if (f < gf0 || f >= gf0 + nloc) continue;
-            if ((ord++ % kFzScr) != warp) continue;
-            fz_fast_frame(sm, cluster, sig + (f - gf0) * P.win_d, P.win_d, f - gf0, f, slot, par, warp, P.ncl, cut);
+            if ((ord++ % kFzWarps) != warp) continue;
+            fz_fast_frame(sm, cluster, sig + (f - gf0) * P.win_d, P.win_d, f - gf0, f, slot, par, P.ncl, cut);
           }
         }
         cluster_arrive();
@@ -409,37 +429,44 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
           for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
           // (with a stuck frame fewer passes may count, plus the stuck pass itself: total + 1 bounds both cases)
           const bool hand_over = over || (long long)passes + total + (kstar != 0ull ? 1 : 0) > (long long)P.max_iter;
+          // If no flattened frame fell below the old middle value(s), the median and with it the threshold are what
+          // they were: nothing else can exceed it and the row is finished without another round.
+          const float floor_v = P.median_mode == MPCG_MEDIAN_LOWER ? sm.df.lo_mid : sm.df.hi_mid;
+          const bool same_median = __all_sync(kFull, (!h0 || sm.df.xtop[par][lane] >= floor_v) &&
+                                                         (!h1 || sm.df.xtop[par][lane + 32] >= floor_v));
           if (!hand_over && kstar == 0ull) {
             if (h0) sm.ftops[sm.df.act_frame[lane]] = sm.df.xtop[par][lane];
             if (h1) sm.ftops[sm.df.act_frame[lane + 32]] = sm.df.xtop[par][lane + 32];
           }
           if (lane == 0) {
-            sm.df.verdict = hand_over ? 2 : (kstar != 0ull ? 1 : 0);
+            sm.df.verdict = hand_over ? 2 : (kstar != 0ull ? 1 : (same_median ? 3 : 0));
             sm.df.total = total;
             sm.df.kstar = kstar;
           }
         }
         __syncthreads();
         const int verdict = sm.df.verdict;
-        if (verdict == 2) { serial = true; break; }
         const unsigned long long kstar = sm.df.kstar;
-        for (int slot = warp; slot < nact; slot += kFzWarps) {     // commit my frames' spans to the resident signal
+        for (int slot = warp; slot < nact; slot += kFzWarps) {     // take back my frames' passes that do not happen
           const int f = sm.df.act_frame[slot];
           if (f < gf0 || f >= gf0 + nloc) continue;
           const int fl = f - gf0;
           float* fr = sig + fl * P.win_d;
           const int k = sm.df.xmeta[par][slot] & 0xff;
           int jc = k;
+          if (verdict == 2) jc = 0;                         // the serial path restarts from the committed state
           if (verdict == 1) {                               // only passes that started above K* (all of the stuck frame's)
             if (spike_key(sm.df.seq[fl][k], f) != kstar)
               jc = __popc(__ballot_sync(kFull, lane < k && spike_key(sm.df.seq[fl][lane < k ? lane : 0], f) > kstar));
             if (P.edits && lane == 0) *cluster.map_shared_rank(&sm.df.xj[slot], 0) = jc;
           }
-          for (int j = 0; j < jc; ++j) {
-            const int lo = sm.df.span[fl][j][0], hi = sm.df.span[fl][j][1];
-            for (int i = lo + lane; i < hi; i += 32) fr[i] = kSpikeFill;
+          for (int j = k - 1; j >= jc; --j) {               // newest first: spans of later passes may cover earlier fills
+            const int lo = sm.df.span[fl][j][0], hi = sm.df.span[fl][j][1], off = sm.df.span[fl][j][2];
+            for (int i = lo + lane; i < hi; i += 32) fr[i] = sm.df.undo[off + i - lo];
+            __syncwarp();
           }
         }
+        if (verdict == 2) { serial = true; break; }
         if (verdict == 1) {
           if (P.edits) {                                    // exact pass count: rank 0 adds up what really counted
             cluster_arrive();
@@ -456,6 +483,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
           break;
         }
         passes += sm.df.total;
+        if (verdict == 3) break;
         __syncthreads();
       }
     }
@@ -514,7 +542,7 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
                 if (lane == 0) {
                   cur[dec.worst] = new_top;
                   if (P.trace && passes < P.trace_cap) {
-                    int* tr = P.trace + (row * P.trace_cap + passes) * 4;
+                    int* tr = P.trace + ((long long)row * P.trace_cap + passes) * 4;
                     tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
                   }
                 }
@@ -556,7 +584,9 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   for (int i = tid; i < 512; i += kFzThreads) sm.f.mtab[i & 15][i >> 4] = (&Kg->mlane[0][0])[i];
   for (int i = tid; i < L * 4; i += kFzThreads) (&sm.f.wt[0][0])[i] = (&Kg->wt[0][0])[i];
   for (int i = tid; i < 160; i += kFzThreads) (&sm.f.mp[0][0])[i] = (&Kg->mp[0][0])[i];
-  if (tid < 16) { sm.f.prop_slice[tid] = Kg->prop_slice[tid]; sm.f.prop_part[tid] = Kg->prop_part[tid]; }
+  for (int i = tid; i < kFzMaxCluster * 16; i += kFzThreads) (&sm.f.prop_pow[0][0])[i] = (&Kg->prop_pow[0][0])[i];
+  for (int i = tid; i < kFzFW * 16; i += kFzThreads) (&sm.f.mwarp[0][0])[i] = (&Kg->mwarp[0][0])[i];
+  if (tid < 16) sm.f.prop_part[tid] = Kg->prop_part[tid];
   if (tid < 10) (&sm.f.c[0][0])[tid] = (&Kg->c[0][0])[tid];
   __syncthreads();
   // ---------------------------------------------------------------- 3. low-pass + high-pass as one 4-state scan
@@ -576,15 +606,20 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     p[3] = fma(w23.y, xv, p[3]);
   }
   stamp();                                                // 4: pass 1 done
+  // zero-state response of the partial last chunk of a full slice (the piece of E that the scan does not give):
+  // the exporting thread's whole warp shares the dot product
   const bool exporter = (P.ncl > 1) && (rank < P.ncl - 1) && (tid == P.q);
   double pp[4] = {0.0, 0.0, 0.0, 0.0};
-  if (exporter) {                                         // zero-state response of the partial last chunk
+  if ((P.ncl > 1) && (rank < P.ncl - 1) && (warp == (P.q >> 5))) {
+    const float* qs = sig + P.q * L;
     const int shift = L - P.nq;
-    for (int j = 0; j < P.nq; ++j) {
-      const double xv = (double)mine[j];
+    for (int j = lane; j < P.nq; j += 32) {
+      const double xv = (double)qs[j];
 #pragma unroll
       for (int s = 0; s < 4; ++s) pp[s] = fma(sm.f.wt[j + shift][s], xv, pp[s]);
     }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) pp[s] = warp_sum(pp[s]);
   }
 #pragma unroll
   for (int d = 0; d < 5; ++d) {                           // inclusive scan inside the warp
@@ -641,24 +676,22 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     }
     cluster_arrive();
     cluster_wait();
-    // true slice start state c_(r+1) = A^S c_r + E_r, then carried to my chunk: M^(32*warp + lane)
-    double c[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int r = 0; r < rank; ++r) {
-      double nx[4];
+    // true slice start state c_rank = sum_k (A^S)^(rank-1-k) E_k (independent products, two accumulators),
+    // then carried to my chunk: M^lane (M^(32 warp) c)
+    double c0[4] = {0.0, 0.0, 0.0, 0.0}, c1[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < rank; r += 2) {
+      double e0[4], e1[4];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) nx[s] = sm.xE[r][s];
-      mv4_acc(sm.f.prop_slice, c, nx);
-#pragma unroll
-      for (int s = 0; s < 4; ++s) c[s] = nx[s];
+      for (int s = 0; s < 4; ++s) { e0[s] = sm.xE[r][s]; e1[s] = (r + 1 < rank) ? sm.xE[r + 1][s] : 0.0; }
+      mv4_acc(sm.f.prop_pow[rank - 1 - r], e0, c0);
+      if (r + 1 < rank) mv4_acc(sm.f.prop_pow[rank - 2 - r], e1, c1);
     }
+    double c[4];
+    {
+      double cs[4];
 #pragma unroll
-    for (int d = 0; d < 5; ++d) {
-      if ((warp >> d) & 1) {
-        double nx[4];
-        mv4_set(sm.f.mp[5 + d], c, nx);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) c[s] = nx[s];
-      }
+      for (int s = 0; s < 4; ++s) cs[s] = c0[s] + c1[s];
+      mv4_set(sm.f.mwarp[filt ? warp : 0], cs, c);
     }
     mv4_lane_acc(sm.f.mtab, lane, c, z);
   }
@@ -679,12 +712,15 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     for (; j + 8 <= lim; j += 8) {
       float sacc = 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float v = (float)fz_step(kc, z, (double)mine[j + u]);
-        mine[j + u] = v;
-        sacc += v;
-        lmin = fminf(lmin, v);
-        lmax = fmaxf(lmax, v);
+      for (int u = 0; u < 8; u += 2) {
+        const float v0 = (float)fz_step(kc, z, (double)mine[j + u]);
+        const float v1 = (float)fz_step(kc, z, (double)mine[j + u + 1]);
+        mine[j + u] = v0;
+        mine[j + u + 1] = v1;
+        sacc += v0;
+        sacc += v1;
+        lmin = fminf(lmin, fminf(v0, v1));                // three-input min / max
+        lmax = fmaxf(lmax, fmaxf(v0, v1));
       }
       lsum += (double)sacc;
     }
@@ -717,33 +753,39 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
 
   stamp();                                                // 7: pass 2 done
   // ---------------------------------------------------------------- 4. row statistics across the cluster
+  // every warp hands its (sum, min, max) straight to every rank; after ONE cluster barrier warp 0 folds the
+  // cluster's ncl x warps partials (fixed order: bit-reproducible)
   lsum = warp_sum(lsum);
   lmin = warp_min(lmin);
   lmax = warp_max(lmax);
-  if (lane == 0) { sm.wstat[warp][0] = lsum; sm.wstat[warp][1] = (double)lmin; sm.wstat[warp][2] = (double)lmax; }
-  __syncthreads();
-  if (tid < P.ncl) {
-    double a = 0.0, b = INFINITY, c = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < kFzWarps; ++w) { a += sm.wstat[w][0]; b = fmin(b, sm.wstat[w][1]); c = fmax(c, sm.wstat[w][2]); }
-    double* dst = cluster.map_shared_rank(&sm.xstat[rank][0], tid);
-    dst[0] = a; dst[1] = b; dst[2] = c;
+  if (lane < P.ncl) {
+    FzWarpStat* dst = cluster.map_shared_rank(&sm.xstat[rank][warp], lane);
+    dst->sum = lsum; dst->lo = lmin; dst->hi = lmax;
   }
   cluster_arrive();
   cluster_wait();
-  double tot = 0.0, lo_all = INFINITY, hi_all = -INFINITY;
-  for (int r = 0; r < P.ncl; ++r) {
-    tot += sm.xstat[r][0];
-    lo_all = fmin(lo_all, sm.xstat[r][1]);
-    hi_all = fmax(hi_all, sm.xstat[r][2]);
+  if (warp == 0) {                                        // one warp turns the cluster's statistics into the map
+    double tot = 0.0;
+    float lo_f = INFINITY, hi_f = -INFINITY;
+    const FzWarpStat* all = &sm.xstat[0][0];
+    for (int e = lane; e < P.ncl * kFzWarps; e += 32) {
+      tot += all[e].sum;
+      lo_f = fminf(lo_f, all[e].lo);
+      hi_f = fmaxf(hi_f, all[e].hi);
+    }
+    tot = warp_sum(tot);
+    const double lo_all = (double)warp_min(lo_f), hi_all = (double)warp_max(hi_f);
+    const double mean = tot / (double)P.t;
+    const double peak = fmax(hi_all - mean, mean - lo_all);
+    double inv_peak;
+    if (P.norm_flags & MPCG_NORM_PEAK_GT0) inv_peak = (peak > 0.0) ? 1.0 / peak : 1.0;
+    else inv_peak = 1.0 / fmax(peak, 1e-12);
+    // fp32 map: the mean is split hi + lo so (s - hi) - lo carries no cancellation error
+    const float mh = (float)mean;
+    if (lane == 0) { sm.fscr[0] = mh; sm.fscr[1] = (float)(mean - (double)mh); sm.fscr[2] = (float)inv_peak; }
   }
-  const double mean = tot / (double)P.t;
-  const double peak = fmax(hi_all - mean, mean - lo_all);
-  double inv_peak;
-  if (P.norm_flags & MPCG_NORM_PEAK_GT0) inv_peak = (peak > 0.0) ? 1.0 / peak : 1.0;
-  else inv_peak = 1.0 / fmax(peak, 1e-12);
-  // fp32 map: the mean is split hi + lo so (s - hi) - lo carries no cancellation error
-  const float mean_hi = (float)mean, mean_lo = (float)(mean - (double)mean_hi), inv_f = (float)inv_peak;
+  __syncthreads();
+  const float mean_hi = sm.fscr[0], mean_lo = sm.fscr[1], inv_f = sm.fscr[2];
 
   stamp();                                                // 8: statistics exchanged
   // ---------------------------------------------------------------- 5. normalise + write my share of every window
@@ -765,16 +807,35 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
     const float* sp = sig + (a - s0);
     if (P.so_j == 1) {
       float* dp = obase + k * P.so_k + (a - w0);
-      int i = tid;
-      for (; i + 3 * kFzThreads < len; i += 4 * kFzThreads) {
-        const float u0 = scaled(sp[i]), u1 = scaled(sp[i + kFzThreads]);
-        const float u2 = scaled(sp[i + 2 * kFzThreads]), u3 = scaled(sp[i + 3 * kFzThreads]);
-        st_stream(dp + i, u0);
-        st_stream(dp + i + kFzThreads, u1);
-        st_stream(dp + i + 2 * kFzThreads, u2);
-        st_stream(dp + i + 3 * kFzThreads, u3);
+      // 64-bit stores: one head element if dp is odd, pairs, one tail element
+      int head = (int)((reinterpret_cast<uintptr_t>(dp) >> 2) & 1u);
+      if (head > len) head = len;
+      if (head && tid == 0) st_stream(dp, scaled(sp[0]));
+      const int npair = (len - head) >> 1;
+      const float* sq = sp + head;
+      float2* dq = reinterpret_cast<float2*>(dp + head);
+      if ((reinterpret_cast<uintptr_t>(sq) & 7u) == 0) {    // shared side aligned too: 64-bit loads
+        const float2* sq2 = reinterpret_cast<const float2*>(sq);
+        int i = tid;
+        for (; i + kFzThreads < npair; i += 2 * kFzThreads) {
+          const float2 p0 = sq2[i], p1 = sq2[i + kFzThreads];
+          st_stream2(dq + i, make_float2(scaled(p0.x), scaled(p0.y)));
+          st_stream2(dq + i + kFzThreads, make_float2(scaled(p1.x), scaled(p1.y)));
+        }
+        for (; i < npair; i += kFzThreads) {
+          const float2 p0 = sq2[i];
+          st_stream2(dq + i, make_float2(scaled(p0.x), scaled(p0.y)));
+        }
+      } else {
+        int i = tid;
+        for (; i + kFzThreads < npair; i += 2 * kFzThreads) {
+          const float a0 = sq[2 * i], a1 = sq[2 * i + 1], b0 = sq[2 * (i + kFzThreads)], b1 = sq[2 * (i + kFzThreads) + 1];
+          st_stream2(dq + i, make_float2(scaled(a0), scaled(a1)));
+          st_stream2(dq + i + kFzThreads, make_float2(scaled(b0), scaled(b1)));
+        }
+        for (; i < npair; i += kFzThreads) st_stream2(dq + i, make_float2(scaled(sq[2 * i]), scaled(sq[2 * i + 1])));
       }
-      for (; i < len; i += kFzThreads) st_stream(dp + i, scaled(sp[i]));
+      if (((len - head) & 1) && tid == 32) st_stream(dp + len - 1, scaled(sp[len - 1]));
     } else {
       float* dp = obase + k * P.so_k + (long long)(a - w0) * P.so_j;
       for (int i = tid; i < len; i += kFzThreads) dp[(long long)i * P.so_j] = scaled(sp[i]);
@@ -804,13 +865,21 @@ int fz_launch(const FzParams& P, size_t smem, long long rows, cudaStream_t strea
   cfg.blockDim = dim3(kFzThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)P.ncl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (const char* e = getenv("MPCG_FZ_CLUSTER_POLICY")) {   // experiments: 1 = spread, 2 = load balancing
+    const int v = atoi(e);
+    if (v == 1 || v == 2) {
+      attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+      attr[1].val.clusterSchedulingPolicyPreference = v == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyLoadBalancing;
+      cfg.numAttrs = 2;
+    }
+  }
   e = cudaLaunchKernelEx(&cfg, kern, P);
   if (e != cudaSuccess) return (int)e;
   return MPCG_OK;
