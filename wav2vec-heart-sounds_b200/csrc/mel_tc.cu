@@ -24,7 +24,7 @@
 
 namespace mpcg {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 512;            // 16 warps: TMEM lane quarter = warp & 3, column share = warp >> 2
 constexpr int kTcRows = 128;                 // hop rows per tile = UMMA M
 
 struct MelTcArgs {
@@ -86,6 +86,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ float mel_log_map(float mel) {
   const float db = 20.f * log10f(fmaxf(mel, 1e-5f)) - 20.f;
   return fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
@@ -105,6 +115,7 @@ mel_tc_kernel(const MelTcArgs a) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);         // 8 B
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8);
   float* twq = reinterpret_cast<float*>(tail + 16);           // [Q][2]
+  float* fbs = reinterpret_cast<float*>(tail + 16 + 64);      // [nbins][n_mels4] filterbank, rows padded to 4 mels
   float* stage = reinterpret_cast<float*>(tc_smem);           // [128][N + 1], reuses the A region after the MMAs
   const int nb2 = a.nbins + 2;
   const int srow = N + 1;
@@ -119,6 +130,11 @@ mel_tc_kernel(const MelTcArgs a) {
     for (int i = tid; i < (2 * b_bytes) / 16; i += kTcThreads) dst[i] = __ldg(src + i);
   }
   if (tid < 2 * Q) twq[tid] = a.twq[tid];
+  const int nm4 = (a.n_mels + 3) & ~3;
+  for (int i = tid; i < a.nbins * nm4; i += kTcThreads) {
+    const int k = i / nm4, m = i - k * nm4;
+    fbs[i] = m < a.n_mels ? a.fb[(long long)k * a.n_mels + m] : 0.f;
+  }
   if (tid == 0) mbar_init(mbar, 1);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
@@ -145,11 +161,13 @@ mel_tc_kernel(const MelTcArgs a) {
     // ---- A tile: 128 hop rows x hop samples, split into fp16 hi / lo, canonical core-matrix order
     const int chunks_per_row = hop >> 3;
     const int nchunks = kTcRows * chunks_per_row;
+    const bool cpr_pow2 = (chunks_per_row & (chunks_per_row - 1)) == 0;
+    const int cpr_shift = 31 - __clz(chunks_per_row);
     for (int idx = tid; idx < nchunks; idx += kTcThreads) {
       const int r8 = idx & 7;
       const int rest = idx >> 3;
-      const int jc = rest % chunks_per_row;
-      const int g8 = rest / chunks_per_row;
+      const int g8 = cpr_pow2 ? (rest >> cpr_shift) : rest / chunks_per_row;
+      const int jc = rest - g8 * chunks_per_row;
       const int g = g8 * 8 + r8;
       const long long s0 = (long long)(g0 + g) * hop - pad + jc * 8;    // first un-padded sample index of the chunk
       float v[8];
@@ -198,50 +216,65 @@ mel_tc_kernel(const MelTcArgs a) {
     mbar_wait(mbar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- accumulator -> shared staging (A is dead now): row = TMEM lane, N columns
+    // ---- accumulator -> shared staging (A is dead now): row = TMEM lane, N columns.  A warp reaches the 32 TMEM
+    //      lanes of quarter (warp & 3); the four warps of a quarter share its columns in chunks of eight.
     {
-      const int r = warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
+      const int quarter = warp & 3;
+      const int r = quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = (warp >> 2) * 8; c0 < N; c0 += 8 * (kTcThreads / 128)) {
+        float v[8];
+        tmem_ld8(taddr + (uint32_t)c0, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) stage[r * srow + c0 + e] = v[e];
+        for (int e = 0; e < 8; ++e) stage[r * srow + c0 + e] = v[e];
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- frame spectra: twiddle sum over the Q hop rows, Hann in the frequency domain, magnitude
-    if (tid < fpt) {
-      const int f = tid;
-      float pre = 0.f, pim = 0.f, cre = 0.f, cim = 0.f;       // previous and current rectangular-window bins
-      for (int b = 0; b < nb2; ++b) {
+    // ---- frame spectra: twiddle sum over the Q hop rows, Hann in the frequency domain, magnitude.
+    //      One item = (frame f, output bin kb); frames run fastest so staging reads walk rows (odd stride).
+    for (int item = tid; item < fpt * a.nbins; item += kTcThreads) {
+      const int kb = item / fpt, f = item - kb * fpt;
+      float re[3], im[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int b = kb + j;                                 // rectangular-window bin k0 - 1 + b
         const int k = a.k0 - 1 + b;
-        float re = 0.f, im = 0.f;
+        int m = 0;                                            // (k * q) mod Q, stepped
+        const int kq = ((k % Q) + Q) % Q;
+        float sr = 0.f, si = 0.f;
         for (int q = 0; q < Q; ++q) {
-          const int m = (int)(((long long)k * q) % Q + Q) % Q;
           const float wr = twq[2 * m], wi = twq[2 * m + 1];
           const float pr = stage[(f + q) * srow + b], pi = stage[(f + q) * srow + nb2 + b];
-          re = fmaf(wr, pr, fmaf(-wi, pi, re));
-          im = fmaf(wr, pi, fmaf(wi, pr, im));
+          sr = fmaf(wr, pr, fmaf(-wi, pi, sr));
+          si = fmaf(wr, pi, fmaf(wi, pr, si));
+          m += kq;
+          if (m >= Q) m -= Q;
         }
-        if (b >= 2) {                                         // bins b-2, b-1, b known: output bin index b-1 (interior)
-          const float xr2 = 0.5f * cre - 0.25f * (pre + re), xi2 = 0.5f * cim - 0.25f * (pim + im);
-          mags[f * (a.nbins + 1) + (b - 2)] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
-        }
-        pre = cre; pim = cim; cre = re; cim = im;
+        re[j] = sr; im[j] = si;
       }
+      const float xr2 = 0.5f * re[1] - 0.25f * (re[0] + re[2]), xi2 = 0.5f * im[1] - 0.25f * (im[0] + im[2]);
+      mags[f * (a.nbins + 1) + kb] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
     }
     __syncthreads();
-    // ---- mel projection, dB map, store (lanes run over frames: contiguous stores)
-    for (int o = tid; o < a.n_mels * kTcRows; o += kTcThreads) {
-      const int m = o / kTcRows, f = o - m * kTcRows;
+    // ---- mel projection, dB map, store: one item = (frame, four mels); frames run fastest (contiguous stores)
+    for (int item = tid; item < fpt * (nm4 >> 2); item += kTcThreads) {
+      const int mg4 = item / fpt, f = item - mg4 * fpt;
       const int fg = g0 + f;
-      if (f >= fpt || fg >= a.frames) continue;
+      if (fg >= a.frames) continue;
       const float* mg = mags + f * (a.nbins + 1);
-      float acc = 0.f;
-      for (int k = 0; k < a.nbins; ++k) acc = fmaf(__ldg(a.fb + (long long)k * a.n_mels + m), mg[k], acc);
-      a.out[(row * a.n_mels + m) * a.frames + fg] = a.log_map ? mel_log_map(acc) : acc;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < a.nbins; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(fbs + k * nm4 + 4 * mg4);
+        const float v = mg[k];
+        acc[0] = fmaf(w.x, v, acc[0]); acc[1] = fmaf(w.y, v, acc[1]);
+        acc[2] = fmaf(w.z, v, acc[2]); acc[3] = fmaf(w.w, v, acc[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = 4 * mg4 + e;
+        if (m < a.n_mels) a.out[((long long)row * a.n_mels + m) * a.frames + fg] = a.log_map ? mel_log_map(acc[e]) : acc[e];
+      }
     }
     __syncthreads();                                          // staging / mags are reused by the next tile's A
   }
@@ -270,7 +303,7 @@ extern "C" int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t
   const size_t a_bytes = (size_t)kTcRows * hop * 2, b_bytes = (size_t)ncols * hop * 2;
   const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * (nbins + 1) * 4;
   if (stage_bytes > 2 * a_bytes) return MPCG_EUNSUPPORTED;
-  const size_t smem = 2 * a_bytes + 2 * b_bytes + 16 + 2 * 8 * sizeof(float) + 64;
+  const size_t smem = 2 * a_bytes + 2 * b_bytes + 16 + 64 + (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + 64;
   if (smem > 227 * 1024) return MPCG_EUNSUPPORTED;
   MelTcArgs a;
   a.x = x; a.out = out; a.basis = (const __half*)basis_f16; a.fb = fb; a.twq = twq; a.t = t; a.rows = rows;
