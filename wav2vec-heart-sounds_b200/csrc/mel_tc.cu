@@ -14,7 +14,10 @@
 // accumulate in fp32 in TMEM: ~2^-22 relative, i.e. fp32-class.  This is the `fast` tier of MelConfig.build():
 // like the fp32 FMA path it resolves leakage skirts only down to ~1e-6 of a frame's largest rectangular-window bin.
 //
-// One persistent CTA per SM (128 threads).  Per tile of 128 hop rows: threads load + split the samples straight
+// Tiles are cut from the CONCATENATED hop rows of all signals (frames + Q - 1 per signal), fpt = 128 - (Q - 1)
+// frames each, so a signal's last frames share a tile with the next signal's first ones instead of leaving a
+// nearly empty tile per signal; frames that would straddle two signals are simply not stored.
+// One persistent CTA per SM (512 threads).  Per tile of 128 hop rows: threads load + split the samples straight
 // into the canonical K-major (no swizzle) core-matrix layout, one elected thread issues 3 * hop/16 tcgen05.mma
 // (M=128, N<=256, K=16) into a TMEM accumulator, a tcgen05.commit on an mbarrier signals completion, four warps
 // pull the accumulator back with tcgen05.ld, and the epilogue (twiddle sum, Hann, magnitude, mel projection, dB
@@ -34,7 +37,8 @@ struct MelTcArgs {
   const float* fb;         // [nbins][n_mels]
   const float* twq;        // [Q][2] cos, sin of -2 pi m / Q
   long long t, rows;
-  int n_fft, hop, Q, k0, nbins, N, n_mels, frames, log_map, tiles_per_row;
+  int n_fft, hop, Q, k0, nbins, N, n_mels, frames, log_map, rps;   // rps: hop rows per signal
+  long long total_tiles;
   float inv_norm;
 };
 
@@ -115,11 +119,14 @@ mel_tc_kernel(const MelTcArgs a) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);         // 8 B
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8);
   float* twq = reinterpret_cast<float*>(tail + 16);           // [Q][2]
-  float* fbs = reinterpret_cast<float*>(tail + 16 + 64);      // [nbins][n_mels4] filterbank, rows padded to 4 mels
+  int* row_sig = reinterpret_cast<int*>(tail + 16 + 64);      // [128] signal of each hop row of the tile (-1: none)
+  int* row_loc = row_sig + kTcRows;                           // [128] its hop-row index inside that signal
+  float* fbs = reinterpret_cast<float*>(row_loc + kTcRows);   // [nbins][n_mels4] filterbank, rows padded to 4 mels
   float* stage = reinterpret_cast<float*>(tc_smem);           // [128][N + 1], reuses the A region after the MMAs
   const int nb2 = a.nbins + 2;
   const int srow = N + 1;
-  float* mags = stage + kTcRows * srow;                       // [FPT][nbins + 1]
+  const int mstride = (a.nbins + 1) | 1;                      // odd: frames run across lanes
+  float* mags = stage + kTcRows * srow;                       // [FPT][mstride]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fpt = kTcRows - (Q - 1);                          // frames per tile
 
@@ -150,14 +157,19 @@ mel_tc_kernel(const MelTcArgs a) {
   const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
   const uint32_t sbo = (uint32_t)hop * 16u;                   // bytes between 8-row groups: (hop/8) core matrices of 128 B
   const int pad = a.n_fft / 2;
-  const long long total_tiles = (long long)a.rows * a.tiles_per_row;
+  const long long total_tiles = a.total_tiles;
+  const bool q_pow2 = (Q & (Q - 1)) == 0;
   uint32_t phase = 0;
 
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const long long row = tile / a.tiles_per_row;
-    const int trow = (int)(tile - row * a.tiles_per_row);
-    const int g0 = trow * fpt;                                // first hop row (= first frame) of this tile
-    const float* xr = a.x + row * a.t;
+    const long long G0 = tile * fpt;                          // first global hop row (= first frame slot) of this tile
+    if (tid < kTcRows) {
+      const long long G = G0 + tid;
+      const long long sg = G / a.rps;
+      row_sig[tid] = sg < a.rows ? (int)sg : -1;
+      row_loc[tid] = (int)(G - sg * a.rps);
+    }
+    __syncthreads();
     // ---- A tile: 128 hop rows x hop samples, split into fp16 hi / lo, canonical core-matrix order
     const int chunks_per_row = hop >> 3;
     const int nchunks = kTcRows * chunks_per_row;
@@ -169,9 +181,14 @@ mel_tc_kernel(const MelTcArgs a) {
       const int g8 = cpr_pow2 ? (rest >> cpr_shift) : rest / chunks_per_row;
       const int jc = rest - g8 * chunks_per_row;
       const int g = g8 * 8 + r8;
-      const long long s0 = (long long)(g0 + g) * hop - pad + jc * 8;    // first un-padded sample index of the chunk
+      const int sg = row_sig[g];
+      const float* xr = a.x + (long long)(sg < 0 ? 0 : sg) * a.t;
+      const long long s0 = (long long)row_loc[g] * hop - pad + jc * 8;  // first un-padded sample index of the chunk
       float v[8];
-      if (s0 >= 0 && s0 + 7 < a.t && ((((uintptr_t)(xr + s0)) & 15u) == 0)) {
+      if (sg < 0 || s0 >= a.t + pad) {                        // past the last signal / past the reflected tail
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      } else if (s0 >= 0 && s0 + 7 < a.t && ((((uintptr_t)(xr + s0)) & 15u) == 0)) {
         const float4 p0 = __ldg(reinterpret_cast<const float4*>(xr + s0));
         const float4 p1 = __ldg(reinterpret_cast<const float4*>(xr + s0 + 4));
         v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
@@ -233,15 +250,18 @@ mel_tc_kernel(const MelTcArgs a) {
     __syncthreads();
     // ---- frame spectra: twiddle sum over the Q hop rows, Hann in the frequency domain, magnitude.
     //      One item = (frame f, output bin kb); frames run fastest so staging reads walk rows (odd stride).
-    for (int item = tid; item < fpt * a.nbins; item += kTcThreads) {
-      const int kb = item / fpt, f = item - kb * fpt;
+    {
+    int kb = tid / fpt, f = tid - kb * fpt;                   // item = kb * fpt + f, stepped without divisions
+    const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
+    for (; kb < a.nbins; kb += dk, f += df) {
+      if (f >= fpt) { f -= fpt; ++kb; if (kb >= a.nbins) break; }
       float re[3], im[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int b = kb + j;                                 // rectangular-window bin k0 - 1 + b
         const int k = a.k0 - 1 + b;
         int m = 0;                                            // (k * q) mod Q, stepped
-        const int kq = ((k % Q) + Q) % Q;
+        const int kq = q_pow2 ? (k & (Q - 1)) : ((k % Q) + Q) % Q;
         float sr = 0.f, si = 0.f;
         for (int q = 0; q < Q; ++q) {
           const float wr = twq[2 * m], wi = twq[2 * m + 1];
@@ -254,15 +274,20 @@ mel_tc_kernel(const MelTcArgs a) {
         re[j] = sr; im[j] = si;
       }
       const float xr2 = 0.5f * re[1] - 0.25f * (re[0] + re[2]), xi2 = 0.5f * im[1] - 0.25f * (im[0] + im[2]);
-      mags[f * (a.nbins + 1) + kb] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
+      mags[f * mstride + kb] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
+    }
     }
     __syncthreads();
     // ---- mel projection, dB map, store: one item = (frame, four mels); frames run fastest (contiguous stores)
-    for (int item = tid; item < fpt * (nm4 >> 2); item += kTcThreads) {
-      const int mg4 = item / fpt, f = item - mg4 * fpt;
-      const int fg = g0 + f;
-      if (fg >= a.frames) continue;
-      const float* mg = mags + f * (a.nbins + 1);
+    {
+    int mg4 = tid / fpt, f = tid - mg4 * fpt;
+    const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
+    for (; mg4 < (nm4 >> 2); mg4 += dk, f += df) {
+      if (f >= fpt) { f -= fpt; ++mg4; if (mg4 >= (nm4 >> 2)) break; }
+      const int sg = row_sig[f], fg = row_loc[f];             // frame slot f = hop row f of the tile
+      if (sg < 0 || fg >= a.frames) continue;
+      const long long row = sg;
+      const float* mg = mags + f * mstride;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = 0; k < a.nbins; ++k) {
         const float4 w = *reinterpret_cast<const float4*>(fbs + k * nm4 + 4 * mg4);
@@ -275,6 +300,7 @@ mel_tc_kernel(const MelTcArgs a) {
         const int m = 4 * mg4 + e;
         if (m < a.n_mels) a.out[((long long)row * a.n_mels + m) * a.frames + fg] = a.log_map ? mel_log_map(acc[e]) : acc[e];
       }
+    }
     }
     __syncthreads();                                          // staging / mags are reused by the next tile's A
   }
@@ -301,21 +327,23 @@ extern "C" int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t
   if (t <= n_fft / 2) return MPCG_EINVAL;
   const int fpt = kTcRows - (Q - 1);
   const size_t a_bytes = (size_t)kTcRows * hop * 2, b_bytes = (size_t)ncols * hop * 2;
-  const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * (nbins + 1) * 4;
+  const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * ((nbins + 1) | 1) * 4;
   if (stage_bytes > 2 * a_bytes) return MPCG_EUNSUPPORTED;
-  const size_t smem = 2 * a_bytes + 2 * b_bytes + 16 + 64 + (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + 64;
+  const size_t smem = 2 * a_bytes + 2 * b_bytes + 16 + 64 + 2 * kTcRows * sizeof(int) +
+                      (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + 64;
   if (smem > 227 * 1024) return MPCG_EUNSUPPORTED;
   MelTcArgs a;
   a.x = x; a.out = out; a.basis = (const __half*)basis_f16; a.fb = fb; a.twq = twq; a.t = t; a.rows = rows;
   a.n_fft = n_fft; a.hop = hop; a.Q = Q; a.k0 = k0; a.nbins = nbins; a.N = ncols; a.n_mels = n_mels;
   a.frames = (int)frames; a.log_map = log_map; a.inv_norm = inv_norm;
-  a.tiles_per_row = (int)((frames + fpt - 1) / fpt);
+  a.rps = (int)frames + Q - 1;
+  a.total_tiles = ((long long)rows * a.rps + fpt - 1) / fpt;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t e = cudaFuncSetAttribute(mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const long long total = (long long)rows * a.tiles_per_row;
+  const long long total = a.total_tiles;
   const int grid = (int)(total < sms ? total : sms);
   mel_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a);
   MPCG_LAUNCH_CHECK();
