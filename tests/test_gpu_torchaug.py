@@ -172,3 +172,35 @@ def test_mix_noise_arithmetic(ta):
         assert rel_err(got[r].cpu().numpy(), want) < 1e-5
     out = ta.mix_noise(torch.from_numpy(x).cuda(), torch.from_numpy(bank).cuda())          # random draws
     assert out.shape == (3, 4000) and float(out.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("t,rows", [(64000, 24), (8250, 40), (12347, 16), (133000, 5), (600, 9)])
+@pytest.mark.parametrize("noise", [None, "philox"])
+def test_fused_chain_equals_stage_kernels(ta, t, rows, noise):
+    """The one-kernel chain (rows resident in cluster shared memory) against the kernel-per-stage path on the same
+    random draws: the per-element arithmetic is the same, only the summation order of the row means differs, so the
+    two agree to float32 rounding (1e-6 of the [-1, 1] range).  Covers 1-, 2-, 4- and 8-CTA clusters, ragged tails,
+    rows with every mask on and with every mask off."""
+    from wav2vec_heart_sounds_b200 import AugmentConfig
+    g = torch.Generator(device="cuda").manual_seed(t)
+    x = torch.randn(rows, t, device="cuda", generator=g) * 0.3 + torch.sin(torch.arange(t, device="cuda") / 37.0)[None]
+    for cfg in (AugmentConfig(), AugmentConfig(prob_noise=4.0, prob_wandering_volume=1.0, prob_banding=1.0),
+                AugmentConfig(prob_noise=0.0, prob_wandering_volume=0.0, prob_banding=0.0)):
+        outs = []
+        for fused, collapse in ((True, True), (True, False), (False, False)):
+            torch.manual_seed(3); np.random.seed(3)
+            outs.append(ta.augment_pcg_batch(x, 4125, cfg, noise=noise, fused=fused, collapse=collapse))
+        assert torch.isfinite(outs[0]).all()
+        assert float((outs[1] - outs[2]).abs().max()) < 2e-6       # every stage re-normalised: float32 rounding apart
+        assert float((outs[0] - outs[2]).abs().max()) < 4e-6       # idempotent re-normalisations collapsed
+
+
+def test_fused_chain_rejects_rows_beyond_a_cluster(ta):
+    x = torch.randn(2, 140000, device="cuda")
+    with pytest.raises(ValueError):
+        ta.augment_pcg_batch(x, 4125, fused=True)
+    torch.manual_seed(1); np.random.seed(1)
+    a = ta.augment_pcg_batch(x, 4125)                      # falls back to the stage kernels
+    torch.manual_seed(1); np.random.seed(1)
+    b = ta.augment_pcg_batch(x, 4125, fused=False)
+    assert torch.equal(a, b)

@@ -191,12 +191,19 @@ def parametric_eq(x: torch.Tensor, fs: float, low: float, high: float, num_bands
 
 
 def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None, *, draws: dict | None = None,
-                      noise: str | None = None) -> torch.Tensor:
+                      noise: str | None = None, fused: bool | None = None, collapse: bool = True) -> torch.Tensor:
     """Noise -> wandering volume -> EQ -> noise, each behind a per-row Bernoulli mask, every row re-normalised
-    after every stage (reference torchaug.py:103-111).  Each stage is one fused kernel (transform + blend +
-    normalise).  ``draws`` injects every random quantity (keys as in ``oracle.torch_path.augment_pcg_batch``)."""
+    after every stage (reference torchaug.py:103-111).  ``draws`` injects every random quantity (keys as in
+    ``oracle.torch_path.augment_pcg_batch``); ``noise="philox"`` draws the white noise inside the kernel.
+
+    ``fused``: ``None`` = the one-kernel chain (rows resident in cluster shared memory, read once and written once)
+    when a row fits an 8-CTA cluster, ``True`` = require it, ``False`` = one kernel per stage (transform + blend +
+    normalise each).  Both paths consume the random draws in the reference's order and perform the same arithmetic.
+    ``collapse`` (fused path): a stage whose mask is off for a row does not normalise the already normalised row a
+    second time -- ``N(N(x)) == N(x)`` up to float32 rounding (~1e-7 of the [-1, 1] range, far inside the 1e-5
+    tolerance) -- which saves that stage's sweep and its cluster exchange; ``False`` re-normalises every time."""
     cfg = cfg or AugmentConfig()
-    x = _normalise(_rows2d(x))
+    x = _rows2d(x)
     b, dev = x.shape[0], x.device
     d = draws or {}
 
@@ -204,19 +211,51 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
         m = d.get(key)
         return _mask(b, prob, dev).reshape(b) if m is None else _dev_f32(m, dev, (b,))
 
-    def noise_stage(x, i, mask_key):
+    def noise_draws(i, mask_key):
         rowp, nz = _draw_noise(x, d.get(f"std{i}"), d.get(f"scale{i}"), d.get(f"noise{i}", noise))
         seed, sid = _philox_key() if nz is None else (0, 0)
-        return _stage(x, _lib.AUG_NOISE, rowp=rowp, noise=nz, mask=mask_of(mask_key, cfg.prob_noise / 4),
-                      normalise=True, seed=seed, stream_id=sid)
+        return rowp, nz, seed, sid, mask_of(mask_key, cfg.prob_noise / 4)
 
-    x = noise_stage(x, 1, "mask1")
-    rowp = _draw_sines(x, 0.24, d.get("amp"), d.get("freq"), d.get("phase"))
-    x = _stage(x, _lib.AUG_SINE_MUL, fs=fs, rowp=rowp, mask=mask_of("mask2", cfg.prob_wandering_volume), normalise=True)
-    bands = _draw_bands(2, 500, 5, d.get("bands"))
-    m3 = mask_of("mask3", cfg.prob_banding)
+    if fused is not False and x.shape[1] > 0 and b > 0:
+        # every draw first (reference order), then one launch
+        rowp1, nz1, seed1, sid1, m1 = noise_draws(1, "mask1")
+        rowp2 = _draw_sines(x, 0.24, d.get("amp"), d.get("freq"), d.get("phase"))
+        m2 = mask_of("mask2", cfg.prob_wandering_volume)
+        bands = _draw_bands(2, 500, 5, d.get("bands"))
+        m3 = mask_of("mask3", cfg.prob_banding)
+        rowp4, nz4, seed4, sid4, m4 = noise_draws(2, "mask4")
+        sos = np.ascontiguousarray(design.eq_band_sos(fs, bands), dtype=np.float64)
+        out = torch.empty_like(x)
+        rc = _lib.lib().mpcg_aug_chain_f32(x.data_ptr(), out.data_ptr(), b, x.shape[1], float(fs), rowp1.data_ptr(),
+                                           _lib.ptr(nz1), m1.data_ptr(), seed1, sid1, rowp2.data_ptr(), m2.data_ptr(),
+                                           sos.ctypes.data, sos.shape[0], m3.data_ptr(), rowp4.data_ptr(), _lib.ptr(nz4),
+                                           m4.data_ptr(), seed4, sid4, 1 if collapse else 0, _lib.stream_ptr(x))
+        if rc != _lib.EUNSUPPORTED:
+            _lib.check(rc, "fused augmentation chain")
+            return out
+        if fused is True:
+            raise ValueError("rows of this length do not fit the fused augmentation kernel")
+        # (the draws above are reused below so the random stream is consumed once)
+        pre = dict(n1=(rowp1, nz1, seed1, sid1, m1), rowp2=rowp2, m2=m2, bands=bands, m3=m3, n4=(rowp4, nz4, seed4, sid4, m4))
+    else:
+        if fused is True:
+            raise ValueError("nothing to fuse for an empty batch")
+        pre = None
+
+    x = _normalise(x)
+
+    def noise_stage(x, i, mask_key, key):
+        rowp, nz, seed, sid, m = pre[key] if pre else noise_draws(i, mask_key)
+        return _stage(x, _lib.AUG_NOISE, rowp=rowp, noise=nz, mask=m, normalise=True, seed=seed, stream_id=sid)
+
+    x = noise_stage(x, 1, "mask1", "n1")
+    rowp = pre["rowp2"] if pre else _draw_sines(x, 0.24, d.get("amp"), d.get("freq"), d.get("phase"))
+    m2 = pre["m2"] if pre else mask_of("mask2", cfg.prob_wandering_volume)
+    x = _stage(x, _lib.AUG_SINE_MUL, fs=fs, rowp=rowp, mask=m2, normalise=True)
+    bands = pre["bands"] if pre else _draw_bands(2, 500, 5, d.get("bands"))
+    m3 = pre["m3"] if pre else mask_of("mask3", cfg.prob_banding)
     x = _eq_mix(x, _coloured(x, fs, bands, m3), m3, False)
-    x = noise_stage(x, 2, "mask4")
+    x = noise_stage(x, 2, "mask4", "n4")
     return x
 
 
