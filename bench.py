@@ -14,6 +14,8 @@ A step = one pass of the hot path over that batch.
              timed region.
   roofline   algorithmic bytes of the fused kernel (input read once + windows written once) / its measured
              duration, against the measured HBM peak in MEASURED_PEAKS.json.
+  other_paths   (N=1) kernel times of the fused augmentation chain (configs[2]) and the tensor-core log-mel
+             (configs[3]) at their BASELINE.json shapes, measured outside the timed region.
   cpu_baseline  the NumPy oracle (the reference's CPU algorithm, restated in oracle/numpy_path.py) timed on the
              box's host cores on a bounded sample of the same workload (rank 0, N=1 only).
 
@@ -264,8 +266,10 @@ def run_ours(args):
                         "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "matches_device_run": same},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": recorded_traffic(), "algorithmic_bytes_per_launch": algo_bytes,
-                             "kernel": "fused_preprocess_kernel<33,16,30,1,2>", "peak_source": peak_src},
+                             "kernel": "fused_preprocess_kernel<33,16,30,4>", "peak_source": peak_src},
                 "clocks": clocks.summary()}
+        if world == 1 and not args.no_extras:
+            line["other_paths"] = other_paths(dev, peak)
         if world == 1 and not args.no_cpu:
             cores = host_cores()
             n = min(RECORDINGS, 40 * cores)                   # ~10 s of wall clock on the host cores
@@ -278,6 +282,63 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def other_paths(dev, peak):
+    """Outside the timed region, N=1 only: kernel times of the two other hot-path families at BASELINE.json's
+    configs[2] and configs[3] shapes (CUDA events, best of 5, inputs resident), for the record beside the headline."""
+    import numpy as np
+    from wav2vec_heart_sounds_b200 import torchaug as ta, AugmentConfig, MelConfig, log_mel, _lib, design
+
+    def best_ms(fn, reps=5):
+        fn(); fn(); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    res = {}
+    # configs[2]: full torchaug chain on 4096 windows x 64000 samples @ 16 kHz, in-kernel Philox noise, default masks
+    b, t, fs = 4096, 64000, 16000
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(b, t, device=dev, generator=g)
+    torch.manual_seed(7); np.random.seed(7)
+    cfg = AugmentConfig()
+    rowp1, _ = ta._draw_noise(x, None, None, "philox"); m1 = ta._mask(b, cfg.prob_noise / 4, dev).reshape(b)
+    rowp2 = ta._draw_sines(x, 0.24); m2 = ta._mask(b, cfg.prob_wandering_volume, dev).reshape(b)
+    bands = ta._draw_bands(2, 500, 5); m3 = ta._mask(b, cfg.prob_banding, dev).reshape(b)
+    rowp4, _ = ta._draw_noise(x, None, None, "philox"); m4 = ta._mask(b, cfg.prob_noise / 4, dev).reshape(b)
+    sos = np.ascontiguousarray(design.eq_band_sos(fs, bands), dtype=np.float64)
+    y = torch.empty_like(x)
+
+    def chain():
+        _lib.check(_lib.lib().mpcg_aug_chain_f32(x.data_ptr(), y.data_ptr(), b, t, float(fs), rowp1.data_ptr(), None,
+                                                 m1.data_ptr(), 1, 2, rowp2.data_ptr(), m2.data_ptr(), sos.ctypes.data,
+                                                 sos.shape[0], m3.data_ptr(), rowp4.data_ptr(), None, m4.data_ptr(), 3, 4,
+                                                 1, torch.cuda.current_stream().cuda_stream), "aug chain")
+    ms = best_ms(chain)
+    nbytes = 2 * b * t * 4
+    res["augment_chain"] = {"workload": "configs[2]: augment_pcg_batch, 4096 windows x 64000 samples @16 kHz, one fused "
+                                        "launch (mpcg_aug_chain_f32), Philox noise, default masks",
+                            "ms": ms, "windows_per_s": b / (ms * 1e-3), "audio_s_per_s": b * 4.0 / (ms * 1e-3),
+                            "algorithmic_bytes": nbytes, "GB/s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
+    ms_api = best_ms(lambda: ta.augment_pcg_batch(x, fs, cfg, noise="philox"))
+    res["augment_chain"]["ms_through_python_api"] = ms_api
+    del x, y
+    # configs[3]: log-mel conditioning of 8192 windows x 64000 samples @ 16 kHz on the tensor-core tier
+    xm = torch.randn(8192, 64000, device=dev, generator=g)
+    tr = MelConfig(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build(fast=True)
+    ms = best_ms(lambda: log_mel(xm, tr))
+    nbytes = 8192 * 64000 * 4 + 8192 * 80 * 251 * 4
+    flops = 3 * 2.0 * (8192 * 254) * 256 * 80                     # three split-fp16 MMAs over [hop rows x hop] . [hop x 80]
+    res["log_mel"] = {"workload": "configs[3] (mel part): log_mel of 8192 windows x 64000 @16 kHz, n_fft 1024, hop 256, "
+                                  "80 mels, " + tr.backend,
+                      "ms": ms, "windows_per_s": 8192 / (ms * 1e-3), "algorithmic_bytes": nbytes,
+                      "GB/s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
+                      "tensor_TFLOP/s": flops / ms / 1e9}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +346,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the augmentation / mel side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
