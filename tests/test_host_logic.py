@@ -122,3 +122,22 @@ def test_cpu_tensors_are_refused():
         torchproc.abs_max_normalise(torch.zeros(2, 8))
     with pytest.raises(TypeError):
         torchproc.lowpass(np.zeros(8), 1000, 100)
+
+
+def test_eq_band_design_closed_form_matches_scipy():
+    """design.eq_band_sos writes SciPy's butter(1, band) out in closed form (it runs on the host once per augmentation
+    batch); it must agree with scipy.signal.butter to the last place or two on every band the chain can draw."""
+    import numpy as np
+    from wav2vec_heart_sounds_b200 import design
+    rng = np.random.default_rng(0)
+    for fs in (4125.0, 16000.0, 2000.0):
+        bands = []
+        for _ in range(200):
+            lo = float(rng.uniform(2, 0.95 * 500))
+            hi = float(rng.uniform(lo + 0.05 * 498, 500))
+            if hi < fs / 2:
+                bands.append((lo, hi))
+        bands += [(0.25, 100.0), (2.0, 26.9), (470.0, 499.9)] if fs > 1000 else []
+        got, want = design.eq_band_sos(fs, bands), design.eq_band_sos_scipy(fs, bands)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 4.5e-16 * max(1.0, np.abs(want).max())

@@ -34,7 +34,27 @@ def butter_sos(cutoff_over_fs: float, kind: str, order: int) -> np.ndarray:
 
 
 def eq_band_sos(fs: float, bands) -> np.ndarray:
-    """First-order Butterworth band-pass per (lo, hi) Hz pair -> one biquad each, [n, 6]."""
+    """First-order Butterworth band-pass per (lo, hi) Hz pair -> one biquad each, [n, 6].
+
+    The bands of ``parametric_eq`` are drawn afresh on every call (reference ``augment/torchaug.py:94-96``), so this
+    sits on the host side of every augmentation batch; ``scipy.signal.butter`` costs ~0.3 ms per band.  The section is
+    written out in closed form instead -- SciPy's own recipe for ``butter(1, [lo/nyq, hi/nyq], 'band')``: pre-warp both
+    edges (``fs = 2``), analog band-pass ``H(s) = bw s / (s^2 + bw s + w0^2)``, bilinear transform -- and
+    ``tests/test_host_logic.py`` pins it to ``butter`` within one unit in the last place.
+    """
+    nyq = fs / 2.0
+    rows = []
+    for lo, hi in bands:
+        w1 = 4.0 * math.tan(math.pi * (lo / nyq) / 2.0)
+        w2 = 4.0 * math.tan(math.pi * (hi / nyq) / 2.0)
+        bw, w0sq, k = w2 - w1, w1 * w2, 4.0
+        a0 = k * k + bw * k + w0sq
+        rows.append([bw * k / a0, 0.0, -bw * k / a0, 1.0, (2.0 * w0sq - 2.0 * k * k) / a0, (k * k - bw * k + w0sq) / a0])
+    return np.asarray(rows, dtype=np.float64)
+
+
+def eq_band_sos_scipy(fs: float, bands) -> np.ndarray:
+    """The same sections straight from SciPy (the reference's call, ``augment/torchaug.py:96``); test oracle."""
     nyq = fs / 2.0
     rows = []
     for lo, hi in bands:
