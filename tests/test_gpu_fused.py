@@ -171,3 +171,47 @@ def test_fast_despike_equals_reference_order(pkg, mode, monkeypatch):
         assert int(e_ser.sum()) > rows                       # the despiker really worked
         assert torch.equal(e_fast, e_ser)
         assert torch.equal(fast, ser)
+
+
+def test_fast_despike_hand_over_paths(pkg, monkeypatch):
+    """Rows that the fast despike path cannot settle from its logs and hands to the serial path: frames that need more
+    than 16 passes (a long ringing burst eaten half-cycle by half-cycle), spans that exhaust the undo pool (no sign
+    flips: every pass covers a whole frame), more frames above the threshold than one round's log.  Whatever the path,
+    samples and pass counts must equal the serial path's."""
+    rng = np.random.default_rng(7)
+    n, fs_in = 60000, 2000
+    t = np.arange(n)
+    rows = []
+    base = 0.05 * rng.standard_normal((6, n))
+    ring = base[0].copy()                                    # 1: 60 half-cycles of a slowly decaying 40 Hz burst
+    ring[20000:21500] += 8.0 * np.exp(-np.arange(1500) / 900.0) * np.sin(2 * np.pi * 40.0 * np.arange(1500) / fs_in)
+    rows.append(ring)
+    dc = base[1] + 3.0                                       # 2: never crosses zero; two big bumps in one slice
+    dc[9000:9040] += 40.0
+    dc[13000:13030] += 30.0
+    dc[30000:30020] += 35.0
+    rows.append(dc)
+    many = base[2].copy()                                    # 3: a spike in every third frame (20 frames above the threshold)
+    many[500::3000] += 6.0
+    rows.append(many)
+    rows.append(base[3] * 0.0)                               # 4: silence (median 0)
+    alt = base[4].copy()                                     # 5: one-sample alternating spikes (stuck frames)
+    alt[7001] += 20.0; alt[7002] -= 20.0; alt[33333] -= 25.0
+    rows.append(alt)
+    rows.append(base[5] + np.where((t // 3000) % 2 == 0, 1.0, 0.02) * np.sin(t / 5.0))   # 6: loud/quiet halves
+    x = torch.from_numpy(np.stack(rows).astype(np.float32)).cuda()
+    spec = pkg.WindowSpec(4.0)
+    for mode in ("torch", "numpy"):
+        monkeypatch.delenv("MPCG_FZ_DESPIKE_SERIAL", raising=False)
+        fast, e_fast = pkg.preprocess_segment(x, fs_in, 4125, spec, mode=mode, fused=True, return_edits=True)
+        monkeypatch.setenv("MPCG_FZ_DESPIKE_SERIAL", "1")
+        ser, e_ser = pkg.preprocess_segment(x, fs_in, 4125, spec, mode=mode, fused=True, return_edits=True)
+        monkeypatch.delenv("MPCG_FZ_DESPIKE_SERIAL", raising=False)
+        assert torch.equal(e_fast, e_ser), (mode, e_fast.tolist(), e_ser.tolist())
+        assert torch.equal(fast, ser), mode
+        assert int(e_ser[0]) > 16 and int(e_ser[2]) >= 15
+    # and the serial path itself against the float64 oracle on these rows (torch mode)
+    want, _ = _oracle_torch(x.cpu().numpy(), fs_in, 4125, 4.0)
+    got = pkg.preprocess_segment(x, fs_in, 4125, spec, fused=True).cpu().numpy()
+    for r in range(x.shape[0]):
+        assert rel_err(got[r], want[r]) < TOL or np.abs(want[r]).max() == 0, r

@@ -5,5 +5,10 @@
 #define FZ_I8N 8, 1, 22, 1
 #define FZ_I16 33, 16, 30, 4
 #define FZ_I16N 33, 16, 36, 4
+#if defined(MPCG_FZ_THREADS) && MPCG_FZ_THREADS == 1024      /* 32 warps: eight-warp teams keep the staging inside its budget */
+#define FZ_I32 33, 32, 46, 8
+#define FZ_I32N 33, 32, 52, 8
+#else
 #define FZ_I32 33, 32, 46, 4
 #define FZ_I32N 33, 32, 52, 4
+#endif

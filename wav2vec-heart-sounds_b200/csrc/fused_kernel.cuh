@@ -41,7 +41,7 @@ constexpr int kFzThreads = MPCG_FZ_THREADS;
 constexpr int kFzWarps = kFzThreads / 32;
 constexpr int kFzChunks = MPCG_FZ_FILTER_THREADS;   // one filter chunk per filter thread
 constexpr int kFzFW = kFzChunks / 32;               // filter warps
-constexpr int kFzLmax = 81 * (512 / kFzChunks) + (512 / kFzChunks - 1);   // longest chunk (odd): 81 / 163
+constexpr int kFzLmax = kFzChunks == 1024 ? 41 : (kFzChunks == 512 ? 81 : 163);   // longest chunk (odd)
 constexpr int kFzMaxFrames = 64;         // despike frames per row the fused kernel accepts
 constexpr int kFzMaxCluster = 8;
 constexpr int kFzStageWords = 4608;       // resampler input staging: teams x buffers x block (largest: 8 x 565)
@@ -51,7 +51,7 @@ constexpr int kFzScrWords = 2112;         // longest despike frame the fast path
 constexpr int kFzUndoWords = 3072;        // per-CTA pool for the samples the fast path's passes overwrite
 constexpr int kFzLogCap = 16;             // passes per frame and round it logs before handing over to the serial path
 constexpr int kFzFastLocal = 16;          // frames per CTA the fast path takes
-static_assert(kFzChunks == 512 || kFzChunks == 256, "filter threads: 512 or 256");
+static_assert(kFzChunks == 1024 || kFzChunks == 512 || kFzChunks == 256, "filter threads: 1024, 512 or 256");
 static_assert(kFzChunks <= kFzThreads, "filter threads are a subset of the CTA");
 
 struct FzKind {                           // per channel kind (PCG / ECG): despike on/off + its filter
