@@ -34,3 +34,7 @@ timeit("fused chain, default masks (p = .075/.75/.25/.075)", run)
 ones, zeros = torch.ones(B, device="cuda"), torch.zeros(B, device="cuda")
 timeit("fused chain, all masks off", lambda: run((zeros, zeros, zeros, zeros)))
 timeit("fused chain, all masks on", lambda: run((ones, ones, ones, ones)))
+timeit("only noise 1 on", lambda: run((ones, zeros, zeros, zeros)))
+timeit("only wandering volume on", lambda: run((zeros, ones, zeros, zeros)))
+timeit("only EQ on", lambda: run((zeros, zeros, ones, zeros)))
+timeit("only noise 2 on", lambda: run((zeros, zeros, zeros, ones)))

@@ -122,11 +122,18 @@ mel_tc_kernel(const MelTcArgs a) {
   int* row_sig = reinterpret_cast<int*>(tail + 16 + 64);      // [128] signal of each hop row of the tile (-1: none)
   int* row_loc = row_sig + kTcRows;                           // [128] its hop-row index inside that signal
   float* fbs = reinterpret_cast<float*>(row_loc + kTcRows);   // [nbins][n_mels4] filterbank, rows padded to 4 mels
+  const int nm4_ = (a.n_mels + 3) & ~3;
+  float* twb = fbs + a.nbins * nm4_;                          // [nbins + 2][Q][2] twiddle of (bin, hop row): exp(-2 pi i k q / Q)
+  int* mk0 = reinterpret_cast<int*>(twb + (a.nbins + 2) * a.Q * 2);   // [n_mels] first / last bin with weight
+  int* mk1 = mk0 + a.n_mels;
   float* stage = reinterpret_cast<float*>(tc_smem);           // [128][N + 1], reuses the A region after the MMAs
   const int nb2 = a.nbins + 2;
   const int srow = N + 1;
   const int mstride = (a.nbins + 1) | 1;                      // odd: frames run across lanes
   float* mags = stage + kTcRows * srow;                       // [FPT][mstride]
+  const int rstride = nb2 | 1;
+  float* rect_re = mags + kTcRows * mstride;                  // [FPT][rstride] rectangular-window spectra of the frames
+  float* rect_im = rect_re + kTcRows * rstride;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fpt = kTcRows - (Q - 1);                          // frames per tile
 
@@ -141,6 +148,20 @@ mel_tc_kernel(const MelTcArgs a) {
   for (int i = tid; i < a.nbins * nm4; i += kTcThreads) {
     const int k = i / nm4, m = i - k * nm4;
     fbs[i] = m < a.n_mels ? a.fb[(long long)k * a.n_mels + m] : 0.f;
+  }
+  for (int i = tid; i < nb2 * Q; i += kTcThreads) {           // twiddles per (bin, hop row) from the Q-point table
+    const int b = i / Q, q = i - b * Q;
+    const int k = a.k0 - 1 + b;
+    const int m = (int)((((long long)k * q) % Q + Q) % Q);
+    twb[2 * i] = a.twq[2 * m];
+    twb[2 * i + 1] = a.twq[2 * m + 1];
+  }
+  __syncthreads();                                            // fbs complete
+  for (int m = tid; m < a.n_mels; m += kTcThreads) {          // each mel filter's support (a short run of bins)
+    int k0m = a.nbins, k1m = -1;
+    for (int k = 0; k < a.nbins; ++k)
+      if (fbs[k * nm4 + m] != 0.f) { k0m = k < k0m ? k : k0m; k1m = k; }
+    mk0[m] = k0m; mk1[m] = k1m;
   }
   if (tid == 0) mbar_init(mbar, 1);
   if (warp == 0) {
@@ -175,42 +196,71 @@ mel_tc_kernel(const MelTcArgs a) {
     const int nchunks = kTcRows * chunks_per_row;
     const bool cpr_pow2 = (chunks_per_row & (chunks_per_row - 1)) == 0;
     const int cpr_shift = 31 - __clz(chunks_per_row);
-    for (int idx = tid; idx < nchunks; idx += kTcThreads) {
-      const int r8 = idx & 7;
-      const int rest = idx >> 3;
-      const int g8 = cpr_pow2 ? (rest >> cpr_shift) : rest / chunks_per_row;
-      const int jc = rest - g8 * chunks_per_row;
-      const int g = g8 * 8 + r8;
-      const int sg = row_sig[g];
-      const float* xr = a.x + (long long)(sg < 0 ? 0 : sg) * a.t;
-      const long long s0 = (long long)row_loc[g] * hop - pad + jc * 8;  // first un-padded sample index of the chunk
-      float v[8];
-      if (sg < 0 || s0 >= a.t + pad) {                        // past the last signal / past the reflected tail
+    // Four chunks per thread in flight: all global loads of a batch are issued before the first conversion.
+    constexpr int kBatch = 4;
+    for (int idx0 = tid; idx0 < nchunks; idx0 += kBatch * kTcThreads) {
+      float4 p0[kBatch], p1[kBatch];
+      int off[kBatch], kind[kBatch];                          // kind: 0 = zeros, 1 = loaded (aligned interior), 2 = edge
+      const float* xrs[kBatch];
+      long long s0s[kBatch];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      } else if (s0 >= 0 && s0 + 7 < a.t && ((((uintptr_t)(xr + s0)) & 15u) == 0)) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(xr + s0));
-        const float4 p1 = __ldg(reinterpret_cast<const float4*>(xr + s0 + 4));
-        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          long long j = s0 + e;
-          if (j < 0) j = -j;                                  // reflect padding (no edge repeat)
-          if (j >= a.t) j = 2 * (a.t - 1) - j;
-          v[e] = (j >= 0 && j < a.t) ? __ldg(xr + j) : 0.f;
+      for (int u = 0; u < kBatch; ++u) {
+        const int idx = idx0 + u * kTcThreads;
+        kind[u] = -1;
+        if (idx < nchunks) {
+          const int r8 = idx & 7;
+          const int rest = idx >> 3;
+          const int g8 = cpr_pow2 ? (rest >> cpr_shift) : rest / chunks_per_row;
+          const int jc = rest - g8 * chunks_per_row;
+          const int g = g8 * 8 + r8;
+          const int sg = row_sig[g];
+          const float* xr = a.x + (long long)(sg < 0 ? 0 : sg) * a.t;
+          const long long s0 = (long long)row_loc[g] * hop - pad + jc * 8;   // first un-padded sample index of the chunk
+          off[u] = g8 * (int)sbo + jc * 128 + r8 * 16;
+          xrs[u] = xr; s0s[u] = s0;
+          if (sg < 0 || s0 >= a.t + pad) {                    // past the last signal / past the reflected tail
+            kind[u] = 0;
+          } else if (s0 >= 0 && s0 + 7 < a.t && ((((uintptr_t)(xr + s0)) & 15u) == 0)) {
+            kind[u] = 1;
+            p0[u] = __ldg(reinterpret_cast<const float4*>(xr + s0));
+            p1[u] = __ldg(reinterpret_cast<const float4*>(xr + s0 + 4));
+          } else {
+            kind[u] = 2;
+          }
         }
       }
-      __half2 hi[4], lo[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __half h0 = __float2half_rn(v[2 * e]), h1 = __float2half_rn(v[2 * e + 1]);
-        hi[e] = __halves2half2(h0, h1);
-        lo[e] = __halves2half2(__float2half_rn(v[2 * e] - __half2float(h0)), __float2half_rn(v[2 * e + 1] - __half2float(h1)));
+      for (int u = 0; u < kBatch; ++u) {
+        if (kind[u] < 0) continue;
+        float v[8];
+        if (kind[u] == 1) {
+          v[0] = p0[u].x; v[1] = p0[u].y; v[2] = p0[u].z; v[3] = p0[u].w;
+          v[4] = p1[u].x; v[5] = p1[u].y; v[6] = p1[u].z; v[7] = p1[u].w;
+        } else if (kind[u] == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        } else {
+          long long js[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            long long j = s0s[u] + e;
+            if (j < 0) j = -j;                                // reflect padding (no edge repeat)
+            if (j >= a.t) j = 2 * (a.t - 1) - j;
+            js[e] = j;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (js[e] >= 0 && js[e] < a.t) ? __ldg(xrs[u] + js[e]) : 0.f;
+        }
+        __half2 hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half h0 = __float2half_rn(v[2 * e]), h1 = __float2half_rn(v[2 * e + 1]);
+          hi[e] = __halves2half2(h0, h1);
+          lo[e] = __halves2half2(__float2half_rn(v[2 * e] - __half2float(h0)), __float2half_rn(v[2 * e + 1] - __half2float(h1)));
+        }
+        *reinterpret_cast<uint4*>(A_hi + off[u]) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(A_lo + off[u]) = *reinterpret_cast<uint4*>(lo);
       }
-      const int off = g8 * (int)sbo + jc * 128 + r8 * 16;
-      *reinterpret_cast<uint4*>(A_hi + off) = *reinterpret_cast<uint4*>(hi);
-      *reinterpret_cast<uint4*>(A_lo + off) = *reinterpret_cast<uint4*>(lo);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     __syncthreads();
@@ -248,59 +298,51 @@ mel_tc_kernel(const MelTcArgs a) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- frame spectra: twiddle sum over the Q hop rows, Hann in the frequency domain, magnitude.
-    //      One item = (frame f, output bin kb); frames run fastest so staging reads walk rows (odd stride).
+    // ---- frame spectra, pass A: rectangular-window bins of every frame = twiddle sum over its Q hop rows.
+    //      One item = (frame f, bin b); frames run fastest so staging reads walk rows (odd stride).
     {
-    int kb = tid / fpt, f = tid - kb * fpt;                   // item = kb * fpt + f, stepped without divisions
-    const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
-    for (; kb < a.nbins; kb += dk, f += df) {
-      if (f >= fpt) { f -= fpt; ++kb; if (kb >= a.nbins) break; }
-      float re[3], im[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int b = kb + j;                                 // rectangular-window bin k0 - 1 + b
-        const int k = a.k0 - 1 + b;
-        int m = 0;                                            // (k * q) mod Q, stepped
-        const int kq = q_pow2 ? (k & (Q - 1)) : ((k % Q) + Q) % Q;
+      int b = tid / fpt, f = tid - b * fpt;                   // item = b * fpt + f, stepped without divisions
+      const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
+      for (; b < nb2; b += dk, f += df) {
+        if (f >= fpt) { f -= fpt; ++b; if (b >= nb2) break; }
         float sr = 0.f, si = 0.f;
         for (int q = 0; q < Q; ++q) {
-          const float wr = twq[2 * m], wi = twq[2 * m + 1];
+          const float wr = twb[2 * (b * Q + q)], wi = twb[2 * (b * Q + q) + 1];
           const float pr = stage[(f + q) * srow + b], pi = stage[(f + q) * srow + nb2 + b];
           sr = fmaf(wr, pr, fmaf(-wi, pi, sr));
           si = fmaf(wr, pi, fmaf(wi, pr, si));
-          m += kq;
-          if (m >= Q) m -= Q;
         }
-        re[j] = sr; im[j] = si;
+        rect_re[f * rstride + b] = sr;
+        rect_im[f * rstride + b] = si;
       }
-      const float xr2 = 0.5f * re[1] - 0.25f * (re[0] + re[2]), xi2 = 0.5f * im[1] - 0.25f * (im[0] + im[2]);
-      mags[f * mstride + kb] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
-    }
     }
     __syncthreads();
-    // ---- mel projection, dB map, store: one item = (frame, four mels); frames run fastest (contiguous stores)
+    // ---- pass B: Hann in the frequency domain (0.5 X[k] - 0.25 (X[k-1] + X[k+1])), magnitude
     {
-    int mg4 = tid / fpt, f = tid - mg4 * fpt;
-    const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
-    for (; mg4 < (nm4 >> 2); mg4 += dk, f += df) {
-      if (f >= fpt) { f -= fpt; ++mg4; if (mg4 >= (nm4 >> 2)) break; }
-      const int sg = row_sig[f], fg = row_loc[f];             // frame slot f = hop row f of the tile
-      if (sg < 0 || fg >= a.frames) continue;
-      const long long row = sg;
-      const float* mg = mags + f * mstride;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k < a.nbins; ++k) {
-        const float4 w = *reinterpret_cast<const float4*>(fbs + k * nm4 + 4 * mg4);
-        const float v = mg[k];
-        acc[0] = fmaf(w.x, v, acc[0]); acc[1] = fmaf(w.y, v, acc[1]);
-        acc[2] = fmaf(w.z, v, acc[2]); acc[3] = fmaf(w.w, v, acc[3]);
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = 4 * mg4 + e;
-        if (m < a.n_mels) a.out[((long long)row * a.n_mels + m) * a.frames + fg] = a.log_map ? mel_log_map(acc[e]) : acc[e];
+      int kb = tid / fpt, f = tid - kb * fpt;
+      const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
+      for (; kb < a.nbins; kb += dk, f += df) {
+        if (f >= fpt) { f -= fpt; ++kb; if (kb >= a.nbins) break; }
+        const float* rr = rect_re + f * rstride + kb;
+        const float* ri = rect_im + f * rstride + kb;
+        const float xr2 = 0.5f * rr[1] - 0.25f * (rr[0] + rr[2]), xi2 = 0.5f * ri[1] - 0.25f * (ri[0] + ri[2]);
+        mags[f * mstride + kb] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
       }
     }
+    __syncthreads();
+    // ---- mel projection over each filter's own bins, dB map, store: one item = (frame, mel); frames run fastest
+    {
+      int m = tid / fpt, f = tid - m * fpt;
+      const int dk = kTcThreads / fpt, df = kTcThreads - dk * fpt;
+      for (; m < a.n_mels; m += dk, f += df) {
+        if (f >= fpt) { f -= fpt; ++m; if (m >= a.n_mels) break; }
+        const int sg = row_sig[f], fg = row_loc[f];           // frame slot f = hop row f of the tile
+        if (sg < 0 || fg >= a.frames) continue;
+        const float* mg = mags + f * mstride;
+        float acc = 0.f;
+        for (int k = mk0[m]; k <= mk1[m]; ++k) acc = fmaf(fbs[k * nm4 + m], mg[k], acc);
+        a.out[((long long)sg * a.n_mels + m) * a.frames + fg] = a.log_map ? mel_log_map(acc) : acc;
+      }
     }
     __syncthreads();                                          // staging / mags are reused by the next tile's A
   }
@@ -327,10 +369,12 @@ extern "C" int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t
   if (t <= n_fft / 2) return MPCG_EINVAL;
   const int fpt = kTcRows - (Q - 1);
   const size_t a_bytes = (size_t)kTcRows * hop * 2, b_bytes = (size_t)ncols * hop * 2;
-  const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * ((nbins + 1) | 1) * 4;
+  const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * ((nbins + 1) | 1) * 4 +
+                             2 * (size_t)kTcRows * ((nbins + 2) | 1) * 4;
   if (stage_bytes > 2 * a_bytes) return MPCG_EUNSUPPORTED;
   const size_t smem = 2 * a_bytes + 2 * b_bytes + 16 + 64 + 2 * kTcRows * sizeof(int) +
-                      (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + 64;
+                      (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + (size_t)(nbins + 2) * Q * 2 * sizeof(float) +
+                      2 * (size_t)n_mels * sizeof(int) + 64;
   if (smem > 227 * 1024) return MPCG_EUNSUPPORTED;
   MelTcArgs a;
   a.x = x; a.out = out; a.basis = (const __half*)basis_f16; a.fb = fb; a.twq = twq; a.t = t; a.rows = rows;

@@ -61,8 +61,9 @@ class MelTransform:
         if (self.fast and self.win_length == self.n_fft and q * self.hop_length == self.n_fft and 1 <= q <= 8
                 and self.hop_length % 16 == 0 and ncols <= 256
                 and (2 * 128 * self.hop_length * 2 + 2 * ncols * self.hop_length * 2 + 256
-                     + 1024 + self.nbins * ((self.n_mels + 3) // 4 * 4) * 4) <= 227 * 1024
-                and 128 * (ncols + 1) * 4 + 128 * ((self.nbins + 1) | 1) * 4 <= 2 * 128 * self.hop_length * 2):
+                     + 1024 + self.nbins * ((self.n_mels + 3) // 4 * 4) * 4 + (self.nbins + 2) * q * 8 + 8 * self.n_mels) <= 227 * 1024
+                and (128 * (ncols + 1) * 4 + 128 * ((self.nbins + 1) | 1) * 4 + 2 * 128 * ((self.nbins + 2) | 1) * 4
+                     <= 2 * 128 * self.hop_length * 2)):
             hop, nb2 = self.hop_length, self.nbins + 2
             j = np.arange(hop, dtype=np.float64)[None, :]
             kk = (k0 - 1 + np.arange(nb2, dtype=np.float64))[:, None]
