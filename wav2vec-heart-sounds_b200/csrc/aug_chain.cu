@@ -327,33 +327,44 @@ aug_chain_kernel(const __grid_constant__ AcParams P) {
     const AcMap m = map[0];
     float4* buf4 = reinterpret_cast<float4*>(buf);
     if (on && op == MPCG_AUG_SINE_MUL) {
-      // wandering volume: exact sine at the first sample of each group of four, the other three by rotation
+      // wandering volume: each thread evaluates the two sinusoids exactly once (at its first sample, with the
+      // reference's rounding sequence) and then ROTATES: by one sample inside a group of four, by kAcThreads groups from
+      // one of its groups to the next.  At most ~40 rotations per thread: ~3e-6 rad of phase, < 1e-6 of the output.
       const float two_pi = 6.283185307179586f;
-      float cd[2], sd[2];
+      float cd[2], sd[2], cj[2], sj[2], sg[2], cg[2];
+      const float tt0 = __fdiv_rn((float)(s0 + 4 * tid), P.fs);
 #pragma unroll
-      for (int b = 0; b < 2; ++b) __sincosf(__fdiv_rn(__fmul_rn(two_pi, p[3 * b + 1]), P.fs), &sd[b], &cd[b]);
+      for (int b = 0; b < 2; ++b) {
+        const float dw = __fdiv_rn(__fmul_rn(two_pi, p[3 * b + 1]), P.fs);          // phase step per sample
+        sincosf(dw, &sd[b], &cd[b]);
+        sincosf(dw * (float)(4 * kAcThreads), &sj[b], &cj[b]);
+        sincosf(__fmul_rn(two_pi, __fadd_rn(__fmul_rn(p[3 * b + 1], tt0), p[3 * b + 2])), &sg[b], &cg[b]);
+      }
       for (int q = tid; q < nq; q += kAcThreads) {
         const float4 b4 = buf4[q];
         float w[4] = {b4.x, b4.y, b4.z, b4.w};
-        const float tt = __fdiv_rn((float)(s0 + 4 * q), P.fs);
-        float sn[2], cs[2];
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-          sincosf(__fmul_rn(two_pi, __fadd_rn(__fmul_rn(p[3 * b + 1], tt), p[3 * b + 2])), &sn[b], &cs[b]);
+        float sn[2] = {sg[0], sg[1]}, cs[2] = {cg[0], cg[1]};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float mod = __fadd_rn(__fadd_rn(0.f, __fmul_rn(p[0], sn[0])), __fmul_rn(p[3], sn[1]));
           const float v = m(w[k]);
           w[k] = __fmul_rn(v, __fadd_rn(1.f, mod));
           if (4 * q + k < n) st[0].add(w[k]);
+          if (k < 3) {
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const float s_n = fmaf(sn[b], cd[b], cs[b] * sd[b]), c_n = fmaf(cs[b], cd[b], -sn[b] * sd[b]);
-            sn[b] = s_n; cs[b] = c_n;
+            for (int b = 0; b < 2; ++b) {
+              const float s_n = fmaf(sn[b], cd[b], cs[b] * sd[b]), c_n = fmaf(cs[b], cd[b], -sn[b] * sd[b]);
+              sn[b] = s_n; cs[b] = c_n;
+            }
           }
         }
         buf4[q] = make_float4(w[0], w[1], w[2], w[3]);
         st[0].flush();
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {                         // on to this thread's next group
+          const float s_n = fmaf(sg[b], cj[b], cg[b] * sj[b]), c_n = fmaf(cg[b], cj[b], -sg[b] * sj[b]);
+          sg[b] = s_n; cg[b] = c_n;
+        }
       }
     } else {
     for (int q = tid; q < nq; q += kAcThreads) {
