@@ -232,7 +232,7 @@ def run_ours(args):
     kernel_ms = ms / args.steps                                   # one launch per step
 
     # ---- end to end: host buffers in, host buffers out
-    hp = HostPipeline(RECORDINGS, 2, T_IN, FS_IN, FS_OUT, spec, kinds=KINDS, chunk=128, device=dev)
+    hp = HostPipeline(RECORDINGS, 2, T_IN, FS_IN, FS_OUT, spec, kinds=KINDS, chunk=32, device=dev)
     x_host = x.cpu().pin_memory()
     out_host = hp.empty_output()
     e2e_steps = max(3, min(args.steps, 10))
