@@ -215,3 +215,24 @@ def test_fast_despike_hand_over_paths(pkg, monkeypatch):
     got = pkg.preprocess_segment(x, fs_in, 4125, spec, fused=True).cpu().numpy()
     for r in range(x.shape[0]):
         assert rel_err(got[r], want[r]) < TOL or np.abs(want[r]).max() == 0, r
+
+
+def test_fused_config5_chunk_properties(pkg):
+    """configs[4] per-GPU chunk shape, scaled to 1024 recordings x 6 channels x 8 s at 4 kHz -> 4125 Hz, 2 s windows:
+    2-CTA clusters, the 33/32 resampler instance, both output layouts."""
+    from wav2vec_heart_sounds_b200.synth import synth_pcg
+    r, c, t = 1024, 6, 32000
+    x = synth_pcg(r * c, t, 4000.0, seed=9, device="cuda").reshape(r, c, t)
+    spec = pkg.WindowSpec(2.0)
+    planar = pkg.preprocess_segment(x, 4000, 4125, spec, fused=True)
+    last = pkg.preprocess_segment(x, 4000, 4125, spec, channels_last=True, fused=True)
+    assert planar.shape == (r, c, 4, 8250) and last.shape == (r, 4, 8250, c)
+    assert torch.isfinite(planar).all() and float(planar.abs().max()) <= 1.0
+    assert torch.equal(last.permute(0, 3, 1, 2), planar)
+    ov = 8250 - 7219
+    assert torch.equal(planar[:, :, :-1, -ov:], planar[:, :, 1:, :ov])       # overlapping windows carry the same samples
+    sub = pkg.preprocess_segment(x[100:103].contiguous(), 4000, 4125, spec, fused=True)
+    assert torch.equal(sub, planar[100:103])                                 # rows are independent
+    # three recordings against the float64 oracle
+    want, _ = _oracle_torch(x[7].cpu().numpy(), 4000, 4125, 2.0)
+    assert rel_err(planar[7].cpu().numpy(), want) < TOL
