@@ -1,0 +1,145 @@
+"""Batched dataset building on the device: the caller side of the hot path.
+
+The reference builds its in-memory fragment lists one record at a time on the CPU --
+``datasets/cinc.py:54-125`` (``build_fragments``: read record -> ``preprocess_pcg`` [-> ``preprocess_ecg``] ->
+``segment`` -> one ``Fragment`` per window) and ``datasets/vest.py:54-113`` (six PCG channels) -- and hands them to
+``datasets/fragments.py:30-83`` (``FragmentDataset``).  Here the records of one call are grouped by length and rate,
+each group goes through ONE fused preprocess + segment launch (``pipeline.preprocess_segment``, NumPy-path arithmetic
+by default because that is what the loaders call), and the windows land in one tensor in the reference's order with
+label / record index tensors beside it.  File reading (wfdb / WAV) stays with the caller: records arrive as arrays.
+
+``FragmentTensorDataset`` serves the same item dictionaries as the reference's ``FragmentDataset`` (so ``pad_collate``
+and the trainers work unchanged); ``device_batch_transform`` is the ``SupervisedTrainer(batch_transform=...)`` hook
+(``classify/trainer.py:65-68``) that runs the fused augmentation chain on the PCG channel of a device batch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, torchaug
+from .pipeline import preprocess_segment
+from .segment import start_index
+
+
+@dataclass
+class FragmentBatch:
+    """All windows of a set of records.  ``windows``: ``[F, win]`` (mono) or ``[F, win, C]`` (the loader layout of
+    ``datasets/cinc.py:90`` / ``datasets/vest.py:83-85``); ``labels`` / ``record``: ``[F]`` int64, ``record`` indexing
+    ``patients``; windows of a record are contiguous and records keep the caller's order, like the reference's list."""
+    windows: torch.Tensor
+    labels: torch.Tensor
+    record: torch.Tensor
+    patients: list
+    fs: int
+
+    def __len__(self) -> int:
+        return int(self.windows.shape[0])
+
+    def class_counts(self) -> dict:
+        vals, cnt = torch.unique(self.labels, return_counts=True)
+        return {int(v): int(c) for v, c in zip(vals.tolist(), cnt.tolist())}
+
+
+def build_fragments_batched(records: Iterable, *, fs_out: int, window, ecg: bool = False, channels: Sequence[str] | None = None,
+                            mode: str = "numpy", device="cuda") -> FragmentBatch:
+    """``records``: iterable of ``(signal, fs, label, patient)`` with ``signal`` a ``[T]`` or ``[T, C]`` array (time
+    major, as ``wfdb`` / the WAV readers return it).
+
+    * CinC (``datasets/cinc.py``): column 0 is the PCG; with ``ecg=True`` column 1 is the ECG and fragments are
+      ``[win, 2]``; otherwise fragments are mono ``[win]``.
+    * Vest (``datasets/vest.py``): pass ``channels=("pcg",) * 6`` -- every column is conditioned as PCG, fragments are
+      ``[win, 6]``.
+
+    Records shorter than the start pad yield no fragment in ``mode="numpy"`` (``signalproc/segment.py:34-35``) and one
+    zero window in ``mode="torch"`` (``signalproc/torchproc.py:119-129``), as in the reference.
+    """
+    recs = [(np.asarray(s), float(fs), int(label), patient) for s, fs, label, patient in records]
+    dev = torch.device(device)
+    kinds = tuple(channels) if channels is not None else (("pcg", "ecg") if ecg else ("pcg",))
+    c = len(kinds)
+    mono = c == 1
+    win = window.window_len(fs_out)
+    groups: dict = {}
+    for i, (sig, fs, _, _) in enumerate(recs):
+        sig2 = sig[:, None] if sig.ndim == 1 else sig
+        if sig2.shape[1] < c:
+            raise ValueError(f"record {i} has {sig2.shape[1]} channels, {c} are needed")
+        groups.setdefault((sig2.shape[0], fs), []).append(i)
+    counts = [0] * len(recs)
+    pieces: dict = {}
+    for (t_in, fs), idx in groups.items():
+        host = np.stack([(recs[i][0][:, None] if recs[i][0].ndim == 1 else recs[i][0])[:, :c].T for i in idx]).astype(np.float32)
+        x = torch.from_numpy(np.ascontiguousarray(host)).to(dev)                      # [B, C, T]
+        if mode == "numpy":
+            t_out = _numpy_out_len(t_in, fs, fs_out)
+            if t_out <= start_index(fs_out, window):
+                continue                                                              # segment() returns no window
+        w = preprocess_segment(x, fs, fs_out, window, kinds=kinds, mode=mode, channels_last=not mono)
+        w = w[:, 0] if mono else w                                                    # [B, N, win] or [B, N, win, C]
+        for k, i in enumerate(idx):
+            pieces[i] = w[k]
+            counts[i] = int(w.shape[1])
+    total = sum(counts)
+    shape = (total, win) if mono else (total, win, c)
+    windows = torch.empty(shape, device=dev, dtype=torch.float32)
+    labels = torch.empty(total, dtype=torch.int64)
+    record = torch.empty(total, dtype=torch.int64)
+    at = 0
+    for i, n in enumerate(counts):
+        if n:
+            windows[at:at + n] = pieces[i]
+            labels[at:at + n] = recs[i][2]
+            record[at:at + n] = i
+            at += n
+    return FragmentBatch(windows, labels.to(dev), record.to(dev), [r[3] for r in recs], int(fs_out))
+
+
+def _numpy_out_len(t_in: int, fs_in: float, fs_out: float) -> int:
+    from . import design
+    if fs_in == fs_out:
+        return t_in
+    up, down = design.reduce_ratio(fs_in, fs_out)
+    return t_in if up == down else design.kaiser_out_len(t_in, up, down)
+
+
+class FragmentTensorDataset(torch.utils.data.Dataset):
+    """The reference's ``FragmentDataset`` items (``datasets/fragments.py:62-83``: ``waveform``, ``label``, ``patient``)
+    served from a :class:`FragmentBatch`; ``channel`` selects one column of multichannel fragments (-1 keeps all)."""
+
+    def __init__(self, batch: FragmentBatch, channel: int = -1):
+        self.batch, self.channel = batch, channel
+
+    @property
+    def labels(self) -> list:
+        return self.batch.labels.tolist()
+
+    def __len__(self) -> int:
+        return len(self.batch)
+
+    def __getitem__(self, idx: int) -> dict:
+        w = self.batch.windows[idx]
+        if w.dim() == 2 and self.channel != -1:
+            w = w[:, self.channel]
+        return {"waveform": w, "label": int(self.batch.labels[idx]), "patient": self.batch.patients[int(self.batch.record[idx])]}
+
+
+def device_batch_transform(fs: int, cfg=None, *, pcg_channel: int = 0, noise: str | None = "philox"):
+    """A ``batch_transform`` for ``SupervisedTrainer`` (``classify/trainer.py:65-68``): ``x`` is the device batch,
+    ``[B, T]`` or time-major ``[B, T, C]`` (``pad_collate``'s layout); the PCG column goes through the fused
+    ``augment_pcg_batch`` chain, other columns pass through."""
+
+    def transform(x: torch.Tensor) -> torch.Tensor:
+        x = _lib.require_cuda_f32(x)
+        if x.dim() == 2:
+            return torchaug.augment_pcg_batch(x.contiguous(), fs, cfg, noise=noise)
+        if x.dim() != 3:
+            raise ValueError("batch_transform expects [B, T] or [B, T, C]")
+        out = x.clone()
+        out[:, :, pcg_channel] = torchaug.augment_pcg_batch(x[:, :, pcg_channel].contiguous(), fs, cfg, noise=noise)
+        return out
+
+    return transform
