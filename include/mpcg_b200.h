@@ -181,6 +181,13 @@ int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float 
                        int flags, void* stream);
 #define MPCG_AUG_CHAIN_COLLAPSE 1
 
+/* Generator-dataset conditioning of one batch (reference datasets/generative.py:77-115 with
+ * signalproc/preprocess.py:45-64): y [rows, crop] = fit_length(fade(abs_max_normalise(x [rows, t])), crop) with 128-sample
+ * linear fade ramps (fade_n) at both ends of the length-t signal (none when t < 2 fade_n); chirp (optional, [rows, crop]) =
+ * add_chirp(y, fs): y plus a full-band linear chirp scaled to max(0.5, max|y|).  norm_flags as in mpcg_absmax_norm_f32. */
+int mpcg_gen_condition_f32(const float* x, float* y, float* chirp, int64_t rows, int64_t t, int64_t crop, int fade_n,
+                           double fs, int norm_flags, void* stream);
+
 /* Tensor-core tier of the same transform (tcgen05, split-fp16 operands, fp32 accumulation in TMEM) for configurations
  * with n_fft = Q * hop (Q <= 8), win_length == n_fft and at most 126 weighted bins.  The GEMM is the rectangular-window
  * partial DFT of every hop row; frames are assembled by a Q-term twiddle sum and the Hann window is applied in the

@@ -266,6 +266,26 @@ def main():
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 
+    gen_condition_fixture(sp, versions)
+
+
+def gen_condition_fixture(sp, versions):
+    """G6: generator conditioning: the waveform part of GenerativeDataset.__getitem__ run through
+    the reference's own functions (datasets/generative.py:36-42,88-104,112; signalproc/preprocess.py:45-64)."""
+    from mpcg_wav2vec.datasets.generative import _fade
+    from mpcg_wav2vec.signalproc.preprocess import fit_length
+    rng = np.random.default_rng(61)
+    fs, crop = 4000, 24 * 256
+    g = dict(fs=fs, crop=crop)
+    for tag, t in (("long", 8000), ("exact", crop), ("short", 3000), ("tiny", 200)):
+        x = (np.sin(np.arange(t) / 9.0)[None] * rng.uniform(0.2, 3, (2, 1)) + 0.1 * rng.standard_normal((2, t)) + 0.3)
+        x = x.astype(np.float32)
+        y = np.stack([fit_length(_fade(sp.abs_max_normalise(r)), crop)[0] for r in x])
+        g[f"{tag}_x"] = x
+        g[f"{tag}_y"] = y
+        g[f"{tag}_chirp"] = np.stack([sp.add_chirp(r, fs) for r in y])
+    np.savez_compressed(OUT / "gen_condition.npz", versions=str(versions), **g)
+
 
 if __name__ == "__main__":
     main()

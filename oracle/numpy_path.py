@@ -183,3 +183,44 @@ def segment(x, fs: float, spec) -> np.ndarray:
         piece = v[s:s + win]
         out[k, :piece.shape[0]] = piece
     return out
+
+
+# --------------------------------------------------------------------------- generator conditioning
+def fade(x, n: int = 128) -> np.ndarray:
+    """``datasets/generative.py:36-42`` (``_fade``): linear ramps over the first and last ``n`` samples."""
+    x = np.asarray(x, dtype=np.float64)
+    if len(x) < 2 * n:
+        return x
+    x = x.copy()
+    x[:n] *= np.linspace(0.0, 1.0, n)
+    x[-n:] *= np.linspace(1.0, 0.0, n)
+    return x
+
+
+def fit_length(x, length: int):
+    """``signalproc/preprocess.py:45-64``: zero-pad or crop along axis 0; returns ``(array, valid_length)``."""
+    x = np.asarray(x)
+    orig = x.shape[0]
+    if orig < length:
+        x = np.pad(x, ((0, length - orig),) + tuple((0, 0) for _ in range(x.ndim - 1)), mode="constant")
+    elif orig > length:
+        x = x[:length]
+    return x, min(orig, length)
+
+
+def add_chirp(x, fs: float) -> np.ndarray:
+    """``signalproc/preprocess.py`` (``add_chirp``): full-band linear chirp scaled to ``max(0.5, max|x|)``."""
+    x = np.asarray(x, dtype=np.float64)
+    t = np.arange(len(x)) / fs
+    wave = np.asarray(_sig.chirp(t, f0=0, f1=fs / 2, t1=t[-1] if len(t) else 1.0, method="linear"))
+    peak = np.max(np.abs(wave)) or 1.0
+    wave = wave / peak * max(0.5, float(np.max(np.abs(x))) if len(x) else 0.5)
+    return x + wave
+
+
+def generator_item(reference, conditioning, fs: float, crop: int):
+    """The waveform part of ``GenerativeDataset.__getitem__`` without cycle rearrangement
+    (``datasets/generative.py:88-104,112``): returns ``(ref, con, chirp)``, each ``[crop]``."""
+    ref = fit_length(fade(abs_max_normalise(reference)), crop)[0]
+    con = fit_length(fade(abs_max_normalise(conditioning)), crop)[0]
+    return ref, con, add_chirp(ref, fs)

@@ -77,3 +77,42 @@ def test_vest_six_channels_and_batch_transform(ds):
     assert y.shape == fb.windows[:5].shape and torch.isfinite(y).all()
     assert torch.equal(y[:, :, 1:], fb.windows[:5][:, :, 1:])             # only the PCG column is augmented
     assert float(y[:, :, 0].abs().max()) <= 1.0 and not torch.equal(y[:, :, 0], fb.windows[:5][:, :, 0])
+
+
+@pytest.mark.parametrize("t", [24576, 30000, 9000, 200])
+def test_generator_conditioning_batch(ds, t):
+    """normalise -> fade -> fit_length -> log_mel / add_chirp of GenerativeDataset.__getitem__
+    (datasets/generative.py:88-115), batched, against the NumPy restatement and torchaudio's float64 mel."""
+    import wav2vec_heart_sounds_b200 as pkg
+    from oracle import torch_path as otp
+    rng = np.random.default_rng(t)
+    fs, crop_frames, hop = 4000, 96, 256
+    crop = crop_frames * hop
+    ref = (np.sin(np.arange(t) / 9.0)[None] * rng.uniform(0.2, 3, (4, 1)) + 0.1 * rng.standard_normal((4, t)) + 0.3).astype(np.float32)
+    con = (np.sin(np.arange(t) / 23.0)[None] + 0.2 * rng.standard_normal((4, t))).astype(np.float32)
+    tr = pkg.MelConfig(sample_rate=fs, n_fft=1024, hop_length=hop, n_mels=80, f_max=500).build()
+    got = ds.condition_generator_batch(torch.from_numpy(ref).cuda(), torch.from_numpy(con).cuda(), fs, tr, crop_frames, hop)
+    otr = otp.mel_transform(fs, 1024, hop, n_mels=80, f_max=500).double()
+    for r in range(4):
+        wref, wcon, wchirp = onp.generator_item(ref[r], con[r], fs, crop)
+        assert got["ref_audio"].shape == (4, crop)
+        assert np.abs(got["ref_audio"][r].cpu().numpy() - wref).max() < TOL
+        assert np.abs(got["con_audio"][r].cpu().numpy() - wcon).max() < TOL
+        assert np.abs(got["chirp_wave"][r].cpu().numpy() - wchirp).max() < 2e-5 * max(1.0, np.abs(wchirp).max())
+        wspec = otp.log_mel(torch.from_numpy(wcon).double(), otr)
+        wspec = wspec[..., :crop_frames] if wspec.shape[-1] >= crop_frames else torch.nn.functional.pad(wspec, (0, crop_frames - wspec.shape[-1]))
+        assert got["con_spec"].shape == (4, 80, crop_frames)
+        assert float((got["con_spec"][r].cpu().double() - wspec).abs().max()) < TOL
+
+
+def test_generator_conditioning_vs_golden(ds, golden):
+    """The same kernel against the vectors the reference itself produced (tests/golden/gen_condition.npz)."""
+    import wav2vec_heart_sounds_b200 as pkg
+    g = golden("gen_condition.npz")
+    fs, crop = int(g["fs"]), int(g["crop"])
+    tr = pkg.MelConfig(sample_rate=fs, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build()
+    for tag in ("long", "exact", "short", "tiny"):
+        x = torch.from_numpy(g[f"{tag}_x"]).cuda()
+        got = ds.condition_generator_batch(x, x, fs, tr, crop // 256, 256)
+        assert np.abs(got["ref_audio"].cpu().numpy() - g[f"{tag}_y"]).max() < TOL
+        assert np.abs(got["chirp_wave"].cpu().numpy() - g[f"{tag}_chirp"]).max() < 2e-5

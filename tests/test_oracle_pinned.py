@@ -140,3 +140,16 @@ def test_against_live_reference_when_mounted():
     from mpcg_wav2vec.signalproc.segment import WindowSpec as RefSpec
     w1 = otp.segment(xt, 2000, onp.WindowSpec(1.0)).numpy()
     np.testing.assert_array_equal(w1, tp.segment(xt, 2000, RefSpec(1.0)).numpy())
+
+
+def test_generator_conditioning_matches_golden(golden):
+    """fade / fit_length / add_chirp of the oracle against the reference's own functions
+    (datasets/generative.py:36-42, signalproc/preprocess.py:45-64), bit for bit."""
+    g = golden("gen_condition.npz")
+    fs, crop = int(g["fs"]), int(g["crop"])
+    for tag in ("long", "exact", "short", "tiny"):
+        x = g[f"{tag}_x"]
+        for r in range(x.shape[0]):
+            ref, _, chirp = onp.generator_item(x[r], x[r], fs, crop)
+            np.testing.assert_array_equal(ref, g[f"{tag}_y"][r])
+            np.testing.assert_array_equal(chirp, g[f"{tag}_chirp"][r])

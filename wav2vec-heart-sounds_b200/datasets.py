@@ -143,3 +143,38 @@ def device_batch_transform(fs: int, cfg=None, *, pcg_channel: int = 0, noise: st
         return out
 
     return transform
+
+
+def condition_generator_batch(reference: torch.Tensor, conditioning: torch.Tensor, fs: int, mel_transform, crop_frames: int,
+                              hop_length: int, *, fade: int = 128, chirp: bool = True) -> dict:
+    """The per-item work of the generator datasets for a whole batch on the device (SURVEY.md section 8f, rank 2;
+    reference ``datasets/generative.py:77-115``, without the cardiac-cycle rearrangement, which reads per-record
+    segmentation files): ``abs_max_normalise`` -> fade -> ``fit_length(crop_frames * hop_length)`` for the reference
+    and the conditioning waveforms ``[B, T]``, ``log_mel`` of the conditioning cut or zero-padded to ``crop_frames``
+    frames, and the chirp reference plot signal.  Keys as in the reference's item dictionary."""
+    ref = _lib.require_cuda_f32(reference, "reference")
+    con = _lib.require_cuda_f32(conditioning, "conditioning")
+    if ref.dim() != 2 or con.dim() != 2 or ref.shape[0] != con.shape[0]:
+        raise ValueError("reference and conditioning must be [B, T] batches of the same size")
+    b, crop = ref.shape[0], int(crop_frames) * int(hop_length)
+    from .spectrogram import log_mel
+
+    def run(x, want_chirp):
+        x = x.contiguous()
+        y = torch.empty((b, crop), device=x.device, dtype=torch.float32)
+        c = torch.empty((b, crop), device=x.device, dtype=torch.float32) if want_chirp else None
+        _lib.check(_lib.lib().mpcg_gen_condition_f32(x.data_ptr(), y.data_ptr(), _lib.ptr(c), b, x.shape[1], crop, int(fade),
+                                                     float(fs), _lib.NORM_PEAK_GT0, _lib.stream_ptr(x)), "generator conditioning")
+        return y, c
+
+    ref_y, chirp_y = run(ref, chirp)
+    con_y, _ = run(con, False)
+    spec = log_mel(con_y, mel_transform)
+    if spec.shape[-1] >= crop_frames:
+        spec = spec[..., :crop_frames].contiguous()
+    else:
+        spec = torch.nn.functional.pad(spec, (0, crop_frames - spec.shape[-1]))
+    out = {"ref_audio": ref_y, "con_audio": con_y, "con_spec": spec, "seg_wave": ref_y.clone()}
+    if chirp:
+        out["chirp_wave"] = chirp_y
+    return out
