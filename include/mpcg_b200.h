@@ -181,6 +181,13 @@ int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float 
                        int flags, void* stream);
 #define MPCG_AUG_CHAIN_COLLAPSE 1
 
+/* Zero-phase IIR filtering, scipy.signal.sosfiltfilt arithmetic (reference signalproc/filters.py:44-90): odd extension by
+ * `edge` samples, forward and backward cascade passes started from zi * (first sample).  sos: HOST [n_sections, 6]
+ * (<= 6 sections); zi: HOST [n_sections, 2] = scipy.signal.sosfilt_zi(sos); work: device scratch [rows, t + 2 edge];
+ * t must exceed edge (SciPy raises ValueError otherwise -> MPCG_EINVAL). */
+int mpcg_sosfiltfilt_f32(const float* x, float* y, float* work, int64_t rows, int64_t t, const double* sos, int n_sections,
+                         const double* zi, int64_t edge, void* stream);
+
 /* Generator-dataset conditioning of one batch (reference datasets/generative.py:77-115 with
  * signalproc/preprocess.py:45-64): y [rows, crop] = fit_length(fade(abs_max_normalise(x [rows, t])), crop) with 128-sample
  * linear fade ramps (fade_n) at both ends of the length-t signal (none when t < 2 fade_n); chirp (optional, [rows, crop]) =

@@ -267,6 +267,24 @@ def main():
         print(f.name, f.stat().st_size)
 
     gen_condition_fixture(sp, versions)
+    zerophase_fixture(versions)
+
+
+def zerophase_fixture(versions):
+    """G7: zero-phase filters through the reference's signalproc/filters.py:44-90."""
+    from mpcg_wav2vec.signalproc import filters as F
+    rng = np.random.default_rng(71)
+    fs, t = 4125.0, 4000
+    x = (np.sin(2 * np.pi * 50.0 * np.arange(t) / fs)[None] * 0.5 + np.sin(2 * np.pi * 180.0 * np.arange(t) / fs)[None]
+         + 0.3 * rng.standard_normal((2, t)) + 0.7).astype(np.float32)
+    g = dict(fs=fs, x=x)
+    g["bandpass"] = np.stack([F.butter_bandpass(r, fs, 25.0, 400.0) for r in x])
+    g["lowpass"] = np.stack([F.butter_lowpass(r, fs, 150.0) for r in x])
+    g["highpass"] = np.stack([F.butter_highpass(r, fs, 20.0) for r in x])
+    g["band_stop"] = np.stack([F.band_stop(r, fs, 45.0, 55.0) for r in x])
+    g["notch"] = np.stack([F.notch(r, fs, 50.0) for r in x])
+    g["notch_chain"] = np.stack([F.notch_chain(r, fs, (50.0, 100.0, 150.0, 3000.0)) for r in x])
+    np.savez_compressed(OUT / "zerophase.npz", versions=str(versions), **g)
 
 
 def gen_condition_fixture(sp, versions):

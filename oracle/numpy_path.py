@@ -224,3 +224,41 @@ def generator_item(reference, conditioning, fs: float, crop: int):
     ref = fit_length(fade(abs_max_normalise(reference)), crop)[0]
     con = fit_length(fade(abs_max_normalise(conditioning)), crop)[0]
     return ref, con, add_chirp(ref, fs)
+
+
+# --------------------------------------------------------------------------- zero-phase filters
+def butter_bandpass_zp(x, fs: float, low: float, high: float, order: int = 4) -> np.ndarray:
+    """``signalproc/filters.py:44-48``."""
+    nyq = 0.5 * fs
+    return _sig.sosfiltfilt(_sig.butter(order, [low / nyq, high / nyq], btype="bandpass", output="sos"), np.asarray(x, dtype=np.float64))
+
+
+def butter_lowpass_zp(x, fs: float, cutoff: float, order: int = 4) -> np.ndarray:
+    """``signalproc/filters.py:51-53``."""
+    return _sig.sosfiltfilt(_sig.butter(order, cutoff / (0.5 * fs), btype="lowpass", output="sos"), np.asarray(x, dtype=np.float64))
+
+
+def butter_highpass_zp(x, fs: float, cutoff: float, order: int = 4) -> np.ndarray:
+    """``signalproc/filters.py:56-58``."""
+    return _sig.sosfiltfilt(_sig.butter(order, cutoff / (0.5 * fs), btype="highpass", output="sos"), np.asarray(x, dtype=np.float64))
+
+
+def band_stop_zp(x, fs: float, low: float, high: float, order: int = 4) -> np.ndarray:
+    """``signalproc/filters.py:78-82``."""
+    nyq = 0.5 * fs
+    return _sig.sosfiltfilt(_sig.butter(order, [low / nyq, high / nyq], btype="bandstop", output="sos"), np.asarray(x, dtype=np.float64))
+
+
+def notch_zp(x, fs: float, freq: float, q: float = 30.0) -> np.ndarray:
+    """``signalproc/filters.py:62-65``."""
+    b, a = _sig.iirnotch(freq / (0.5 * fs), q)
+    return _sig.filtfilt(b, a, np.asarray(x, dtype=np.float64))
+
+
+def notch_chain_zp(x, fs: float, freqs, q: float = 55.0) -> np.ndarray:
+    """``signalproc/filters.py:68-74``."""
+    y = np.asarray(x, dtype=np.float64)
+    for f in freqs:
+        if f < 0.5 * fs:
+            y = notch_zp(y, fs, f, q)
+    return y

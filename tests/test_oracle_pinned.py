@@ -153,3 +153,16 @@ def test_generator_conditioning_matches_golden(golden):
             ref, _, chirp = onp.generator_item(x[r], x[r], fs, crop)
             np.testing.assert_array_equal(ref, g[f"{tag}_y"][r])
             np.testing.assert_array_equal(chirp, g[f"{tag}_chirp"][r])
+
+
+def test_zero_phase_filters_match_golden(golden):
+    """the oracle's zero-phase filters against the reference's signalproc/filters.py:44-90, bit for bit."""
+    g = golden("zerophase.npz")
+    fs, x = float(g["fs"]), g["x"]
+    for r in range(x.shape[0]):
+        np.testing.assert_array_equal(onp.butter_bandpass_zp(x[r], fs, 25.0, 400.0), g["bandpass"][r])
+        np.testing.assert_array_equal(onp.butter_lowpass_zp(x[r], fs, 150.0), g["lowpass"][r])
+        np.testing.assert_array_equal(onp.butter_highpass_zp(x[r], fs, 20.0), g["highpass"][r])
+        np.testing.assert_array_equal(onp.band_stop_zp(x[r], fs, 45.0, 55.0), g["band_stop"][r])
+        np.testing.assert_array_equal(onp.notch_zp(x[r], fs, 50.0), g["notch"][r])
+        np.testing.assert_array_equal(onp.notch_chain_zp(x[r], fs, (50.0, 100.0, 150.0, 3000.0)), g["notch_chain"][r])

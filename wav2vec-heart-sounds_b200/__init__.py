@@ -10,8 +10,9 @@ from . import torchproc, torchaug
 from .torchaug import AugmentConfig, augment_pcg_batch
 from .pipeline import preprocess_segment
 from .spectrogram import MelConfig, log_mel
-from . import datasets
-from .datasets import build_fragments_batched, FragmentBatch, FragmentTensorDataset, device_batch_transform
+from . import datasets, filters
+from .datasets import (build_fragments_batched, FragmentBatch, FragmentTensorDataset, device_batch_transform,
+                       condition_generator_batch)
 
 __all__ = ["torchproc", "MelConfig", "log_mel", "torchaug", "AugmentConfig", "augment_pcg_batch", "preprocess_segment", "WindowSpec", "WINDOWS", "default_window", "design",
-           "datasets", "build_fragments_batched", "FragmentBatch", "FragmentTensorDataset", "device_batch_transform"]
+           "datasets", "filters", "build_fragments_batched", "FragmentBatch", "FragmentTensorDataset", "device_batch_transform", "condition_generator_batch"]

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "mpcg_aug_chain_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, ctypes.c_float, c_f32p, c_f32p, c_f32p, ctypes.c_uint64,
                                    ctypes.c_uint64, c_f32p, c_f32p, ctypes.c_void_p, c_int, c_f32p, c_f32p, c_f32p, c_f32p,
                                    ctypes.c_uint64, ctypes.c_uint64, c_int, ctypes.c_void_p]),
+    "mpcg_sosfiltfilt_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p, c_i64,
+                                     ctypes.c_void_p]),
     "mpcg_gen_condition_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_i64, c_int, ctypes.c_double, c_int,
                                        ctypes.c_void_p]),
     "mpcg_mel_tc_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p,
