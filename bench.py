@@ -1,19 +1,22 @@
 #!/usr/bin/env python
-"""Headline benchmark: PCG audio-seconds preprocessed per second (BASELINE.json metric).
+"""Headline benchmark: PCG audio-seconds preprocessed + augmented per second (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload (BASELINE.json configs[1], named in `config.workload`): 1024 synthetic Training-A-shaped recordings per
 GPU, two channels (PCG + ECG), 30 s at 2 kHz -> resample to 4125 Hz, Schmidt despike (PCG), 25-450 Hz / 2-40 Hz
-band (fs-normalised, as the reference does), abs-max normalise, 4 s windows with 0.25 s overlap.
-A step = one pass of the hot path over that batch.
+band (fs-normalised, as the reference does), abs-max normalise, 4 s windows with 0.25 s overlap; then the torchaug
+chain (augment_pcg_batch, default AugmentConfig: noise, wandering volume, parametric EQ, noise, each behind its per-row
+mask) on the 7168 PCG windows that come out.  A step = one pass of the hot path over that batch: two launches of
+this repo's kernels (fused preprocess+segment, fused augmentation chain).
 
-  value      whole-job audio-s/s with inputs already resident in HBM (one fused kernel launch per step),
+  value      whole-job audio-s/s with inputs already resident in HBM (two kernel launches per step),
              CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
   e2e        same metric through HostPipeline: pinned HOST buffers in, HOST buffers out, copies inside the
              timed region.
-  roofline   algorithmic bytes of the fused kernel (input read once + windows written once) / its measured
-             duration, against the measured HBM peak in MEASURED_PEAKS.json.
+  roofline   the dominant kernel (fused preprocess+segment, ~70 % of a step): its algorithmic bytes (input read once +
+             windows written once) / its own duration (CUDA events around each of its launches inside the timed
+             region), against the measured HBM peak in MEASURED_PEAKS.json.  `stages` holds both kernels' times.
   other_paths   (N=1) kernel times of the fused augmentation chain (configs[2]) and the tensor-core log-mel
              (configs[3]) at their BASELINE.json shapes, measured outside the timed region.
   cpu_baseline  the NumPy oracle (the reference's CPU algorithm, restated in oracle/numpy_path.py) timed on the
@@ -43,10 +46,11 @@ FS_IN, FS_OUT = 2000, 4125
 SECONDS = T_IN / FS_IN
 WINDOW_S = 4.0
 KINDS = ("pcg", "ecg")
-METRIC = "PCG audio-seconds preprocessed/sec"
+METRIC = "PCG audio-seconds preprocessed+augmented/sec"
 UNIT = "audio-s/s"
 WORKLOAD = ("configs[1]: Training-A-shaped PCG+ECG two-channel preprocessing, 1024 synthetic 30 s recordings per GPU, "
-            "2 kHz -> 4125 Hz, despike (PCG), PCG 25-450 Hz / ECG 2-40 Hz band, abs-max norm, 4 s / 0.25 s-overlap windows")
+            "2 kHz -> 4125 Hz, despike (PCG), PCG 25-450 Hz / ECG 2-40 Hz band, abs-max norm, 4 s / 0.25 s-overlap windows, "
+            "then augment_pcg_batch (default AugmentConfig) on the 7168 PCG windows per GPU")
 
 
 def measured_peak():
@@ -67,15 +71,38 @@ def recorded_traffic():
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def _cpu_one(args):
-    """One recording through the reference's NumPy algorithm (oracle port): both channels + windows."""
+def _cpu_draws(rng, rows, t):
+    """Random draws of one augment_pcg_batch call in the oracle's injected form (default AugmentConfig probabilities)."""
     import numpy as np
+    import torch
+    u = lambda *s: torch.from_numpy(rng.random(s))
+    bands = []
+    for _ in range(5):
+        lo = float(rng.uniform(2, 0.95 * 500))
+        bands.append((lo, float(rng.uniform(lo + 0.05 * 498, 500))))
+    d = {"std1": float(rng.choice([1e-4, 1e-3, 1e-2])), "scale1": u(rows, 1) * 0.1, "noise1": torch.from_numpy(rng.standard_normal((rows, t))),
+         "mask1": (u(rows, 1) < 0.3 / 4).double(), "amp": 0.01 + u(rows, 2) * 0.24, "phase": u(rows, 2),
+         "freq": torch.stack([0.05 + u(rows) * 0.45, 0.001 + u(rows) * 0.049], dim=1), "mask2": (u(rows, 1) < 0.75).double(),
+         "bands": bands, "mask3": (u(rows, 1) < 0.25).double(), "std2": float(rng.choice([1e-4, 1e-3, 1e-2])),
+         "scale2": u(rows, 1) * 0.1, "noise2": torch.from_numpy(rng.standard_normal((rows, t))), "mask4": (u(rows, 1) < 0.3 / 4).double()}
+    return d
+
+
+def _cpu_one(args):
+    """One recording through the reference's CPU algorithms (oracle ports): NumPy preprocessing of both channels +
+    windows, then the torchaug chain on the PCG windows (float64, as the parity tests run it)."""
+    import numpy as np
+    import torch
     from oracle import numpy_path as onp
-    pcg, ecg = args
+    from oracle import torch_path as otp
+    pcg, ecg, seed = args
     spec = onp.WindowSpec(WINDOW_S)
     p = onp.preprocess_pcg(pcg, FS_IN, FS_OUT)
     e = onp.preprocess_ecg(ecg, FS_IN, FS_OUT)
-    return onp.segment(np.stack([p, e], axis=1), FS_OUT, spec).shape[0]
+    w = onp.segment(np.stack([p, e], axis=1), FS_OUT, spec)                  # [N, win, 2]
+    wp = torch.from_numpy(np.ascontiguousarray(w[:, :, 0]))
+    aug = otp.augment_pcg_batch(wp, FS_OUT, _cpu_draws(np.random.default_rng(seed), wp.shape[0], wp.shape[1]))
+    return w.shape[0] + int(aug.shape[0])
 
 
 def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234):
@@ -84,7 +111,7 @@ def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234):
     from wav2vec_heart_sounds_b200.synth import synth_pair
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     x = synth_pair(n_recordings, T_IN, FS_IN, seed=seed).numpy()
-    work = [(x[i, 0], x[i, 1]) for i in range(n_recordings)]
+    work = [(x[i, 0], x[i, 1], seed + i) for i in range(n_recordings)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_one, work[:cores])                     # warm the workers (imports, FFT plans)
@@ -106,8 +133,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    # bounded sample: K + W steps must fit in ~90 s of wall clock at ~0.25 core-seconds per recording
-    per_step = int(90.0 / (args.steps + args.warmup) * cores / 0.25)
+    # bounded sample: K + W steps must fit in ~90 s of wall clock at ~0.35 core-seconds per recording
+    per_step = int(90.0 / (args.steps + args.warmup) * cores / 0.35)
     per_step = max(cores, min(per_step, RECORDINGS))
     torch.set_num_threads(1)
     vals = []
@@ -119,7 +146,8 @@ def run_reference(args):
         vals.append(v)
         t_all += dt
     value = per_step * SECONDS * args.steps / t_all
-    sample = f"{per_step} recordings per step (2 channels x 30 s), {cores} worker processes, NumPy/SciPy float64"
+    sample = (f"{per_step} recordings per step (2 channels x 30 s; NumPy/SciPy float64 preprocessing + windows, then the "
+              f"torchaug chain on the PCG windows in float64 on CPU), {cores} worker processes")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -205,13 +233,32 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # shard `rank` of the job: its own 1024 recordings, generated on the device (no host or peer traffic)
+    from wav2vec_heart_sounds_b200 import AugmentConfig, torchaug
+    import numpy as np
+    cfg = AugmentConfig()
+    torch.manual_seed(1234 + rank)
+    np.random.seed(1234 + rank)
     x = synth_pair(RECORDINGS, T_IN, FS_IN, seed=1234 + rank, device=dev)
-    out = pkg.preprocess_segment(x, FS_IN, FS_OUT, spec, kinds=KINDS, fused=True)     # also the first warm-up
+    # channel-major windows [2, B, N, win]: the PCG windows are one contiguous [B * N, win] batch for the augmentation
+    out = pkg.preprocess_segment(x, FS_IN, FS_OUT, spec, kinds=KINDS, fused=True, channel_major=True)   # also a warm-up
     n_win, win = out.shape[2], out.shape[3]
+    pcg_windows = out[0].view(RECORDINGS * n_win, win)
+    aug_out = torch.empty_like(pcg_windows)
     algo_bytes = x.numel() * 4 + out.numel() * 4
+    aug_bytes = 2 * pcg_windows.numel() * 4
+    ev = []
 
-    def step():
-        pkg.preprocess_segment(x, FS_IN, FS_OUT, spec, kinds=KINDS, fused=True, out=out)
+    def step(timed=False):
+        if timed:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+        pkg.preprocess_segment(x, FS_IN, FS_OUT, spec, kinds=KINDS, fused=True, channel_major=True, out=out)
+        if timed:
+            e1.record()
+        torchaug.augment_pcg_batch(pcg_windows, FS_OUT, cfg, noise="philox", fused=True, out=aug_out)
+        if timed:
+            e2.record()
+            ev.append((e0, e1, e2))
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -220,19 +267,22 @@ def run_ours(args):
     with ClockSampler(local) as clocks:
         start.record()
         for _ in range(args.steps):
-            step()
+            step(timed=True)
         stop.record()
         barrier()
     ms = start.elapsed_time(stop)
+    pre_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / args.steps         # the fused preprocess kernel alone
+    aug_ms = sum(b.elapsed_time(c) for _, b, c in ev) / args.steps         # the augmentation chain (its small RNG launches included)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * RECORDINGS * SECONDS * args.steps / (ms * 1e-3)
-    kernel_ms = ms / args.steps                                   # one launch per step
+    step_ms = ms / args.steps
+    kernel_ms = pre_ms
 
     # ---- end to end: host buffers in, host buffers out
-    hp = HostPipeline(RECORDINGS, 2, T_IN, FS_IN, FS_OUT, spec, kinds=KINDS, chunk=32, device=dev)
+    hp = HostPipeline(RECORDINGS, 2, T_IN, FS_IN, FS_OUT, spec, kinds=KINDS, chunk=64, device=dev, augment=cfg)
     x_host = x.cpu().pin_memory()
     out_host = hp.empty_output()
     e2e_steps = max(3, min(args.steps, 10))
@@ -249,34 +299,49 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * RECORDINGS * SECONDS * e2e_steps / float(t.item())
-    same = bool(torch.equal(out_host[:8], out[:8].cpu()))
+    same = bool(torch.equal(out_host[1, :8], out[1, :8].cpu()))               # the ECG windows (the PCG ones carry fresh random draws)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 samples, f64 filter/normalise state", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "recordings_per_gpu": RECORDINGS, "channels": list(KINDS),
-                           "layout": f"[{RECORDINGS}, 2, {T_IN}] -> [{RECORDINGS}, 2, {n_win}, {win}]", "mode": "torch",
-                           "cache": "inputs (492 MB) and outputs (946 MB) per step exceed the 126 MB L2",
+                           "layout": f"[{RECORDINGS}, 2, {T_IN}] -> [2, {RECORDINGS}, {n_win}, {win}] -> PCG [{RECORDINGS * n_win}, {win}] augmented",
+                           "mode": "torch", "augment": "default AugmentConfig, in-kernel Philox noise, fresh draws every step",
+                           "cache": "inputs (492 MB), windows (946 MB) and augmented windows (473 MB) per step exceed the 126 MB L2",
                            "sharding": f"{world} x index-sharded, no collective"},
-                "gpu_launches": args.steps,
+                "gpu_launches": 2 * args.steps,
+                "stages": {"preprocess_segment_ms": pre_ms, "augment_chain_ms": aug_ms,
+                           "preprocess_only_audio_s_per_s": RECORDINGS * SECONDS / (pre_ms * 1e-3),
+                           "augment_GB/s": aug_bytes / (aug_ms * 1e-3) / 1e9},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
                         "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "matches_device_run": same},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": recorded_traffic(), "algorithmic_bytes_per_launch": algo_bytes,
-                             "kernel": "fused_preprocess_kernel<33,16,30,4>", "peak_source": peak_src},
+                             "kernel": "fused_preprocess_kernel<33,16,30,4>", "share_of_step": pre_ms / step_ms,
+                             "peak_source": peak_src},
                 "clocks": clocks.summary()}
         if world == 1 and not args.no_extras:
             line["other_paths"] = other_paths(dev, peak)
         if world == 1 and not args.no_cpu:
+            # a fresh interpreter: the CPU leg forks worker processes that run torch CPU ops, which must not inherit
+            # this process's CUDA context and thread pools
+            import subprocess
             cores = host_cores()
-            n = min(RECORDINGS, 40 * cores)                   # ~10 s of wall clock on the host cores
-            v, dt = cpu_throughput(n, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n} of the {RECORDINGS} recordings, NumPy/SciPy float64 oracle "
-                                              f"(oracle/numpy_path.py), {cores} worker processes, {dt:.1f} s"}
+            n = min(RECORDINGS, 32 * cores)                   # ~10 s of wall clock on the host cores
+            try:
+                proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", str(n)], capture_output=True,
+                                      text=True, timeout=240, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+                leg = json.loads(proc.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = {"value": leg["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"{n} of the {RECORDINGS} recordings, NumPy/SciPy float64 oracle "
+                                                  f"(oracle/numpy_path.py) + float64 torchaug chain (oracle/torch_path.py), "
+                                                  f"{cores} worker processes, {leg['seconds']:.1f} s"}
+            except Exception as exc:                          # never lose the GPU line over the CPU leg
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"CPU leg failed: {type(exc).__name__}: {exc}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -347,8 +412,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the augmentation / mel side measurements")
+    ap.add_argument("--cpu-leg", type=int, default=0, help=argparse.SUPPRESS)      # internal: time the CPU port on N recordings
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.cpu_leg > 0:
+        torch.set_num_threads(1)
+        v, dt = cpu_throughput(args.cpu_leg, host_cores())
+        print(json.dumps({"value": v, "seconds": dt}))
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

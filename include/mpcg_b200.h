@@ -112,7 +112,7 @@ typedef struct mpcg_chain_desc {
   int median_mode;              /* MPCG_MEDIAN_*                                                      */
   int norm_flags;               /* MPCG_NORM_*                                                        */
   int64_t seg_start, seg_win, seg_hop, seg_n;   /* seg_n = mpcg_window_count(t_out, start, win, hop)  */
-  int channels_last;            /* 0: out[rec, ch, n, win]   1: out[rec, n, win, ch]                  */
+  int channels_last;            /* 0: out[rec, ch, n, win]   1: out[rec, n, win, ch]   2: out[ch, rec, n, win] */
   int n_kinds;                  /* 1 or 2 distinct channel recipes                                    */
   mpcg_chain_kind kinds[2];
   uint8_t kind_of_channel[8];   /* recipe index of each channel (channels <= 8)                       */

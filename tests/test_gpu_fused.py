@@ -236,3 +236,34 @@ def test_fused_config5_chunk_properties(pkg):
     # three recordings against the float64 oracle
     want, _ = _oracle_torch(x[7].cpu().numpy(), 4000, 4125, 2.0)
     assert rel_err(planar[7].cpu().numpy(), want) < TOL
+
+
+def test_channel_major_layout_and_host_pipeline_augment(pkg):
+    """channel_major output ([C, B, N, win]: every channel one contiguous batch of windows) equals the planar one;
+    HostPipeline(augment=...) returns the ECG windows untouched and normalised augmented PCG windows."""
+    from wav2vec_heart_sounds_b200.pipeline import HostPipeline
+    from wav2vec_heart_sounds_b200.synth import synth_pair
+    from wav2vec_heart_sounds_b200 import AugmentConfig
+    x = synth_pair(70, 20000, 2000, seed=3, device="cuda")
+    spec = pkg.WindowSpec(4.0)
+    planar = pkg.preprocess_segment(x, 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True)
+    cm = pkg.preprocess_segment(x, 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True, channel_major=True)
+    assert cm.shape == (2, 70) + tuple(planar.shape[2:])
+    assert torch.equal(cm.permute(1, 0, 2, 3), planar)
+    with pytest.raises(ValueError):
+        pkg.preprocess_segment(x, 2000, 4125, spec, kinds=("pcg", "ecg"), fused=False, channel_major=True)
+    hp = HostPipeline(70, 2, 20000, 2000, 4125, spec, kinds=("pcg", "ecg"), chunk=32, augment=AugmentConfig())
+    oh = hp.empty_output()
+    torch.manual_seed(0); np.random.seed(0)
+    hp(x.cpu().pin_memory(), oh)
+    torch.cuda.synchronize()
+    assert oh.shape == cm.shape
+    assert torch.equal(oh[1], cm[1].cpu())                                   # ECG windows pass through
+    a = oh[0].reshape(-1, oh.shape[-1])
+    assert torch.isfinite(a).all() and float(a.abs().max()) <= 1.0
+    assert float(a.mean(dim=1).abs().max()) < 1e-5 and float((a.abs().amax(dim=1) - 1).abs().max()) < 1e-5
+    plain = HostPipeline(70, 2, 20000, 2000, 4125, spec, kinds=("pcg", "ecg"), chunk=32)
+    op = plain.empty_output()
+    plain(x.cpu().pin_memory(), op)
+    torch.cuda.synchronize()
+    assert torch.equal(op, planar.cpu())

@@ -178,7 +178,10 @@ extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t r
     P.serial_despike = (e && atoi(e) != 0) ? 1 : 0;
   }
   P.start = (int)d->seg_start; P.win = (int)d->seg_win; P.hop = (int)d->seg_hop; P.n = (int)d->seg_n;
-  if (d->channels_last) {
+  if (d->channels_last == 2) {                             // channel-major: out[channel, recording, window, sample]
+    P.so_j = 1; P.so_k = d->seg_win; P.so_b = (long long)d->seg_n * d->seg_win;
+    P.so_c = (long long)recordings * d->seg_n * d->seg_win;
+  } else if (d->channels_last) {
     P.so_j = channels; P.so_c = 1; P.so_k = (long long)d->seg_win * channels;
     P.so_b = (long long)d->seg_n * d->seg_win * channels;
   } else {

@@ -35,7 +35,7 @@ def _kind_struct(kind: str, fs_out: float, despike: bool) -> _lib.ChainKind:
 def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, kinds=None, despike: bool = True,
                        mode: str = "torch", channels_last: bool = False, return_trace: bool = False,
                        trace_cap: int = 64, fused: bool | None = None, out: torch.Tensor | None = None,
-                       return_edits: bool = False):
+                       return_edits: bool = False, channel_major: bool = False):
     """``[B, T]`` -> ``[B, N, win]``  or  ``[B, C, T]`` -> ``[B, C, N, win]`` (``[B, N, win, C]`` with
     ``channels_last``): resample, (PCG only) Schmidt despike, band-limit, abs-max normalise, segment.
 
@@ -44,7 +44,8 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
     ``False`` = always chain the stand-alone kernels.  ``out``: optional preallocated result tensor.
     ``return_trace``: also return ``(edits[B*C], trace[B*C, cap, 4])``, the despike passes in the reference's order
     (this takes the fused kernel's serial despike path); ``return_edits``: also return the pass counts alone
-    (fused kernel only; the fast despike path stays on).
+    (fused kernel only; the fast despike path stays on).  ``channel_major``: ``[B, C, T]`` -> ``[C, B, N, win]`` (every
+    channel's windows form one contiguous ``[B * N, win]`` batch, ready for ``augment_pcg_batch``; fused kernel only).
     """
     torchproc._check_mode(mode)
     x = _lib.require_cuda_f32(x)
@@ -58,6 +59,8 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
         raise ValueError(f"kinds must name 'pcg' or 'ecg' for each of the {c} channels")
     if channels_last and planar_in:
         raise ValueError("channels_last needs a [B, C, T] input")
+    if channel_major and (planar_in or channels_last or fused is False):
+        raise ValueError("channel_major needs a [B, C, T] input, the fused kernel and excludes channels_last")
     win, hop, start = spec.window_len(fs_out), spec.hop_len(fs_out), start_index(fs_out, spec)
 
     same_rate = fs_in == fs_out
@@ -70,6 +73,8 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
             same_rate, t_out = True, t_in
     n = int(_lib.lib().mpcg_window_count(t_out, start, win, hop))
     shape = (b, n, win, c) if channels_last else ((b, n, win) if planar_in else (b, c, n, win))
+    if channel_major:
+        shape = (c, b, n, win)
 
     edits = trace = None
     if return_trace:
@@ -92,7 +97,7 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
             d.median_mode = _lib.MEDIAN_LOWER if mode == "torch" else _lib.MEDIAN_MEAN
             d.norm_flags = _lib.NORM_NAN_TO_NUM if mode == "torch" else _lib.NORM_PEAK_GT0
             d.seg_start, d.seg_win, d.seg_hop, d.seg_n = start, win, hop, n
-            d.channels_last = 1 if channels_last else 0
+            d.channels_last = 2 if channel_major else (1 if channels_last else 0)
             d.n_kinds = len(uniq)
             for i, k in enumerate(uniq):
                 d.kinds[i] = _kind_struct(k, fs_out, despike)
@@ -110,7 +115,7 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
                 if return_trace:
                     return out, edits, trace
                 return (out, edits) if return_edits else out
-    if fused is True or (return_edits and not return_trace):
+    if fused is True or channel_major or (return_edits and not return_trace):
         raise ValueError("this geometry does not fit the fused kernel")
 
     # ---- chained stand-alone kernels (same arithmetic, more HBM traffic)
@@ -141,22 +146,37 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
 class HostPipeline:
     """Host buffers in, host buffers out: the call a loader makes per batch of recordings.
 
-    The batch is cut into chunks; chunk i's host->device copy, chunk i-1's kernel and chunk i-2's device->host
+    The batch is cut into chunks; chunk i's host->device copy, chunk i-1's kernel(s) and chunk i-2's device->host
     copy run concurrently on three CUDA streams (PCIe is full duplex), so a step costs about
     max(H2D, D2H) instead of their sum.  Buffers are allocated once and reused.
+
+    ``augment`` (an ``AugmentConfig`` or ``True``): the windows of channel 0 (the PCG) also go through the fused
+    ``augment_pcg_batch`` chain before they leave the device; the output is then channel-major ``[C, B, N, win]``.
     """
 
     def __init__(self, recordings: int, channels: int, t_in: int, fs_in: float, fs_out: float, spec, *, kinds=None,
-                 mode: str = "torch", channels_last: bool = False, chunk: int = 128, device="cuda"):
+                 mode: str = "torch", channels_last: bool = False, chunk: int = 128, device="cuda", augment=None):
+        self.augment = augment
+        if augment is not None and channels_last:
+            raise ValueError("augment uses the channel-major layout; channels_last is not available with it")
         self.args = dict(fs_in=fs_in, fs_out=fs_out, spec=spec, kinds=kinds, mode=mode, channels_last=channels_last)
+        if augment is not None:
+            self.args["channel_major"] = True
+        self.fs_out = fs_out
         self.device = torch.device(device)
         self.chunk = min(chunk, recordings)
         self.recordings, self.channels, self.t_in = recordings, channels, t_in
         probe = preprocess_segment(torch.zeros(1, channels, t_in, device=self.device), **self.args)
-        self.out_shape = (recordings,) + tuple(probe.shape[1:])
         nbuf = 3
         self.dev_in = [torch.empty(self.chunk, channels, t_in, device=self.device) for _ in range(nbuf)]
-        self.dev_out = [torch.empty((self.chunk,) + tuple(probe.shape[1:]), device=self.device) for _ in range(nbuf)]
+        if augment is None:
+            self.out_shape = (recordings,) + tuple(probe.shape[1:])
+            self.dev_out = [torch.empty((self.chunk,) + tuple(probe.shape[1:]), device=self.device) for _ in range(nbuf)]
+        else:
+            self.win_shape = tuple(probe.shape[2:])                                   # (N, win)
+            self.out_shape = (channels, recordings) + self.win_shape
+            self.dev_out = [torch.empty((channels, self.chunk) + self.win_shape, device=self.device) for _ in range(nbuf)]
+            self.dev_aug = [torch.empty((self.chunk,) + self.win_shape, device=self.device) for _ in range(nbuf)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self.h2d_bytes = recordings * channels * t_in * 4
         self.d2h_bytes = int(torch.tensor(self.out_shape).prod()) * 4
@@ -168,31 +188,47 @@ class HostPipeline:
         """x_host [recordings, channels, t_in] (pinned for speed) -> out_host (pinned), both on the host."""
         if x_host.is_cuda or out_host.is_cuda:
             raise ValueError("HostPipeline takes host tensors; use preprocess_segment for device tensors")
+        from . import torchaug
         n = self.recordings
         nbuf = len(self.dev_in)
         copied = [torch.cuda.Event() for _ in range(nbuf)]
         ran = [torch.cuda.Event() for _ in range(nbuf)]
         drained = [torch.cuda.Event() for _ in range(nbuf)]
         entry = torch.cuda.current_stream(self.device)
+        cfg = None if self.augment in (None, True) else self.augment
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(entry)
         for i, lo in enumerate(range(0, n, self.chunk)):
             hi = min(lo + self.chunk, n)
+            m = hi - lo
             b = i % nbuf
             with torch.cuda.stream(self.s_in):
                 if i >= nbuf:
                     self.s_in.wait_event(ran[b])              # the kernel that read this buffer is done
-                self.dev_in[b][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                self.dev_in[b][:m].copy_(x_host[lo:hi], non_blocking=True)
                 copied[b].record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(copied[b])
                 if i >= nbuf:
                     self.s_run.wait_event(drained[b])         # the copy-out that read this buffer is done
-                preprocess_segment(self.dev_in[b][: hi - lo], out=self.dev_out[b][: hi - lo], **self.args)
+                if self.augment is None:
+                    preprocess_segment(self.dev_in[b][:m], out=self.dev_out[b][:m], **self.args)
+                else:
+                    dout = self.dev_out[b].view(-1)[: self.channels * m * self.win_shape[0] * self.win_shape[1]]
+                    dout = dout.view((self.channels, m) + self.win_shape)
+                    preprocess_segment(self.dev_in[b][:m], out=dout, **self.args)
+                    daug = self.dev_aug[b][:m]
+                    torchaug.augment_pcg_batch(dout[0].reshape(m * self.win_shape[0], self.win_shape[1]), self.fs_out, cfg,
+                                               noise="philox", out=daug.view(m * self.win_shape[0], self.win_shape[1]))
                 ran[b].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ran[b])
-                out_host[lo:hi].copy_(self.dev_out[b][: hi - lo], non_blocking=True)
+                if self.augment is None:
+                    out_host[lo:hi].copy_(self.dev_out[b][:m], non_blocking=True)
+                else:
+                    out_host[0, lo:hi].copy_(daug, non_blocking=True)
+                    for c in range(1, self.channels):
+                        out_host[c, lo:hi].copy_(dout[c], non_blocking=True)
                 drained[b].record(self.s_out)
         for s in (self.s_in, self.s_run, self.s_out):
             entry.wait_stream(s)

@@ -191,7 +191,8 @@ def parametric_eq(x: torch.Tensor, fs: float, low: float, high: float, num_bands
 
 
 def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None, *, draws: dict | None = None,
-                      noise: str | None = None, fused: bool | None = None, collapse: bool = True) -> torch.Tensor:
+                      noise: str | None = None, fused: bool | None = None, collapse: bool = True,
+                      out: torch.Tensor | None = None) -> torch.Tensor:
     """Noise -> wandering volume -> EQ -> noise, each behind a per-row Bernoulli mask, every row re-normalised
     after every stage (reference torchaug.py:103-111).  ``draws`` injects every random quantity (keys as in
     ``oracle.torch_path.augment_pcg_batch``); ``noise="philox"`` draws the white noise inside the kernel.
@@ -225,7 +226,11 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
         m3 = mask_of("mask3", cfg.prob_banding)
         rowp4, nz4, seed4, sid4, m4 = noise_draws(2, "mask4")
         sos = np.ascontiguousarray(design.eq_band_sos(fs, bands), dtype=np.float64)
-        out = torch.empty_like(x)
+        if out is None:
+            out = torch.empty_like(x)
+        elif out.shape != x.shape or not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or \
+                out.data_ptr() == x.data_ptr():
+            raise ValueError("out must be a contiguous CUDA float32 tensor of x's shape that does not alias x")
         rc = _lib.lib().mpcg_aug_chain_f32(x.data_ptr(), out.data_ptr(), b, x.shape[1], float(fs), rowp1.data_ptr(),
                                            _lib.ptr(nz1), m1.data_ptr(), seed1, sid1, rowp2.data_ptr(), m2.data_ptr(),
                                            sos.ctypes.data, sos.shape[0], m3.data_ptr(), rowp4.data_ptr(), _lib.ptr(nz4),
@@ -256,6 +261,9 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
     m3 = pre["m3"] if pre else mask_of("mask3", cfg.prob_banding)
     x = _eq_mix(x, _coloured(x, fs, bands, m3), m3, False)
     x = noise_stage(x, 2, "mask4", "n4")
+    if out is not None:
+        out.copy_(x)
+        return out
     return x
 
 
