@@ -189,7 +189,8 @@ def test_fused_chain_equals_stage_kernels(ta, t, rows, noise):
         outs = []
         for fused, collapse in ((True, True), (True, False), (False, False)):
             torch.manual_seed(3); np.random.seed(3)
-            outs.append(ta.augment_pcg_batch(x, 4125, cfg, noise=noise, fused=fused, collapse=collapse))
+            outs.append(ta.augment_pcg_batch(x, 4125, cfg, noise=noise, fused=fused, collapse=collapse,
+                                             fast_draws=False if fused else None))
         assert torch.isfinite(outs[0]).all()
         assert float((outs[1] - outs[2]).abs().max()) < 2e-6       # every stage re-normalised: float32 rounding apart
         assert float((outs[0] - outs[2]).abs().max()) < 4e-6       # idempotent re-normalisations collapsed
@@ -225,3 +226,28 @@ def test_fused_chain_full_size_properties(ta):
     off = AugmentConfig(prob_noise=0.0, prob_wandering_volume=0.0, prob_banding=0.0)
     z = ta.augment_pcg_batch(x[:512], 16000, off, noise="philox")
     assert float((z - ta._normalise(x[:512])).abs().max()) < 1e-6
+
+
+def test_fast_draws_distributions(ta):
+    """Throughput mode (noise="philox", no injected draws): the per-row quantities come from two device draws; their
+    distributions are the reference's (torchaug.py:39-54,103-111) and the run is reproducible under torch / numpy seeds."""
+    from wav2vec_heart_sounds_b200 import AugmentConfig
+    b = 20000
+    scale, offset = ta._fast_draw_affine(0.01, 0.001, torch.device("cuda"))
+    torch.manual_seed(1)
+    tab = torch.addcmul(offset, torch.rand(3, b, 8, device="cuda"), scale)
+    assert float(tab[0, :, 0].min()) >= 0 and float(tab[0, :, 0].max()) <= 0.1 * 0.01 and float(tab[0, :, 1:].abs().max()) == 0
+    assert 0.0009 * 0.1 * 0.5 * 0.9 < float(tab[2, :, 0].mean()) * 0.9 and float(tab[2, :, 0].max()) <= 0.1 * 0.001 * 1.0000001
+    amp, freq, phase = tab[1, :, 0], tab[1, :, 1], tab[1, :, 2]
+    assert 0.01 <= float(amp.min()) and float(amp.max()) <= 0.25 and abs(float(amp.mean()) - 0.13) < 0.005
+    assert 0.05 <= float(freq.min()) and float(freq.max()) <= 0.5 and 0.001 <= float(tab[1, :, 4].min()) and float(tab[1, :, 4].max()) <= 0.05
+    assert 0 <= float(phase.min()) and float(phase.max()) < 1 and float(tab[1, :, 6:].abs().max()) == 0
+    x = torch.randn(512, 4125, device="cuda")
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(9); np.random.seed(9)
+        outs.append(ta.augment_pcg_batch(x, 4125, AugmentConfig(), noise="philox"))
+    assert torch.equal(outs[0], outs[1])
+    base = ta._normalise(x)
+    changed = ((outs[0] - base).abs().amax(dim=1) > 1e-4).float().mean()
+    assert 0.6 < float(changed) < 0.95                         # P(at least one stage on) = 1 - .925 * .25 * .75 * .925 = 0.84

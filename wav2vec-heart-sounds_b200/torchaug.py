@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import functools
+
 import numpy as np
 import torch
 
@@ -113,6 +115,23 @@ def _draw_bands(low, high, num_bands, bands=None):
     return out
 
 
+@functools.lru_cache(maxsize=64)
+def _fast_draw_affine(std1: float, std4: float, device):
+    """(scale, offset) [3, 1, 8] turning U(0,1) into the rows of (noise 1 | wandering volume | noise 2) parameter tables:
+    noise p[0] = U * 0.1 * std; volume (amp, freq, phase) per band = 0.01 + U * 0.24, lo + U * (hi - lo), U."""
+    scale, offset = np.zeros((3, 1, 8), np.float32), np.zeros((3, 1, 8), np.float32)
+    scale[0, 0, 0], scale[2, 0, 0] = np.float32(0.1) * np.float32(std1), np.float32(0.1) * np.float32(std4)
+    for k, (lo, hi) in enumerate(_SINE_BANDS):
+        scale[1, 0, 3 * k:3 * k + 3] = (0.24, hi - lo, 1.0)
+        offset[1, 0, 3 * k:3 * k + 3] = (0.01, lo, 0.0)
+    return torch.from_numpy(scale).to(device), torch.from_numpy(offset).to(device)
+
+
+@functools.lru_cache(maxsize=64)
+def _fast_draw_probs(p1: float, p2: float, p3: float, device):
+    return torch.tensor([[p1], [p2], [p3], [p1]], dtype=torch.float32, device=device)
+
+
 def _philox_key():
     """A fresh (seed, stream) pair drawn from torch's CPU generator so torch.manual_seed controls it."""
     v = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
@@ -192,7 +211,7 @@ def parametric_eq(x: torch.Tensor, fs: float, low: float, high: float, num_bands
 
 def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None, *, draws: dict | None = None,
                       noise: str | None = None, fused: bool | None = None, collapse: bool = True,
-                      out: torch.Tensor | None = None) -> torch.Tensor:
+                      out: torch.Tensor | None = None, fast_draws: bool | None = None) -> torch.Tensor:
     """Noise -> wandering volume -> EQ -> noise, each behind a per-row Bernoulli mask, every row re-normalised
     after every stage (reference torchaug.py:103-111).  ``draws`` injects every random quantity (keys as in
     ``oracle.torch_path.augment_pcg_batch``); ``noise="philox"`` draws the white noise inside the kernel.
@@ -202,7 +221,10 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
     normalise each).  Both paths consume the random draws in the reference's order and perform the same arithmetic.
     ``collapse`` (fused path): a stage whose mask is off for a row does not normalise the already normalised row a
     second time -- ``N(N(x)) == N(x)`` up to float32 rounding (~1e-7 of the [-1, 1] range, far inside the 1e-5
-    tolerance) -- which saves that stage's sweep and its cluster exchange; ``False`` re-normalises every time."""
+    tolerance) -- which saves that stage's sweep and its cluster exchange; ``False`` re-normalises every time.
+    ``fast_draws`` (default with ``noise="philox"`` and no injected ``draws``): the per-row random quantities come from
+    two device draws (same distributions as the reference, its own random stream) instead of the reference's sequence
+    of ~40 small launches; ``False`` keeps the reference's draw order."""
     cfg = cfg or AugmentConfig()
     x = _rows2d(x)
     b, dev = x.shape[0], x.device
@@ -218,13 +240,31 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
         return rowp, nz, seed, sid, mask_of(mask_key, cfg.prob_noise / 4)
 
     if fused is not False and x.shape[1] > 0 and b > 0:
-        # every draw first (reference order), then one launch
-        rowp1, nz1, seed1, sid1, m1 = noise_draws(1, "mask1")
-        rowp2 = _draw_sines(x, 0.24, d.get("amp"), d.get("freq"), d.get("phase"))
-        m2 = mask_of("mask2", cfg.prob_wandering_volume)
-        bands = _draw_bands(2, 500, 5, d.get("bands"))
-        m3 = mask_of("mask3", cfg.prob_banding)
-        rowp4, nz4, seed4, sid4, m4 = noise_draws(2, "mask4")
+        if fast_draws is None:
+            fast_draws = noise == "philox" and not d
+        if fast_draws and (noise != "philox" or d):
+            raise ValueError("fast_draws goes with noise='philox' and no injected draws")
+        if fast_draws:
+            # throughput mode: every per-row quantity from two device draws (a [3, B, 8] parameter table and a [4, B]
+            # mask table) instead of the reference's ~40 small launches; same distributions, its own random stream
+            std1, std4 = float(np.random.choice(_NOISE_STDS)), float(np.random.choice(_NOISE_STDS))
+            scale, offset = _fast_draw_affine(std1, std4, dev)
+            tab = torch.addcmul(offset, torch.rand(3, b, 8, device=dev), scale)
+            probs = _fast_draw_probs(cfg.prob_noise / 4, cfg.prob_wandering_volume, cfg.prob_banding, dev)
+            masks = (torch.rand(4, b, device=dev) < probs).float()
+            rowp1, rowp2, rowp4 = tab[0], tab[1], tab[2]
+            m1, m2, m3, m4 = masks[0], masks[1], masks[2], masks[3]
+            nz1 = nz4 = None
+            (seed1, sid1), (seed4, sid4) = _philox_key(), _philox_key()
+            bands = _draw_bands(2, 500, 5, None)
+        else:
+            # every draw first (reference order), then one launch
+            rowp1, nz1, seed1, sid1, m1 = noise_draws(1, "mask1")
+            rowp2 = _draw_sines(x, 0.24, d.get("amp"), d.get("freq"), d.get("phase"))
+            m2 = mask_of("mask2", cfg.prob_wandering_volume)
+            bands = _draw_bands(2, 500, 5, d.get("bands"))
+            m3 = mask_of("mask3", cfg.prob_banding)
+            rowp4, nz4, seed4, sid4, m4 = noise_draws(2, "mask4")
         sos = np.ascontiguousarray(design.eq_band_sos(fs, bands), dtype=np.float64)
         if out is None:
             out = torch.empty_like(x)
