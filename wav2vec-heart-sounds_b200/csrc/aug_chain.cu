@@ -75,6 +75,8 @@ struct AcShared {
   AcTables f;
   AcStat xstat[3][kAcMaxCluster][kAcWarps];      // [exchange parity (set 0) | 2 (set 1)][rank][warp]
   double xE[2][kAcMaxCluster][4];               // [group parity][rank]: end states exported by each rank
+  unsigned long long load_bar;                  // mbarrier of the bulk load
+  unsigned long long pad_;
 };
 
 __device__ __forceinline__ void ac_cluster_sync(int ncl) {
@@ -286,27 +288,62 @@ aug_chain_kernel(const __grid_constant__ AcParams P) {
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(yr)) & 15u) == 0;
   int parity = 0;
 
-  // ---- load + statistics of the raw row
+  // ---- load + statistics of the raw row.  A 16-byte aligned slice arrives as ONE bulk asynchronous copy (TMA,
+  //      cp.async.bulk global -> shared, completion counted on an mbarrier): no load instructions in the sweep and the
+  //      whole HBM latency paid once; otherwise plain loads.
   AcAcc st[1];
   AcMap map[1];
   st[0].init();
-  for (int q = tid; q < (P.S >> 2); q += kAcThreads) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    const int i = 4 * q;
-    if (i + 3 < n && vec_ok) {
-      const float4 w = ld_stream4(reinterpret_cast<const float4*>(xr + i));
-      v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (i + k < n) v[k] = ld_stream(xr + i + k);
+  const bool bulk = vec_ok && n > 0 && (n & 3) == 0;
+  if (bulk) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.load_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes = (uint32_t)n * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(buf)),
+                   "l"(xr), "r"(bytes), "r"(bar)
+                   : "memory");
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      buf[i + k] = v[k];
-      if (i + k < n) st[0].add(v[k]);
+    for (int i = n + tid; i < P.S; i += kAcThreads) buf[i] = 0.f;       // the slice's tail while the copy flies
+    __syncthreads();                                                     // the barrier is initialised for everybody
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "AC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra AC_DONE;\n\t"
+        "bra AC_WAIT;\n\t"
+        "AC_DONE:\n\t"
+        "}\n" ::"r"(bar)
+        : "memory");
+    const float4* buf4 = reinterpret_cast<const float4*>(buf);
+    for (int q = tid; q < nq; q += kAcThreads) {
+      const float4 w = buf4[q];
+      st[0].add(w.x); st[0].add(w.y); st[0].add(w.z); st[0].add(w.w);
+      st[0].flush();
     }
-    st[0].flush();
+  } else {
+    for (int q = tid; q < (P.S >> 2); q += kAcThreads) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int i = 4 * q;
+      if (i + 3 < n && vec_ok) {
+        const float4 w = ld_stream4(reinterpret_cast<const float4*>(xr + i));
+        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i + k < n) v[k] = ld_stream(xr + i + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        buf[i + k] = v[k];
+        if (i + k < n) st[0].add(v[k]);
+      }
+      st[0].flush();
+    }
   }
   ac_exchange<1>(sm, cluster, ncl, rank, P.t, parity, st, map);
 
