@@ -77,6 +77,7 @@ struct AcShared {
   double xE[2][kAcMaxCluster][4];               // [group parity][rank]: end states exported by each rank
   unsigned long long load_bar;                  // mbarrier of the bulk load
   unsigned long long pad_;
+  float mapv[2][4];                             // (mean hi, mean lo, 1 / peak) of the exchange in flight
 };
 
 __device__ __forceinline__ void ac_cluster_sync(int ncl) {
@@ -119,24 +120,36 @@ __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& clu
     }
   }
   ac_cluster_sync(ncl);
+  if (warp == 0) {                                          // one warp folds the partials and forms the maps
+#pragma unroll
+    for (int s = 0; s < NSETS; ++s) {
+      const AcStat* all = &sm.xstat[s == 0 ? parity : 2][0][0];
+      double tot = 0.0;
+      float lo = INFINITY, hi = -INFINITY;
+      for (int e = lane; e < ncl * kAcWarps; e += 32) {
+        tot += all[e].sum;
+        lo = fminf(lo, all[e].lo);
+        hi = fmaxf(hi, all[e].hi);
+      }
+      tot = warp_sum(tot);
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      const double mean = tot / (double)t;
+      const double peak = fmax((double)hi - mean, mean - (double)lo);
+      if (lane == 0) {
+        const float mh = (float)mean;
+        sm.mapv[s][0] = mh;
+        sm.mapv[s][1] = (float)(mean - (double)mh);
+        sm.mapv[s][2] = (float)(1.0 / fmax(peak, 1e-12));
+      }
+    }
+  }
+  __syncthreads();
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) {
-    const AcStat* all = &sm.xstat[s == 0 ? parity : 2][0][0];
-    double tot = 0.0;
-    float lo = INFINITY, hi = -INFINITY;
-    for (int e = lane; e < ncl * kAcWarps; e += 32) {
-      tot += all[e].sum;
-      lo = fminf(lo, all[e].lo);
-      hi = fmaxf(hi, all[e].hi);
-    }
-    tot = warp_sum(tot);
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    const double mean = tot / (double)t;
-    const double peak = fmax((double)hi - mean, mean - (double)lo);
-    out[s].mh = (float)mean;
-    out[s].ml = (float)(mean - (double)out[s].mh);
-    out[s].inv = (float)(1.0 / fmax(peak, 1e-12));
+    out[s].mh = sm.mapv[s][0];
+    out[s].ml = sm.mapv[s][1];
+    out[s].inv = sm.mapv[s][2];
   }
   parity ^= 1;
 }
