@@ -133,7 +133,7 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
                     col = torchproc.remove_spikes(col, fs_out, mode=mode)
             col = torchproc.abs_max_normalise(torchproc.bandpass_cascade(col, fs_out, *torchproc.PCG_BAND), mode=mode)
         else:
-            col = torchproc.preprocess_ecg(col, fs_in, fs_out, mode=mode)
+            col = torchproc.preprocess_ecg(col, fs_in, fs_out, mode=mode, fused=False)
         chans.append(col)
     stacked = chans[0] if planar_in else torch.stack(chans, dim=1)
     res = torchproc.segment(stacked, fs_out, spec, channels_last=channels_last)

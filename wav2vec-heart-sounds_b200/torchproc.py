@@ -134,11 +134,55 @@ def remove_spikes(x: torch.Tensor, fs: float, threshold: float = 3.0, max_iterat
     return (out, edits, trace) if return_trace else out
 
 
+class _WholeRow:
+    """A 'window' that is the whole conditioned row: lets the fused preprocess+segment kernel serve preprocess_pcg/ecg."""
+    start_pad_s = 0.0
+
+    def __init__(self, t_out: int):
+        self.t_out = int(t_out)
+
+    def window_len(self, fs) -> int:
+        return self.t_out
+
+    def hop_len(self, fs) -> int:
+        return self.t_out
+
+
+def _fused_rows(x: torch.Tensor, fs_in: float, fs_out: float, kind: str, despike: bool, mode: str):
+    """One fused launch (resample -> [despike] -> band -> normalise, the row written once) or None when the row does
+    not fit the cluster kernel (the caller then chains the stand-alone kernels: same arithmetic, more HBM traffic)."""
+    from .pipeline import preprocess_segment           # late: pipeline imports this module
+    lead, t_in = x.shape[:-1], x.shape[-1]
+    if t_in == 0 or x.numel() == 0:
+        return None
+    if fs_in == fs_out:
+        t_out = t_in
+    else:
+        up, down, _, _, _, t_out = _resample_plan(fs_in, fs_out, t_in, mode)
+        if up == down:
+            t_out = t_in
+    rows = x.reshape(-1, t_in).contiguous()
+    try:
+        out = preprocess_segment(rows, fs_in, fs_out, _WholeRow(t_out), kinds=(kind,), despike=despike, mode=mode, fused=True)
+    except ValueError as exc:
+        if "does not fit the fused kernel" in str(exc):
+            return None
+        raise
+    return out.reshape(*lead, t_out)
+
+
 def preprocess_pcg(x: torch.Tensor, fs_in: float, fs_out: float, *, despike: bool = True,
-                   mode: str = "torch") -> torch.Tensor:
+                   mode: str = "torch", fused: bool | None = None) -> torch.Tensor:
     """resample -> Schmidt despike -> 25-450 Hz band (fs-normalised) -> abs-max normalise
-    (reference torchproc.py:101-108)."""
+    (reference torchproc.py:101-108).  ``fused``: ``None`` = one fused cluster-kernel launch when the row fits it,
+    ``False`` = always the four stand-alone kernels, ``True`` = require the fused launch."""
     x = _lib.require_cuda_f32(x)
+    if fused is not False:
+        out = _fused_rows(x, fs_in, fs_out, "pcg", despike, mode)
+        if out is not None:
+            return out
+        if fused is True:
+            raise ValueError("this geometry does not fit the fused kernel")
     squeeze = x.dim() == 1
     v = resample(x[None] if squeeze else x, fs_in, fs_out, mode=mode)
     if despike:
@@ -147,9 +191,17 @@ def preprocess_pcg(x: torch.Tensor, fs_in: float, fs_out: float, *, despike: boo
     return v[0] if squeeze else v
 
 
-def preprocess_ecg(x: torch.Tensor, fs_in: float, fs_out: float, *, mode: str = "torch") -> torch.Tensor:
-    """resample -> 2-40 Hz band (fs-normalised) -> abs-max normalise (reference torchproc.py:111-116)."""
+def preprocess_ecg(x: torch.Tensor, fs_in: float, fs_out: float, *, mode: str = "torch",
+                   fused: bool | None = None) -> torch.Tensor:
+    """resample -> 2-40 Hz band (fs-normalised) -> abs-max normalise (reference torchproc.py:111-116).
+    ``fused`` as in :func:`preprocess_pcg`."""
     x = _lib.require_cuda_f32(x)
+    if fused is not False:
+        out = _fused_rows(x, fs_in, fs_out, "ecg", False, mode)
+        if out is not None:
+            return out
+        if fused is True:
+            raise ValueError("this geometry does not fit the fused kernel")
     squeeze = x.dim() == 1
     v = resample(x[None] if squeeze else x, fs_in, fs_out, mode=mode)
     v = abs_max_normalise(bandpass_cascade(v, fs_out, *ECG_BAND, order=2), mode=mode)
