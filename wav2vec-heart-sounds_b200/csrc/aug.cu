@@ -45,10 +45,23 @@ aug_stage_kernel(const float* __restrict__ x, float* __restrict__ y, long long t
     }
     stats_finish(st, t, mean, inv_peak, dscr, fscr);
   }
+  const bool vec = ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(yr)) & 15u) == 0;
   for (long long q = tid; q < nq; q += kAgThreads) {
     float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (philox) z4 = philox_normal4(a.seed, a.stream, row, q);
     const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    if (vec && 4 * q + 3 < t) {                                      // whole group: 128-bit load and store
+      const float4 v4 = *reinterpret_cast<const float4*>(xr + 4 * q);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      float ww[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = on ? stage_value(a, p, nz, row, 4 * q + k, vv[k], zz[k]) : vv[k];
+        ww[k] = NORMALISE ? norm_apply(w, mean, inv_peak) : w;
+      }
+      *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long i = 4 * q + k;
