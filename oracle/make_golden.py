@@ -284,6 +284,7 @@ def zerophase_fixture(versions):
     g["band_stop"] = np.stack([F.band_stop(r, fs, 45.0, 55.0) for r in x])
     g["notch"] = np.stack([F.notch(r, fs, 50.0) for r in x])
     g["notch_chain"] = np.stack([F.notch_chain(r, fs, (50.0, 100.0, 150.0, 3000.0)) for r in x])
+    g["bands"] = np.stack([F.decompose_bands(r, fs) for r in x[:1]])
     np.savez_compressed(OUT / "zerophase.npz", versions=str(versions), **g)
 
 

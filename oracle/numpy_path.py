@@ -262,3 +262,18 @@ def notch_chain_zp(x, fs: float, freqs, q: float = 55.0) -> np.ndarray:
         if f < 0.5 * fs:
             y = notch_zp(y, fs, f, q)
     return y
+
+
+def fir_subbands(fs: float, taps: int = 61, edges=(45.0, 80.0, 200.0)):
+    """``signalproc/filters.py:85-95``."""
+    nyq = 0.5 * fs
+    e0, e1, e2 = edges
+    return [_sig.firwin(taps, e0 / nyq, window="hamming", pass_zero="lowpass"),
+            _sig.firwin(taps, [e0 / nyq, e1 / nyq], window="hamming", pass_zero="bandpass"),
+            _sig.firwin(taps, [e1 / nyq, e2 / nyq], window="hamming", pass_zero="bandpass"),
+            _sig.firwin(taps, e2 / nyq, window="hamming", pass_zero="highpass")]
+
+
+def decompose_bands(x, fs: float, **kwargs) -> np.ndarray:
+    """``signalproc/filters.py:98-101``: ``[4, T]`` zero-phase FIR sub-bands."""
+    return np.stack([_sig.filtfilt(b, [1.0], np.asarray(x, dtype=np.float64)) for b in fir_subbands(fs, **kwargs)], axis=0)

@@ -47,3 +47,21 @@ def test_zero_phase_too_short_raises(fl):
         fl.butter_bandpass(torch.zeros(2, 20, device="cuda"), 4125.0, 25.0, 400.0)           # padlen 27 for 4 sections
     with pytest.raises(ValueError):
         fl.notch(torch.zeros(9, device="cuda"), 4125.0, 50.0)
+
+
+def test_fir_band_split(fl, golden):
+    """decompose_bands / preprocess_four_bands (reference filters.py:85-101, preprocess.py:40-42): the golden vectors
+    of the reference and the SciPy oracle on a fresh multi-row input."""
+    g = golden("zerophase.npz")
+    fs, x = float(g["fs"]), torch.from_numpy(g["x"]).cuda()
+    got = fl.decompose_bands(x[0], fs).cpu().numpy()
+    assert got.shape == g["bands"][0].shape and rel_err(got, g["bands"][0]) < TOL
+    four = fl.preprocess_four_bands(x[0], fs)
+    assert four.shape == (x.shape[1], 4) and torch.equal(four.t().cpu(), torch.from_numpy(got))
+    rng = np.random.default_rng(5)
+    y = (rng.standard_normal((3, 20011)) + 0.3).astype(np.float32)
+    got = fl.decompose_bands(torch.from_numpy(y).cuda(), 2000.0).cpu().numpy()
+    want = np.stack([onp.decompose_bands(r, 2000.0) for r in y])
+    assert got.shape == (3, 4, 20011) and rel_err(got, want) < TOL
+    with pytest.raises(ValueError):
+        fl.decompose_bands(torch.zeros(183, device="cuda"), 2000.0)

@@ -166,3 +166,4 @@ def test_zero_phase_filters_match_golden(golden):
         np.testing.assert_array_equal(onp.band_stop_zp(x[r], fs, 45.0, 55.0), g["band_stop"][r])
         np.testing.assert_array_equal(onp.notch_zp(x[r], fs, 50.0), g["notch"][r])
         np.testing.assert_array_equal(onp.notch_chain_zp(x[r], fs, (50.0, 100.0, 150.0, 3000.0)), g["notch_chain"][r])
+    np.testing.assert_array_equal(onp.decompose_bands(x[0], fs), g["bands"][0])
