@@ -218,8 +218,9 @@ int mpcg_hpss_stft_f32(const float* x, float* spec, int64_t rows, int64_t t, int
  * filter, size (1, k)) or along frequency (percussive, size (k, 1)); scipy.ndimage 'reflect' boundary, rank k/2. */
 int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows, int64_t frames, int bins, int k, int along_time,
                          void* stream);
-/* Soft masks (power 2, margins as in decompose.hpss) -> harmonic / percussive / residual spectra -> inverse FFT ->
- * windowed overlap-add into acc[row][3][n_fft + hop*(frames-1)] (zeroed here). */
+/* Soft masks (power 2, margins as in decompose.hpss) -> harmonic and percussive spectra -> ONE packed inverse FFT per frame
+ * (ifft(H + iP) = h + ip) -> windowed overlap-add into acc[row][0..1][n_fft + hop*(frames-1)] (acc[row][3][..] zeroed here;
+ * the residual plane stays zero: mpcg_hpss_finish3_f32 forms the residual as x - harmonic - percussive). */
 int mpcg_hpss_istft_f32(const float* spec, const float* harm, const float* perc, float* acc, int64_t rows, int n_fft,
                         int hop, int64_t frames, float margin_h, float margin_p, const float* window,
                         const float* twiddle, void* stream);
@@ -227,6 +228,10 @@ int mpcg_hpss_istft_f32(const float* spec, const float* harm, const float* perc,
  * normalisation and centre trim.  wsum: device [n_fft + hop*(frames-1)] window sum-of-squares. */
 int mpcg_hpss_finish_f32(const float* acc, const float* wsum, float* y, int64_t lines, int n_fft, int hop,
                          int64_t frames, void* stream);
+/* y[row][c][i], c = 0 harmonic, 1 percussive: acc / wsum as above; c = 2 residual: x[row][i] - (harmonic + percussive)
+ * (istft is linear and istft(stft(x)) = x, so this equals istft(S - (H + P)), primitives.py:92).  x: device [rows, t]. */
+int mpcg_hpss_finish3_f32(const float* acc, const float* wsum, const float* x, float* y, int64_t rows, int64_t t, int n_fft,
+                          int hop, int64_t frames, void* stream);
 /* hpss_recombine's tail (primitives.py:117-123): out = N(N(sum w1_p part_p) + wmix * N(sum w2_p N(part_p))), N =
  * NumPy abs_max_normalise.  parts: device [nparts][rows][n]; w1, w2: HOST [nparts]. */
 int mpcg_hpss_mix_f32(const float* parts, float* out, int64_t rows, int64_t n, int nparts, const float* w1,

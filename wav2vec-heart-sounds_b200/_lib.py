@@ -55,6 +55,7 @@ _SIGNATURES = {
     "mpcg_hpss_istft_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, c_i64, ctypes.c_float,
                                     ctypes.c_float, c_f32p, c_f32p, ctypes.c_void_p]),
     "mpcg_hpss_finish_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_int, c_i64, ctypes.c_void_p]),
+    "mpcg_hpss_finish3_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_i64, ctypes.c_void_p]),
     "mpcg_hpss_mix_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
                                   ctypes.c_void_p]),
     "mpcg_time_warp_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, ctypes.c_double, ctypes.c_void_p]),

@@ -146,21 +146,39 @@ hpss_istft_kernel(const float2* __restrict__ spec, const float* __restrict__ har
     mp[k] = softmask2(p, h * margin_p, split);
   }
   __syncthreads();
+  // ONE inverse FFT per frame: H and P are spectra of real signals, so ifft(H + i P) = h + i p (h, p real).  The
+  // residual needs no transform at all: istft is linear and istft(stft(x)) = x, hence r = x - h - p (finish kernel).
   const float scale = 1.f / (float)n_fft;
-  for (int comp = 0; comp < 3; ++comp) {
-    for (int k = threadIdx.x; k < bins; k += kFftThreads) {
-      const float g = comp == 0 ? mh[k] : (comp == 1 ? mp[k] : 1.f - (mh[k] + mp[k]));
-      const float2 v = make_float2(sp[k].x * g, sp[k].y * g);
-      fft_buf[bitrev((unsigned)k, log2n)] = v;
-      if (k > 0 && k < n_fft / 2) fft_buf[bitrev((unsigned)(n_fft - k), log2n)] = make_float2(v.x, -v.y);
-    }
-    __syncthreads();
-    fft_shared(fft_buf, n_fft, log2n, true, tw);
-    float* dst = acc + ((long long)row * 3 + comp) * acc_len + (long long)frame * hop;
-    for (int i = threadIdx.x; i < n_fft; i += kFftThreads)
-      atomicAdd(dst + i, fft_buf[i].x * scale * __ldg(window + i));
-    __syncthreads();
+  for (int k = threadIdx.x; k < bins; k += kFftThreads) {
+    const float2 sv = sp[k];
+    float2 hv = make_float2(sv.x * mh[k], sv.y * mh[k]), pv = make_float2(sv.x * mp[k], sv.y * mp[k]);
+    if (k == 0 || k == n_fft / 2) { hv.y = 0.f; pv.y = 0.f; }       // irfft ignores the imaginary part of DC / Nyquist
+    fft_buf[bitrev((unsigned)k, log2n)] = make_float2(hv.x - pv.y, hv.y + pv.x);
+    if (k > 0 && k < n_fft / 2) fft_buf[bitrev((unsigned)(n_fft - k), log2n)] = make_float2(hv.x + pv.y, pv.x - hv.y);
   }
+  __syncthreads();
+  fft_shared(fft_buf, n_fft, log2n, true, tw);
+  float* dst_h = acc + ((long long)row * 3 + 0) * acc_len + (long long)frame * hop;
+  float* dst_p = acc + ((long long)row * 3 + 1) * acc_len + (long long)frame * hop;
+  for (int i = threadIdx.x; i < n_fft; i += kFftThreads) {
+    const float w = scale * __ldg(window + i);
+    atomicAdd(dst_h + i, fft_buf[i].x * w);
+    atomicAdd(dst_p + i, fft_buf[i].y * w);
+  }
+}
+
+// y[row][0..1][i] = acc / wsum (istft's normalisation and centre trim); y[row][2][i] = x[row][i] - harmonic - percussive
+__global__ void hpss_finish3_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, const float* __restrict__ x,
+                                    float* __restrict__ y, long long acc_len, long long n_out, long long t, int pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = blockIdx.y;
+  if (i >= n_out) return;
+  const float w = __ldg(wsum + i + pad);
+  float h = acc[(row * 3 + 0) * acc_len + i + pad], p = acc[(row * 3 + 1) * acc_len + i + pad];
+  if (w > FLT_MIN) { h /= w; p /= w; }
+  y[(row * 3 + 0) * n_out + i] = h;
+  y[(row * 3 + 1) * n_out + i] = p;
+  y[(row * 3 + 2) * n_out + i] = x[row * t + i] - (h + p);
 }
 
 __global__ void hpss_finish_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, float* __restrict__ y,
@@ -328,6 +346,21 @@ extern "C" int mpcg_hpss_finish_f32(const float* acc, const float* wsum, float* 
   if (lines > 65535) return MPCG_ERANGE;
   dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)lines);
   hpss_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, wsum, y, acc_len, n_out, n_fft / 2, (long long)lines);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
+
+extern "C" int mpcg_hpss_finish3_f32(const float* acc, const float* wsum, const float* x, float* y, int64_t rows, int64_t t,
+                                     int n_fft, int hop, int64_t frames, void* stream) {
+  using namespace mpcg;
+  if (rows < 0 || n_fft < 2 || hop < 1 || frames < 1 || t < 0) return MPCG_EINVAL;
+  const long long acc_len = (long long)n_fft + (long long)hop * (frames - 1);
+  const long long n_out = (long long)hop * (frames - 1);
+  if (rows == 0 || n_out == 0) return MPCG_OK;
+  if (!acc || !wsum || !x || !y || n_out > t) return MPCG_EINVAL;
+  if (rows > 65535) return MPCG_ERANGE;
+  dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)rows);
+  hpss_finish3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(acc, wsum, x, y, acc_len, n_out, (long long)t, n_fft / 2);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }

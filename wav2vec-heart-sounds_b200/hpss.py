@@ -94,8 +94,9 @@ def hpss_split(y: torch.Tensor, n_fft: int, hop: int, margin, kernel):
         _lib.check(_lib.lib().mpcg_hpss_istft_f32(spec.data_ptr(), harm.data_ptr(), perc.data_ptr(), acc.data_ptr(), nb,
                                                   n_fft, hop, frames, float(margin[0]), float(margin[1]), win.data_ptr(),
                                                   tw.data_ptr(), _lib.stream_ptr(y)), "hpss istft")
-        _lib.check(_lib.lib().mpcg_hpss_finish_f32(acc.data_ptr(), wsum.data_ptr(), out[lo:lo + nb].data_ptr(), nb * 3,
-                                                   n_fft, hop, frames, _lib.stream_ptr(y)), "hpss finish")
+        _lib.check(_lib.lib().mpcg_hpss_finish3_f32(acc.data_ptr(), wsum.data_ptr(), rows.contiguous().data_ptr(),
+                                                    out[lo:lo + nb].data_ptr(), nb, t, n_fft, hop, frames,
+                                                    _lib.stream_ptr(y)), "hpss finish")
     return out[:, 0], out[:, 1], out[:, 2]
 
 
