@@ -40,24 +40,33 @@ __device__ __forceinline__ void fft_shared(float2* a, int n, int log2n, bool inv
 }
 
 // ---------------------------------------------------------------------------------------------- STFT
+// Two real frames per complex FFT: z = a + i b  ->  A[k] = (Z[k] + conj(Z[N-k])) / 2,  B[k] = (Z[k] - conj(Z[N-k])) / (2i).
 __global__ void __launch_bounds__(kFftThreads)
 hpss_stft_kernel(const float* __restrict__ x, float2* __restrict__ spec, long long t, int n_fft, int log2n, int hop,
                  int frames, const float* __restrict__ window, const float2* __restrict__ tw) {
   extern __shared__ float2 fft_buf[];
-  const int frame = blockIdx.x;
+  const int frame = 2 * blockIdx.x;                               // this CTA: frames `frame` and `frame + 1`
+  const bool two = frame + 1 < frames;
   const long long row = blockIdx.y;
   const float* xr = x + row * t;
   const long long base = (long long)frame * hop - n_fft / 2;
   for (int i = threadIdx.x; i < n_fft; i += kFftThreads) {
-    const long long j = base + i;
-    const float v = (j >= 0 && j < t) ? xr[j] * __ldg(window + i) : 0.f;
-    fft_buf[bitrev((unsigned)i, log2n)] = make_float2(v, 0.f);
+    const long long j = base + i, j2 = j + hop;
+    const float w = __ldg(window + i);
+    const float va = (j >= 0 && j < t) ? xr[j] * w : 0.f;
+    const float vb = (two && j2 >= 0 && j2 < t) ? xr[j2] * w : 0.f;
+    fft_buf[bitrev((unsigned)i, log2n)] = make_float2(va, vb);
   }
   __syncthreads();
   fft_shared(fft_buf, n_fft, log2n, false, tw);
   const int bins = n_fft / 2 + 1;
-  float2* out = spec + ((long long)row * frames + frame) * bins;
-  for (int k = threadIdx.x; k < bins; k += kFftThreads) out[k] = fft_buf[k];
+  float2* out_a = spec + ((long long)row * frames + frame) * bins;
+  float2* out_b = out_a + bins;
+  for (int k = threadIdx.x; k < bins; k += kFftThreads) {
+    const float2 z = fft_buf[k], zc = fft_buf[(n_fft - k) & (n_fft - 1)];     // Z[k], Z[N-k] (N-0 -> 0)
+    out_a[k] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+    if (two) out_b[k] = make_float2(0.5f * (z.y + zc.y), 0.5f * (zc.x - z.x));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- medians
@@ -287,7 +296,7 @@ extern "C" int mpcg_hpss_stft_f32(const float* x, float* spec, int64_t rows, int
   const size_t smem = (size_t)n_fft * sizeof(float2);
   cudaError_t e = cudaFuncSetAttribute(hpss_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((unsigned)frames, (unsigned)rows);
+  dim3 grid((unsigned)((frames + 1) / 2), (unsigned)rows);       // two frames per CTA (one packed complex FFT)
   hpss_stft_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream>>>(x, (float2*)spec, (long long)t, n_fft, l2, hop,
                                                                     (int)frames, window, (const float2*)twiddle);
   MPCG_LAUNCH_CHECK();
