@@ -77,31 +77,53 @@ aug_stage_kernel(const float* __restrict__ x, float* __restrict__ y, long long t
 // ---------------------------------------------------------------------------------------------- amplitude warp
 constexpr int kWpTile = 4096;
 constexpr int kWpMaxTaps = 257;
+constexpr int kWpOut = 8;                            // consecutive outputs per thread (register tile)
+__host__ __device__ constexpr int wp_skew(int m) { return m + (m >> 5); }   // lanes step 8 samples: one pad word per 32
+
+// Each thread computes kWpOut consecutive outputs from a sliding register window: per tap one new sample and one tap
+// are read from shared memory for kWpOut FFMAs (the first version read two words per FFMA and was LDS bound).
 __global__ void __launch_bounds__(256)
 aug_warp_kernel(const float* __restrict__ x, float* __restrict__ y, long long t, const float* __restrict__ curves,
                 int ntaps) {
-  extern __shared__ float wp_smem[];                // [kWpTile + ntaps - 1] samples, then [ntaps] taps
+  extern __shared__ float wp_smem[];                // skewed [kWpTile + ntaps - 1 + kWpOut] samples, then [ntaps] taps
   float* xs = wp_smem;
-  float* taps = wp_smem + kWpTile + ntaps - 1;
+  const int span = kWpTile + ntaps - 1;
+  float* taps = wp_smem + wp_skew(span + kWpOut) + 1;
   const long long row = blockIdx.y;
   const long long i0 = (long long)blockIdx.x * kWpTile;
   const float* xr = x + row * t;
   const int half = ntaps / 2;
-  const int span = kWpTile + ntaps - 1;
   for (int k = threadIdx.x; k < ntaps; k += 256) taps[k] = curves[row * ntaps + k];
-  for (int m = threadIdx.x; m < span; m += 256) {
+  for (int m = threadIdx.x; m < span + kWpOut; m += 256) {
     long long j = i0 + m - half;                    // index into the un-padded row, reflect (no edge repeat)
     if (j < 0) j = -j;
     if (j >= t) j = 2 * (t - 1) - j;
-    xs[m] = (j >= 0 && j < t) ? xr[j] : 0.f;
+    xs[wp_skew(m)] = (m < span && j >= 0 && j < t) ? xr[j] : 0.f;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < kWpTile; o += 256) {
-    const long long i = i0 + o;
-    if (i >= t) break;
-    float acc = 0.f;
-    for (int k = 0; k < ntaps; ++k) acc = fmaf(taps[k], xs[o + k], acc);
-    y[row * t + i] = acc;
+  for (int o0 = threadIdx.x * kWpOut; o0 < kWpTile; o0 += 256 * kWpOut) {
+    if (i0 + o0 >= t) break;
+    float acc[kWpOut], win[kWpOut];
+#pragma unroll
+    for (int u = 0; u < kWpOut; ++u) { acc[u] = 0.f; win[u] = xs[wp_skew(o0 + u)]; }
+    int k = 0;
+    for (; k + kWpOut <= ntaps; k += kWpOut) {       // kWpOut taps per trip: the window rotates through its registers
+#pragma unroll
+      for (int s = 0; s < kWpOut; ++s) {
+        const float tp = taps[k + s];
+#pragma unroll
+        for (int u = 0; u < kWpOut; ++u) acc[u] = fmaf(tp, win[(u + s) % kWpOut], acc[u]);
+        win[s] = xs[wp_skew(o0 + k + s + kWpOut)];
+      }
+    }
+    for (; k < ntaps; ++k) {                          // remaining taps
+      const float tp = taps[k];
+#pragma unroll
+      for (int u = 0; u < kWpOut; ++u) acc[u] = fmaf(tp, xs[wp_skew(o0 + k + u)], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kWpOut; ++u)
+      if (i0 + o0 + u < t) y[row * t + i0 + o0 + u] = acc[u];
   }
 }
 
@@ -185,7 +207,7 @@ extern "C" int mpcg_aug_warp_f32(const float* x, float* y, int64_t rows, int64_t
   if (!x || !y || !curves) return MPCG_EINVAL;
   if (t <= ntaps / 2) return MPCG_EINVAL;                           // reflect padding needs pad < length
   if (rows > 65535) return MPCG_ERANGE;
-  const size_t smem = (size_t)(kWpTile + 2 * ntaps) * sizeof(float);
+  const size_t smem = (size_t)(wp_skew(kWpTile + ntaps - 1 + kWpOut) + 1 + ntaps) * sizeof(float);
   dim3 grid((unsigned)((t + kWpTile - 1) / kWpTile), (unsigned)rows);
   aug_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, y, (long long)t, curves, ntaps);
   MPCG_LAUNCH_CHECK();
