@@ -251,3 +251,21 @@ def test_fast_draws_distributions(ta):
     base = ta._normalise(x)
     changed = ((outs[0] - base).abs().amax(dim=1) > 1e-4).float().mean()
     assert 0.6 < float(changed) < 0.95                         # P(at least one stage on) = 1 - .925 * .25 * .75 * .925 = 0.84
+
+
+def test_chain_degenerate_inputs(ta):
+    """Empty batches, five-sample rows, constant rows and a strided (transposed) input all go through."""
+    assert ta.augment_pcg_batch(torch.zeros(0, 100, device="cuda"), 4125).shape == (0, 100)
+    assert ta.augment_pcg_batch(torch.zeros(0, 100, device="cuda"), 4125, fused=False).shape == (0, 100)
+    tiny = ta.augment_pcg_batch(torch.randn(3, 5, device="cuda"), 4125, noise="philox")
+    assert tiny.shape == (3, 5) and torch.isfinite(tiny).all() and float(tiny.abs().max()) <= 1.0
+    const = ta.augment_pcg_batch(torch.ones(2, 64, device="cuda"), 4125, cfg=None, draws=None, noise="philox")
+    assert torch.isfinite(const).all()
+    xt = torch.randn(3001, 5, device="cuda").t()
+    torch.manual_seed(2); np.random.seed(2)
+    a = ta.augment_pcg_batch(xt, 4125, noise="philox")
+    torch.manual_seed(2); np.random.seed(2)
+    b = ta.augment_pcg_batch(xt.contiguous(), 4125, noise="philox")
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        ta.augment_pcg_batch(torch.randn(10, device="cuda"), 4125)

@@ -182,6 +182,7 @@ extern "C" int mpcg_aug_stage_f32(const float* x, float* y, int64_t rows, int64_
   using namespace mpcg;
   if (rows < 0 || t < 0) return MPCG_EINVAL;
   if (op < MPCG_AUG_IDENTITY || op > MPCG_AUG_SELECT) return MPCG_EINVAL;
+  if (rows == 0 || t == 0) return MPCG_OK;                    // nothing to do (empty tensors carry null pointers)
   if (op != MPCG_AUG_IDENTITY && op != MPCG_AUG_SELECT && !rowp) return MPCG_EINVAL;
   if (op == MPCG_AUG_SELECT && !noise) return MPCG_EINVAL;
   if ((op == MPCG_AUG_SINE_MUL || op == MPCG_AUG_SINE_ADD) && !(fs > 0.f)) return MPCG_EINVAL;

@@ -247,6 +247,8 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
     x = _rows2d(x)
     b, dev = x.shape[0], x.device
     d = draws or {}
+    if b == 0 or x.shape[1] == 0:                                # nothing to augment
+        return x.clone() if out is None else out
 
     def mask_of(key, prob):
         m = d.get(key)
