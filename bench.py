@@ -105,8 +105,9 @@ def _cpu_one(args):
     return w.shape[0] + int(aug.shape[0])
 
 
-def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234):
-    """audio-s/s of the oracle port over `n_recordings` synthetic recordings using `cores` worker processes."""
+def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234, steps: int = 1, warmup: int = 0):
+    """audio-s/s of the oracle port over `n_recordings` synthetic recordings per step using `cores` worker processes
+    (one pool for all steps).  Returns (audio-s/s over the timed steps, seconds of the timed steps)."""
     import multiprocessing as mp
     from wav2vec_heart_sounds_b200.synth import synth_pair
     os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -115,10 +116,13 @@ def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234):
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_one, work[:cores])                     # warm the workers (imports, FFT plans)
+        for _ in range(warmup):
+            pool.map(_cpu_one, work, chunksize=1)
         t0 = time.perf_counter()
-        pool.map(_cpu_one, work, chunksize=1)
+        for _ in range(steps):
+            pool.map(_cpu_one, work, chunksize=1)
         dt = time.perf_counter() - t0
-    return n_recordings * SECONDS / dt, dt
+    return n_recordings * SECONDS * steps / dt, dt
 
 
 def host_cores() -> int:
@@ -133,19 +137,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    # bounded sample: K + W steps must fit in ~90 s of wall clock at ~0.35 core-seconds per recording
+    # bounded sample: K + W steps must fit in ~90 s of wall clock at ~0.35 core-seconds per recording; whole rounds of
+    # the worker pool so that no core idles at the end of a step
     per_step = int(90.0 / (args.steps + args.warmup) * cores / 0.35)
     per_step = max(cores, min(per_step, RECORDINGS))
+    per_step = min(RECORDINGS, -(-per_step // cores) * cores)
     torch.set_num_threads(1)
-    vals = []
-    for _ in range(args.warmup):
-        cpu_throughput(min(per_step, cores), cores)
-    t_all = 0.0
-    for _ in range(args.steps):
-        v, dt = cpu_throughput(per_step, cores)
-        vals.append(v)
-        t_all += dt
-    value = per_step * SECONDS * args.steps / t_all
+    value, t_all = cpu_throughput(per_step, cores, steps=args.steps, warmup=args.warmup)
     sample = (f"{per_step} recordings per step (2 channels x 30 s; NumPy/SciPy float64 preprocessing + windows, then the "
               f"torchaug chain on the PCG windows in float64 on CPU), {cores} worker processes")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
