@@ -137,9 +137,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    # bounded sample: K + W steps must fit in ~90 s of wall clock at ~0.35 core-seconds per recording; whole rounds of
+    # bounded sample: K + W steps must fit in ~4 minutes of CPU wall clock at ~0.35 core-seconds per recording; whole rounds of
     # the worker pool so that no core idles at the end of a step
-    per_step = int(90.0 / (args.steps + args.warmup) * cores / 0.35)
+    per_step = int(240.0 / (args.steps + args.warmup) * cores / 0.35)
     per_step = max(cores, min(per_step, RECORDINGS))
     per_step = min(RECORDINGS, -(-per_step // cores) * cores)
     torch.set_num_threads(1)
