@@ -1,4 +1,7 @@
-"""Per-phase clock64 breakdown of the fused kernel (uses mpcg_debug_set_phase_clock_buffer)."""
+"""Per-phase clock64 breakdown of the fused kernel (uses mpcg_debug_set_phase_clock_buffer).
+
+The stamps are compiled in only with -DMPCG_FZ_PHASE_CLOCKS=1: build an instrumented library next to the product one
+(tools/build_clocks.sh writes tools/libmpcg_b200_clocks.so) and run this script with MPCG_B200_LIB pointing at it."""
 import sys, torch, numpy as np
 sys.path.insert(0, ".")
 import wav2vec_heart_sounds_b200 as pkg

@@ -275,11 +275,16 @@ fused_preprocess_kernel(const __grid_constant__ FzParams P) {
   int n = (rank == P.ncl - 1) ? (P.t - s0) : P.S;
   if (n < 0) n = 0;
   const int L = P.L;
+  // per-phase clock stamps: compiled in only for tools/phase_clocks.py (make FZFLAGS=-DMPCG_FZ_PHASE_CLOCKS=1)
+#if defined(MPCG_FZ_PHASE_CLOCKS) && MPCG_FZ_PHASE_CLOCKS
   int dbg_k = 0;
   auto stamp = [&]() {
     if (P.dbg && tid == 0) P.dbg[(long long)blockIdx.x * 16 + dbg_k] = clock64();
     ++dbg_k;
   };
+#else
+  auto stamp = [] {};
+#endif
   stamp();                                                // 0: start
 
   // ---------------------------------------------------------------- 1. resample my slice into shared memory
