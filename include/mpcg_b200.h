@@ -39,6 +39,13 @@ extern "C" {
 #define MPCG_NORM_NAN_TO_NUM 1 /* torch.nan_to_num first (torchproc.py:63); without it = torchaug._normalise */
 #define MPCG_NORM_PEAK_GT0 2   /* numpy rule: divide only if peak > 0 (normalize.py:28-29) instead of clamp_min(1e-12) */
 
+/* mpcg_row_normalise_f32 modes and flags */
+#define MPCG_RN_MINMAX 0 /* (x - min) / span * (hi - lo) + lo                          (normalize.py:33-44) */
+#define MPCG_RN_ZSCORE 1 /* (x - mean) / (population std + 1e-8)                       (normalize.py:47-56) */
+#define MPCG_RN_KPEAK 2  /* lo + (x - lo_ref) / span * (hi - lo), refs = mean of the k smallest / largest (normalize.py:59-78) */
+#define MPCG_RN_EPS 1    /* tensor rule: span + 1e-8 in the denominator; without it the NumPy rule: span <= 0 -> (lo + hi) / 2 */
+#define MPCG_RN_GLOBAL 2 /* one range for the whole [rows, t] tensor, as the reference's tensor functions compute it */
+
 int mpcg_abi_version(void);
 const char* mpcg_error_string(int code);
 
@@ -187,6 +194,22 @@ int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float 
  * t must exceed edge (SciPy raises ValueError otherwise -> MPCG_EINVAL). */
 int mpcg_sosfiltfilt_f32(const float* x, float* y, float* work, int64_t rows, int64_t t, const double* sos, int n_sections,
                          const double* zi, int64_t edge, void* stream);
+/* The same with an epilogue on the stored samples: MPCG_EPI_EXP writes exp(y) -- the last step of the homomorphic
+ * envelope (reference signalproc/envelopes.py:22-23: exp(butter_lowpass(log(envelope)))). */
+#define MPCG_EPI_NONE 0
+#define MPCG_EPI_EXP 1
+int mpcg_sosfiltfilt_epi_f32(const float* x, float* y, float* work, int64_t rows, int64_t t, const double* sos,
+                             int n_sections, const double* zi, int64_t edge, int epilogue, void* stream);
+
+/* Hilbert amplitude envelope of rows x [rows, t] (reference signalproc/envelopes.py:11-13: abs(scipy.signal.hilbert(x)),
+ * the analytic signal of the t-point DFT, any t <= 2^19): two fp64 Bluestein chirp convolutions of a power-of-two length
+ * M >= 2t - 1 through four-step shared-memory FFTs.  y [rows, t] = the envelope, or with MPCG_ENV_LOG
+ * log(max(envelope, DBL_EPSILON)) (the input of the homomorphic envelope's low-pass, envelopes.py:21-22).
+ * work: device scratch of mpcg_hilbert_work_bytes(rows, t) bytes (16-byte aligned; -1 = t out of range); rows <= 65535. */
+#define MPCG_ENV_LOG 1
+int64_t mpcg_hilbert_work_bytes(int64_t rows, int64_t t);
+int mpcg_hilbert_envelope_f32(const float* x, float* y, void* work, int64_t work_bytes, int64_t rows, int64_t t, int flags,
+                              void* stream);
 
 /* Generator-dataset conditioning of one batch (reference datasets/generative.py:77-115 with
  * signalproc/preprocess.py:45-64): y [rows, crop] = fit_length(fade(abs_max_normalise(x [rows, t])), crop) with 128-sample
@@ -194,6 +217,14 @@ int mpcg_sosfiltfilt_f32(const float* x, float* y, float* work, int64_t rows, in
  * add_chirp(y, fs): y plus a full-band linear chirp scaled to max(0.5, max|y|).  norm_flags as in mpcg_absmax_norm_f32. */
 int mpcg_gen_condition_f32(const float* x, float* y, float* chirp, int64_t rows, int64_t t, int64_t crop, int fade_n,
                            double fs, int norm_flags, void* stream);
+
+/* The amplitude normalisers other than abs-max (reference signalproc/normalize.py:33-78), per row of x [rows, t] or, with
+ * MPCG_RN_GLOBAL, with one range for the whole tensor (min / max over every element; k-peak: the mean over all rows' k
+ * largest / smallest values -- what minmax_normalise_torch / kpeak_normalise_torch return for a batched input).
+ * k (k-peak only) is clamped to t.  stats: optional device [rows, 8] doubles receiving (min, max, mean, std, hi_ref, lo_ref,
+ * 0, 0) per row; REQUIRED with MPCG_RN_GLOBAL and then [rows + 1, 8] (the last row holds the combined map). */
+int mpcg_row_normalise_f32(const float* x, float* y, double* stats, int64_t rows, int64_t t, int mode, int k, double lo,
+                           double hi, int flags, void* stream);
 
 /* Tensor-core tier of the same transform (tcgen05, split-fp16 operands, fp32 accumulation in TMEM) for configurations
  * with n_fft = Q * hop (Q <= 8), win_length == n_fft and at most 126 weighted bins.  The GEMM is the rectangular-window

@@ -268,6 +268,42 @@ def main():
 
     gen_condition_fixture(sp, versions)
     zerophase_fixture(versions)
+    normalisers_fixture(sp, versions)
+
+
+def normalisers_fixture(sp, versions):
+    """G8: min-max / z-score / k-peak normalisers and the envelopes through the reference's
+    signalproc/normalize.py:33-78 and signalproc/envelopes.py:11-23."""
+    rng = np.random.default_rng(81)
+    t = 3000
+    x = (np.sin(np.arange(t) / 7.0)[None] * rng.uniform(0.2, 3, (3, 1)) + 0.2 * rng.standard_normal((3, t)) - 0.4)
+    x = x.astype(np.float32)
+    x[1, 100:104] = x[1].max()                                  # ties at the top
+    x[2, 5] = 40.0                                              # an isolated spike
+    flat = np.full((1, 64), 0.25, dtype=np.float32)
+    xt = torch.from_numpy(x)
+    g = dict(x=x, flat=flat)
+    g["minmax"] = np.stack([sp.minmax_normalise(r) for r in x])
+    g["minmax_02"] = np.stack([sp.minmax_normalise(r, 0.0, 2.0) for r in x])
+    g["minmax_flat"] = sp.minmax_normalise(flat[0])[None]
+    g["z"] = np.stack([sp.z_normalise(r) for r in x])
+    g["kpeak3"] = np.stack([sp.kpeak_normalise(r) for r in x])
+    g["kpeak40"] = np.stack([sp.kpeak_normalise(r, k=40, lo=0.0, hi=1.0) for r in x])
+    g["kpeak_flat"] = sp.kpeak_normalise(flat[0])[None]
+    g["minmax_torch_rows"] = np.stack([sp.minmax_normalise_torch(r).numpy() for r in xt])
+    g["minmax_torch_all"] = sp.minmax_normalise_torch(xt).numpy()
+    g["z_torch"] = sp.z_normalise_torch(xt.double()[None]).numpy()[0]
+    g["kpeak_torch_rows"] = np.stack([sp.kpeak_normalise_torch(r.double()).numpy() for r in xt])
+    g["kpeak_torch_all"] = sp.kpeak_normalise_torch(xt.double()).numpy()
+    g["kpeak_torch_all_k5"] = sp.kpeak_normalise_torch(xt.double(), k=5, lo=0.0, hi=3.0).numpy()
+    fs = 1000.0
+    e = (np.sin(2 * np.pi * 40.0 * np.arange(2500) / fs) * (1 + 0.5 * np.sin(2 * np.pi * 1.5 * np.arange(2500) / fs)))[None]
+    e = (np.concatenate([e, e[:, ::-1] * 0.3]) + 0.05 * rng.standard_normal((2, 2500))).astype(np.float32)
+    g["env_x"], g["env_fs"] = e, fs
+    g["hilbert"] = np.stack([sp.hilbert_envelope(r) for r in e])
+    g["hilbert_odd"] = np.stack([sp.hilbert_envelope(r[:2499]) for r in e])
+    g["homomorphic"] = np.stack([sp.homomorphic_envelope(r, fs) for r in e])
+    np.savez_compressed(OUT / "normalisers.npz", versions=str(versions), **g)
 
 
 def zerophase_fixture(versions):

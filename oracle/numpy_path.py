@@ -15,6 +15,8 @@ What is restated (reference file:line -> function here):
 * ``signalproc/filters.py:25-39``     -> :func:`lowpass` / :func:`highpass` / :func:`bandpass_cascade`
 * ``signalproc/preprocess.py:24-37``  -> :func:`preprocess_pcg` / :func:`preprocess_ecg`
 * ``signalproc/segment.py:17-52``     -> :class:`WindowSpec`, :func:`window_starts`, :func:`segment`
+* ``signalproc/normalize.py:33-38,47-49,59-72`` -> :func:`minmax_normalise`, :func:`z_normalise`, :func:`kpeak_normalise`
+* ``signalproc/envelopes.py:11-23``   -> :func:`hilbert_envelope`, :func:`homomorphic_envelope`
 
 Third-party arithmetic (SciPy ``resample_poly``/``butter``/``sosfilt``) is called, not
 restated: SciPy is installed on the GPU box too, and it is the very code the reference runs.
@@ -277,3 +279,46 @@ def fir_subbands(fs: float, taps: int = 61, edges=(45.0, 80.0, 200.0)):
 def decompose_bands(x, fs: float, **kwargs) -> np.ndarray:
     """``signalproc/filters.py:98-101``: ``[4, T]`` zero-phase FIR sub-bands."""
     return np.stack([_sig.filtfilt(b, [1.0], np.asarray(x, dtype=np.float64)) for b in fir_subbands(fs, **kwargs)], axis=0)
+
+
+# --------------------------------------------------------------------------- other normalisers (SURVEY 8f rank 3)
+RANGE_EPS = 1e-8
+
+
+def minmax_normalise(x, lo: float = -1.0, hi: float = 1.0) -> np.ndarray:
+    """``signalproc/normalize.py:33-38``: whole-array range; a flat signal becomes the midpoint."""
+    v = np.asarray(x, dtype=np.float64)
+    bottom, top = v.min(), v.max()
+    if top - bottom <= 0:
+        return np.full_like(v, 0.5 * (lo + hi))
+    return (v - bottom) / (top - bottom) * (hi - lo) + lo
+
+
+def z_normalise(x, axis: int = 0) -> np.ndarray:
+    """``signalproc/normalize.py:47-49``: population standard deviation plus 1e-8."""
+    v = np.asarray(x, dtype=np.float64)
+    return (v - v.mean(axis=axis)) / (v.std(axis=axis) + RANGE_EPS)
+
+
+def kpeak_normalise(x, k: int = 3, lo: float = -1.0, hi: float = 1.0) -> np.ndarray:
+    """``signalproc/normalize.py:59-72``: range = mean of the k smallest .. mean of the k largest samples."""
+    v = np.asarray(x, dtype=np.float64)
+    ranked = np.sort(v)
+    bottom, top = ranked[:k].mean(), ranked[-k:].mean()
+    if top - bottom <= 0:
+        return np.full_like(v, 0.5 * (lo + hi))
+    return lo + (v - bottom) / (top - bottom) * (hi - lo)
+
+
+# --------------------------------------------------------------------------- envelopes (SURVEY 8f rank 3)
+def hilbert_envelope(x) -> np.ndarray:
+    """``signalproc/envelopes.py:11-13``: magnitude of the analytic signal (SciPy's N-point DFT construction)."""
+    return np.abs(_sig.hilbert(np.asarray(x, dtype=np.float64)))
+
+
+def homomorphic_envelope(x, fs: float, cutoff: float = 8.0, order: int = 6) -> np.ndarray:
+    """``signalproc/envelopes.py:16-23``: exp(zero-phase low-pass(log(max(envelope, eps))))."""
+    if cutoff >= 0.5 * fs:
+        raise ValueError(f"cutoff {cutoff} Hz is above Nyquist for fs={fs}")
+    floor = np.finfo(float).eps
+    return np.exp(butter_lowpass_zp(np.log(np.maximum(hilbert_envelope(x), floor)), fs, cutoff, order=order))

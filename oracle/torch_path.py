@@ -23,6 +23,8 @@ reference file:line -> function here
   :func:`baseline_wander`, :func:`amplitude_warp`, :func:`parametric_eq`
 * ``torchaug.py:30-36,103-111`` -> :func:`blend`, :func:`augment_pcg_batch`
 * ``spectrogram.py:13-45`` -> :func:`mel_transform`, :func:`log_mel`
+* ``signalproc/normalize.py:41-44,52-56,75-78`` -> :func:`minmax_normalise_torch`, :func:`z_normalise_torch`,
+  :func:`kpeak_normalise_torch`
 """
 from __future__ import annotations
 
@@ -239,3 +241,26 @@ def log_mel(x, transform):
     m = transform(x)
     m = 20.0 * torch.log10(torch.clamp(m, min=1e-5)) - 20.0
     return torch.clamp((m + 100.0) / 100.0, 0.0, 1.0)
+
+
+# --------------------------------------------------------------------------- other normalisers
+RANGE_EPS = 1e-8
+
+
+def minmax_normalise_torch(x, lo=-1.0, hi=1.0):
+    """``signalproc/normalize.py:41-44``: one range over the whole tensor, epsilon in the denominator."""
+    bottom = x.min()
+    return (x - bottom) / (x.max() - bottom + RANGE_EPS) * (hi - lo) + lo
+
+
+def z_normalise_torch(x):
+    """``signalproc/normalize.py:52-56``: last-dimension z-score, population standard deviation."""
+    centre = x.mean(dim=-1, keepdim=True)
+    return (x - centre) / (x.std(dim=-1, unbiased=False, keepdim=True) + RANGE_EPS)
+
+
+def kpeak_normalise_torch(x, k=26, lo=-1.0, hi=1.0, dim=-1):
+    """``signalproc/normalize.py:75-78``: top-k along ``dim``, then one mean over everything selected."""
+    top = torch.topk(x, k=k, dim=dim).values.mean()
+    bottom = -torch.topk(-x, k=k, dim=dim).values.mean()
+    return lo + (x - bottom) / (top - bottom + RANGE_EPS) * (hi - lo)

@@ -167,3 +167,28 @@ def test_zero_phase_filters_match_golden(golden):
         np.testing.assert_array_equal(onp.notch_zp(x[r], fs, 50.0), g["notch"][r])
         np.testing.assert_array_equal(onp.notch_chain_zp(x[r], fs, (50.0, 100.0, 150.0, 3000.0)), g["notch_chain"][r])
     np.testing.assert_array_equal(onp.decompose_bands(x[0], fs), g["bands"][0])
+
+
+def test_other_normalisers_and_envelopes_match_golden(golden):
+    """the oracle's min-max / z-score / k-peak normalisers and envelopes against the reference's
+    signalproc/normalize.py:33-78 and signalproc/envelopes.py:11-23, bit for bit."""
+    g = golden("normalisers.npz")
+    x = g["x"]
+    for r in range(x.shape[0]):
+        np.testing.assert_array_equal(onp.minmax_normalise(x[r]), g["minmax"][r])
+        np.testing.assert_array_equal(onp.minmax_normalise(x[r], 0.0, 2.0), g["minmax_02"][r])
+        np.testing.assert_array_equal(onp.z_normalise(x[r]), g["z"][r])
+        np.testing.assert_array_equal(onp.kpeak_normalise(x[r]), g["kpeak3"][r])
+        np.testing.assert_array_equal(onp.kpeak_normalise(x[r], k=40, lo=0.0, hi=1.0), g["kpeak40"][r])
+    np.testing.assert_array_equal(onp.minmax_normalise(g["flat"][0]), g["minmax_flat"][0])
+    np.testing.assert_array_equal(onp.kpeak_normalise(g["flat"][0]), g["kpeak_flat"][0])
+    xt = torch.from_numpy(x)
+    np.testing.assert_array_equal(otp.minmax_normalise_torch(xt).numpy(), g["minmax_torch_all"])
+    np.testing.assert_array_equal(otp.z_normalise_torch(xt.double()).numpy(), g["z_torch"])
+    np.testing.assert_array_equal(otp.kpeak_normalise_torch(xt.double()).numpy(), g["kpeak_torch_all"])
+    np.testing.assert_array_equal(otp.kpeak_normalise_torch(xt.double(), k=5, lo=0.0, hi=3.0).numpy(), g["kpeak_torch_all_k5"])
+    e, fs = g["env_x"], float(g["env_fs"])
+    for r in range(e.shape[0]):
+        np.testing.assert_array_equal(onp.hilbert_envelope(e[r]), g["hilbert"][r])
+        np.testing.assert_array_equal(onp.hilbert_envelope(e[r][:2499]), g["hilbert_odd"][r])
+        np.testing.assert_array_equal(onp.homomorphic_envelope(e[r], fs), g["homomorphic"][r])

@@ -32,7 +32,7 @@ __device__ __forceinline__ float ff_ext(const float* __restrict__ x, long long t
 
 __global__ void __launch_bounds__(kFfThreads)
 filtfilt_rows_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ work, long long t, long long edge,
-                     const __grid_constant__ BqPlan plan, const __grid_constant__ FfZi zi) {
+                     const __grid_constant__ BqPlan plan, const __grid_constant__ FfZi zi, int epilogue) {
   extern __shared__ __align__(16) unsigned char ff_raw[];
   FfSmem& sm = *reinterpret_cast<FfSmem*>(ff_raw);
   const long long row = blockIdx.x;
@@ -65,7 +65,7 @@ filtfilt_rows_kernel(const float* __restrict__ x, float* __restrict__ y, float* 
       } else {
         for (int i = tid; i < n; i += kFfThreads) {
           const long long e = te - 1 - (t0 + i);                                         // extended index of this output
-          if (e >= edge && e < edge + t) yr[e - edge] = sh[i];
+          if (e >= edge && e < edge + t) yr[e - edge] = epilogue == MPCG_EPI_EXP ? (float)exp((double)sh[i]) : sh[i];
         }
       }
       __syncthreads();
@@ -77,10 +77,11 @@ filtfilt_rows_kernel(const float* __restrict__ x, float* __restrict__ y, float* 
 
 }  // namespace mpcg
 
-extern "C" int mpcg_sosfiltfilt_f32(const float* x, float* y, float* work, int64_t rows, int64_t t, const double* sos,
-                                    int n_sections, const double* zi, int64_t edge, void* stream) {
+extern "C" int mpcg_sosfiltfilt_epi_f32(const float* x, float* y, float* work, int64_t rows, int64_t t, const double* sos,
+                                        int n_sections, const double* zi, int64_t edge, int epilogue, void* stream) {
   using namespace mpcg;
   if (rows < 0 || t < 0 || edge < 0) return MPCG_EINVAL;
+  if (epilogue != MPCG_EPI_NONE && epilogue != MPCG_EPI_EXP) return MPCG_EINVAL;
   BqPlan plan;
   const int rc = bq_make_plan(sos, n_sections, &plan);
   if (rc != MPCG_OK) return rc;
@@ -98,7 +99,12 @@ extern "C" int mpcg_sosfiltfilt_f32(const float* x, float* y, float* work, int64
   cudaError_t e = cudaFuncSetAttribute(filtfilt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FfSmem));
   if (e != cudaSuccess) return (int)e;
   filtfilt_rows_kernel<<<(unsigned)rows, kFfThreads, sizeof(FfSmem), (cudaStream_t)stream>>>(x, y, work, (long long)t,
-                                                                                            (long long)edge, plan, z);
+                                                                                            (long long)edge, plan, z, epilogue);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
+}
+
+extern "C" int mpcg_sosfiltfilt_f32(const float* x, float* y, float* work, int64_t rows, int64_t t, const double* sos,
+                                    int n_sections, const double* zi, int64_t edge, void* stream) {
+  return mpcg_sosfiltfilt_epi_f32(x, y, work, rows, t, sos, n_sections, zi, edge, MPCG_EPI_NONE, stream);
 }

@@ -29,7 +29,7 @@ def _design(kind: str, args: tuple):
     return np.ascontiguousarray(sos), zi, int(edge)
 
 
-def _filtfilt(x: torch.Tensor, sos: np.ndarray, zi: np.ndarray, edge: int) -> torch.Tensor:
+def _filtfilt(x: torch.Tensor, sos: np.ndarray, zi: np.ndarray, edge: int, epilogue: int = 0) -> torch.Tensor:
     x = _lib.require_cuda_f32(x)
     lead, t = x.shape[:-1], x.shape[-1]
     if t <= edge:
@@ -39,9 +39,9 @@ def _filtfilt(x: torch.Tensor, sos: np.ndarray, zi: np.ndarray, edge: int) -> to
         raise ValueError("at most 6 second-order sections per call")
     out = torch.empty_like(rows)
     work = torch.empty((rows.shape[0], t + 2 * edge), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().mpcg_sosfiltfilt_f32(rows.data_ptr(), out.data_ptr(), work.data_ptr(), rows.shape[0], t,
-                                               sos.ctypes.data, sos.shape[0], zi.ctypes.data, edge, _lib.stream_ptr(x)),
-               "zero-phase filter")
+    _lib.check(_lib.lib().mpcg_sosfiltfilt_epi_f32(rows.data_ptr(), out.data_ptr(), work.data_ptr(), rows.shape[0], t,
+                                                   sos.ctypes.data, sos.shape[0], zi.ctypes.data, edge, int(epilogue),
+                                                   _lib.stream_ptr(x)), "zero-phase filter")
     return out.reshape(*lead, t)
 
 
