@@ -217,6 +217,22 @@ int mpcg_hilbert_envelope_f32(const float* x, float* y, void* work, int64_t work
  * add_chirp(y, fs): y plus a full-band linear chirp scaled to max(0.5, max|y|).  norm_flags as in mpcg_absmax_norm_f32. */
 int mpcg_gen_condition_f32(const float* x, float* y, float* chirp, int64_t rows, int64_t t, int64_t crop, int fade_n,
                            double fs, int norm_flags, void* stream);
+/* The same for rows of different valid lengths: x [rows, t] with row r holding row_len[r] <= t samples (device int64, or
+ * NULL = all t).  MPCG_GEN_NO_NORM in norm_flags skips the normalisation: rows rebuilt from cycles of an already
+ * normalised signal are only faded and fitted (datasets/generative.py:80-91). */
+#define MPCG_GEN_NO_NORM 4
+int mpcg_gen_condition_rows_f32(const float* x, float* y, float* chirp, const int64_t* row_len, int64_t rows, int64_t t,
+                                int64_t crop, int fade_n, double fs, int norm_flags, void* stream);
+
+/* Rebuild a signal from rearranged cardiac cycles (reference datasets/heart_cycles.py:38-69, _crossfade + rebuild).
+ * x [rows, t]: source rows (already normalised); row r has counts[r] cycles, cycle c = x[r, starts[r, c] : starts[r, c] +
+ * lens[r, c]] in the order they are to be joined (device int32 [rows, kmax] / [rows]).  y [rows, cap], out_len [rows]
+ * (device int64): out = cycle 0, then crossfade-append cycle (i mod count) over fade_n samples until out_len >= target_len
+ * (at most 10 count + 5 joins, as the reference's guard allows); counts[r] == 0 copies the row unchanged.  cap must hold
+ * target_len + the longest cycle (and t for pass-through rows); writes never pass cap. */
+int mpcg_cycle_rebuild_f32(const float* x, float* y, int64_t* out_len, const int32_t* starts, const int32_t* lens,
+                           const int32_t* counts, int64_t rows, int64_t t, int64_t cap, int kmax, int64_t target_len,
+                           int fade_n, void* stream);
 
 /* The amplitude normalisers other than abs-max (reference signalproc/normalize.py:33-78), per row of x [rows, t] or, with
  * MPCG_RN_GLOBAL, with one range for the whole tensor (min / max over every element; k-peak: the mean over all rows' k

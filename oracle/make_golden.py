@@ -269,6 +269,7 @@ def main():
     gen_condition_fixture(sp, versions)
     zerophase_fixture(versions)
     normalisers_fixture(sp, versions)
+    heart_cycles_fixture(sp, versions)
 
 
 def normalisers_fixture(sp, versions):
@@ -304,6 +305,41 @@ def normalisers_fixture(sp, versions):
     g["hilbert_odd"] = np.stack([sp.hilbert_envelope(r[:2499]) for r in e])
     g["homomorphic"] = np.stack([sp.homomorphic_envelope(r, fs) for r in e])
     np.savez_compressed(OUT / "normalisers.npz", versions=str(versions), **g)
+
+
+def heart_cycles_fixture(sp, versions):
+    """G9: cardiac-cycle rearrangement through the reference's datasets/heart_cycles.py and the
+    rebuilt branch of GenerativeDataset.__getitem__ (datasets/generative.py:62-91)."""
+    import random
+    from mpcg_wav2vec.datasets import heart_cycles as hc
+    from mpcg_wav2vec.datasets.generative import _fade
+    from mpcg_wav2vec.signalproc.preprocess import fit_length
+    rng = np.random.default_rng(91)
+    fs, t, crop, fade_n = 4000, 16000, 24 * 256, 40
+    n = np.arange(t)
+    beat = np.exp(-(((n % 3100) - 400.0) / 90.0) ** 2) * np.sin(2 * np.pi * 55 * n / fs)
+    x = (beat[None] * rng.uniform(0.5, 2.0, (3, 1)) + 0.02 * rng.standard_normal((3, t)) + 0.1).astype(np.float32)
+    x[2, 6000:9400] = 0.1                                           # a flat stretch: the linear-ramp branch
+    joins = [0, 350, 3420, 6555, 9640, 9660, 12800, 15900, 16000, 17000]   # one 20-sample cycle (shorter than the fade)
+    g = dict(fs=fs, crop=crop, fade_n=fade_n, x=x, joins=np.array(joins))
+    orders = []
+    for seed in (0, 1, 2, 3):
+        for pc in (0.0, 1.0):
+            orders.append(hc.rearrange({"a": list(range(6))}, prob_contiguous=pc, rng=random.Random(seed))["a"])
+    g["orders6"] = np.array(orders)
+    g["orders_seed_pc"] = np.array([(s, pc) for s in (0, 1, 2, 3) for pc in (0.0, 1.0)])
+    for r in range(3):
+        sig = sp.abs_max_normalise(x[r])
+        cyc = hc.split_cycles(sig, joins)
+        arranged = hc.rearrange({"ref": cyc}, prob_contiguous=0.0, rng=random.Random(10 + r))["ref"]
+        order = hc.rearrange({"ref": list(range(len(cyc)))}, prob_contiguous=0.0, rng=random.Random(10 + r))["ref"]
+        out = hc.rebuild(arranged, crop, fade_n)
+        g[f"order_{r}"] = np.array(order)
+        g[f"rebuilt_{r}"] = out
+        g[f"item_{r}"] = fit_length(_fade(out), crop)[0]
+    g["rebuilt_short_target"] = hc.rebuild(hc.split_cycles(sp.abs_max_normalise(x[0]), joins), 100, fade_n)
+    g["rebuilt_long_target"] = hc.rebuild(hc.split_cycles(sp.abs_max_normalise(x[0]), joins)[:2], 200000, fade_n)
+    np.savez_compressed(OUT / "heart_cycles.npz", versions=str(versions), **g)
 
 
 def zerophase_fixture(versions):

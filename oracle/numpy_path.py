@@ -17,6 +17,7 @@ What is restated (reference file:line -> function here):
 * ``signalproc/segment.py:17-52``     -> :class:`WindowSpec`, :func:`window_starts`, :func:`segment`
 * ``signalproc/normalize.py:33-38,47-49,59-72`` -> :func:`minmax_normalise`, :func:`z_normalise`, :func:`kpeak_normalise`
 * ``signalproc/envelopes.py:11-23``   -> :func:`hilbert_envelope`, :func:`homomorphic_envelope`
+* ``datasets/heart_cycles.py:32-69``  -> :func:`split_cycles`, :func:`crossfade`, :func:`rebuild`
 
 Third-party arithmetic (SciPy ``resample_poly``/``butter``/``sosfilt``) is called, not
 restated: SciPy is installed on the GPU box too, and it is the very code the reference runs.
@@ -322,3 +323,42 @@ def homomorphic_envelope(x, fs: float, cutoff: float = 8.0, order: int = 6) -> n
         raise ValueError(f"cutoff {cutoff} Hz is above Nyquist for fs={fs}")
     floor = np.finfo(float).eps
     return np.exp(butter_lowpass_zp(np.log(np.maximum(hilbert_envelope(x), floor)), fs, cutoff, order=order))
+
+
+# --------------------------------------------------------------------------- cardiac-cycle rebuild
+def split_cycles(signal, joins) -> list:
+    """``datasets/heart_cycles.py:32-35``: pieces between consecutive joins that lie strictly inside the signal."""
+    cuts = [j for j in joins if 0 < j < len(signal)]
+    return [signal[lo:hi] for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
+def crossfade(a, b, n: int) -> np.ndarray:
+    """``datasets/heart_cycles.py:38-52``: join ``a`` and ``b`` over ``n`` samples; linear ramp for flat pieces, else the
+    correlation-aware odd/even fade pair."""
+    if n <= 1 or len(a) < n or len(b) < n:
+        return np.concatenate([a, b])
+    out_tail, in_head = a[-n:], b[:n]
+    if np.var(out_tail) < 1e-5 or np.var(in_head) < 1e-5:
+        gain = np.linspace(0.0, 1.0, n)
+    else:
+        rho = np.corrcoef(out_tail, in_head)[0, 1]
+        rho = 0.0 if np.isnan(rho) else abs(rho)
+        u = np.linspace(-1.0, 1.0, n)
+        odd = (9 / 16) * np.sin(np.pi / 2 * u) + (1 / 16) * np.sin(3 * np.pi / 2 * u)
+        even = np.sqrt(np.clip(0.5 / (1 + rho) - ((1 - rho) / (1 + rho)) * odd ** 2, 0.0, None))
+        gain = np.clip(even + odd, 0.0, 1.0)
+    return np.concatenate([a[:-n], out_tail * (1.0 - gain) + in_head * gain, b[n:]])
+
+
+def rebuild(cycles, target_len: int, fade_samples: int) -> np.ndarray:
+    """``datasets/heart_cycles.py:55-69``: append cycles cyclically until ``target_len`` is reached; at most
+    ``10 * len(cycles) + 5`` joins."""
+    if not cycles:
+        return np.zeros(target_len)
+    out, joins = cycles[0], 0
+    while len(out) < target_len:
+        out = crossfade(out, cycles[(joins + 1) % len(cycles)], fade_samples)
+        joins += 1
+        if joins > 10 * len(cycles) + 4:
+            break
+    return out

@@ -192,3 +192,36 @@ def test_other_normalisers_and_envelopes_match_golden(golden):
         np.testing.assert_array_equal(onp.hilbert_envelope(e[r]), g["hilbert"][r])
         np.testing.assert_array_equal(onp.hilbert_envelope(e[r][:2499]), g["hilbert_odd"][r])
         np.testing.assert_array_equal(onp.homomorphic_envelope(e[r], fs), g["homomorphic"][r])
+
+
+def test_heart_cycle_rebuild_matches_golden(golden):
+    """split / crossfade / rebuild of the oracle and the host-side order draw of the package against
+    the reference's datasets/heart_cycles.py run with the same seeded random.Random, bit for bit."""
+    import random
+    from wav2vec_heart_sounds_b200 import heart_cycles as H
+    g = golden("heart_cycles.npz")
+    joins, crop, fade_n = g["joins"].tolist(), int(g["crop"]), int(g["fade_n"])
+    for (seed, pc), want in zip(g["orders_seed_pc"], g["orders6"]):
+        assert H.rearrange_order(6, prob_contiguous=float(pc), rng=random.Random(int(seed))) == want.tolist()
+    for r in range(3):
+        sig = onp.abs_max_normalise(g["x"][r])
+        cycles = onp.split_cycles(sig, joins)
+        assert [(len(c)) for c in cycles] == [hi - lo for lo, hi in H.cycle_bounds(len(sig), joins)]
+        order = H.rearrange_order(len(cycles), rng=random.Random(10 + r))
+        assert order == g[f"order_{r}"].tolist()
+        out = onp.rebuild([cycles[i] for i in order], crop, fade_n)
+        np.testing.assert_array_equal(out, g[f"rebuilt_{r}"])
+        np.testing.assert_array_equal(onp.fit_length(onp.fade(out), crop)[0], g[f"item_{r}"])
+    cycles = onp.split_cycles(onp.abs_max_normalise(g["x"][0]), joins)
+    np.testing.assert_array_equal(onp.rebuild(cycles, 100, fade_n), g["rebuilt_short_target"])
+    np.testing.assert_array_equal(onp.rebuild(cycles[:2], 200000, fade_n), g["rebuilt_long_target"])     # the loop guard
+
+
+def test_load_join_indices(tmp_path):
+    """heart_cycles.py:22-29 (reference test tests/test_heart_cycles.py:17-20): rescaled, zero dropped, sorted, unique."""
+    import json
+    from wav2vec_heart_sounds_b200 import heart_cycles as H
+    path = tmp_path / "p0.json"
+    path.write_text(json.dumps({"segments": [[0], [1500, 1600], [500], [], [1000, 7], [500]], "last_index": 1500, "fs": 1000}))
+    assert H.load_join_indices(path, fs_out=2000) == [1000, 2000, 3000]
+    assert H.load_join_indices(path, fs_out=1000) == [500, 1000, 1500]

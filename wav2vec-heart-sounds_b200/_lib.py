@@ -53,6 +53,10 @@ _SIGNATURES = {
                                        ctypes.c_void_p]),
     "mpcg_row_normalise_f32": (c_int, [c_f32p, c_f32p, ctypes.c_void_p, c_i64, c_i64, c_int, c_int, ctypes.c_double,
                                        ctypes.c_double, c_int, ctypes.c_void_p]),
+    "mpcg_gen_condition_rows_f32": (c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_void_p, c_i64, c_i64, c_i64, c_int,
+                                            ctypes.c_double, c_int, ctypes.c_void_p]),
+    "mpcg_cycle_rebuild_f32": (c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       c_i64, c_i64, c_i64, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_mel_tc_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p,
                                 c_f32p, ctypes.c_float, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_logmap_f32": (c_int, [c_f32p, c_f32p, c_i64, ctypes.c_void_p]),
@@ -95,6 +99,7 @@ RN_MINMAX, RN_ZSCORE, RN_KPEAK = 0, 1, 2
 RN_EPS, RN_GLOBAL = 1, 2
 EPI_NONE, EPI_EXP = 0, 1
 ENV_LOG = 1
+GEN_NO_NORM = 4
 AUG_IDENTITY, AUG_NOISE, AUG_SINE_MUL, AUG_SINE_ADD, AUG_SELECT = 0, 1, 2, 3, 4
 
 

@@ -12,12 +12,13 @@ namespace mpcg {
 constexpr int kGnThreads = 512;
 
 __global__ void __launch_bounds__(kGnThreads)
-gen_condition_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ chirp, long long t, long long crop,
-                     int fade_n, double fs, int norm_flags) {
+gen_condition_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ chirp,
+                     const long long* __restrict__ row_len, long long stride, long long crop, int fade_n, double fs, int norm_flags) {
   __shared__ double dscr[32];
   __shared__ float fscr[32];
   const long long row = blockIdx.x;
-  const float* xr = x + row * t;
+  const float* xr = x + row * stride;
+  const long long t = row_len ? min(max(row_len[row], 0LL), stride) : stride;   // valid samples of this row
   float* yr = y + row * crop;
   const int tid = threadIdx.x;
   // sweep 1: row statistics of the whole recording (normalisation precedes the crop)
@@ -26,12 +27,13 @@ gen_condition_kernel(const float* __restrict__ x, float* __restrict__ y, float* 
   for (long long i = tid; i < t; i += kGnThreads) stats_add(st, xr[i]);
   const double tot = block_sum<kGnThreads>(st.sum, dscr);
   const float lo = block_min<kGnThreads>(st.lo, fscr), hi = block_max<kGnThreads>(st.hi, fscr);
-  const double mean = t > 0 ? tot / (double)t : 0.0;
+  double mean = t > 0 ? tot / (double)t : 0.0;
   const double peak = fmax((double)hi - mean, mean - (double)lo);
   double inv_peak;
   if (norm_flags & MPCG_NORM_PEAK_GT0) inv_peak = (peak > 0.0) ? 1.0 / peak : 1.0;
   else inv_peak = 1.0 / fmax(peak, 1e-12);
-  const bool clampit = (norm_flags & MPCG_NORM_PEAK_GT0) == 0;      // the tensor path clamps, the NumPy path does not
+  bool clampit = (norm_flags & MPCG_NORM_PEAK_GT0) == 0;            // the tensor path clamps, the NumPy path does not
+  if (norm_flags & MPCG_GEN_NO_NORM) { mean = 0.0; inv_peak = 1.0; clampit = false; }   // rows rebuilt from normalised cycles
   const bool fade = fade_n > 1 && t >= 2LL * fade_n;
   const double step = fade_n > 1 ? 1.0 / (double)(fade_n - 1) : 0.0;
   // sweep 2: normalise, fade, fit to `crop`; maximum magnitude of what is written
@@ -68,15 +70,20 @@ gen_condition_kernel(const float* __restrict__ x, float* __restrict__ y, float* 
 
 }  // namespace mpcg
 
-extern "C" int mpcg_gen_condition_f32(const float* x, float* y, float* chirp, int64_t rows, int64_t t, int64_t crop,
-                                      int fade_n, double fs, int norm_flags, void* stream) {
+extern "C" int mpcg_gen_condition_rows_f32(const float* x, float* y, float* chirp, const int64_t* row_len, int64_t rows,
+                                           int64_t t, int64_t crop, int fade_n, double fs, int norm_flags, void* stream) {
   using namespace mpcg;
   if (rows < 0 || t < 0 || crop < 0 || fade_n < 0 || !(fs > 0.0)) return MPCG_EINVAL;
   if (rows == 0 || crop == 0) return MPCG_OK;
   if (!y || (t > 0 && !x)) return MPCG_EINVAL;
   if (rows > 0x7fffffffLL) return MPCG_ERANGE;
-  gen_condition_kernel<<<(unsigned)rows, kGnThreads, 0, (cudaStream_t)stream>>>(x, y, chirp, (long long)t, (long long)crop,
-                                                                               fade_n, fs, norm_flags);
+  gen_condition_kernel<<<(unsigned)rows, kGnThreads, 0, (cudaStream_t)stream>>>(
+      x, y, chirp, reinterpret_cast<const long long*>(row_len), (long long)t, (long long)crop, fade_n, fs, norm_flags);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
+}
+
+extern "C" int mpcg_gen_condition_f32(const float* x, float* y, float* chirp, int64_t rows, int64_t t, int64_t crop,
+                                      int fade_n, double fs, int norm_flags, void* stream) {
+  return mpcg_gen_condition_rows_f32(x, y, chirp, nullptr, rows, t, crop, fade_n, fs, norm_flags, stream);
 }

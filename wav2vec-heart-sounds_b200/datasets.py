@@ -146,12 +146,18 @@ def device_batch_transform(fs: int, cfg=None, *, pcg_channel: int = 0, noise: st
 
 
 def condition_generator_batch(reference: torch.Tensor, conditioning: torch.Tensor, fs: int, mel_transform, crop_frames: int,
-                              hop_length: int, *, fade: int = 128, chirp: bool = True) -> dict:
-    """The per-item work of the generator datasets for a whole batch on the device (SURVEY.md section 8f, rank 2;
-    reference ``datasets/generative.py:77-115``, without the cardiac-cycle rearrangement, which reads per-record
-    segmentation files): ``abs_max_normalise`` -> fade -> ``fit_length(crop_frames * hop_length)`` for the reference
-    and the conditioning waveforms ``[B, T]``, ``log_mel`` of the conditioning cut or zero-padded to ``crop_frames``
-    frames, and the chirp reference plot signal.  Keys as in the reference's item dictionary."""
+                              hop_length: int, *, fade: int = 128, chirp: bool = True, cycles=None,
+                              fade_ms: float = 10.0) -> dict:
+    """The per-item work of the generator datasets for a whole batch on the device (SURVEY.md section 8f, ranks 2 and
+    4; reference ``datasets/generative.py:62-115``): ``abs_max_normalise`` -> [cardiac-cycle rebuild] -> fade ->
+    ``fit_length(crop_frames * hop_length)`` for the reference and the conditioning waveforms ``[B, T]``, ``log_mel``
+    of the conditioning cut or zero-padded to ``crop_frames`` frames, and the chirp reference plot signal.  Keys as in
+    the reference's item dictionary.
+
+    ``cycles``: optional, one entry per row -- the row's cardiac cycles as ``(start, end)`` pairs in the order they
+    are to be joined (``heart_cycles.cycle_bounds`` reordered by ``heart_cycles.rearrange_order``), or ``None`` /
+    fewer than two cycles for a row that keeps its waveform (``generative.py:67-68,86-87``).  Both waveforms of a row
+    are cut at the same joins and crossfaded over ``round(fade_ms / 1000 * fs)`` samples (``generative.py:56``)."""
     ref = _lib.require_cuda_f32(reference, "reference")
     con = _lib.require_cuda_f32(conditioning, "conditioning")
     if ref.dim() != 2 or con.dim() != 2 or ref.shape[0] != con.shape[0]:
@@ -159,12 +165,24 @@ def condition_generator_batch(reference: torch.Tensor, conditioning: torch.Tenso
     b, crop = ref.shape[0], int(crop_frames) * int(hop_length)
     from .spectrogram import log_mel
 
+    if cycles is not None:
+        from . import heart_cycles, torchproc
+        if len(cycles) != b:
+            raise ValueError("cycles needs one entry per row")
+        plan = [list(c) if c is not None and len(c) >= 2 else None for c in cycles]
+        fade_n = int(round(fade_ms / 1000.0 * fs))
+
     def run(x, want_chirp):
         x = x.contiguous()
+        lengths, flags = None, _lib.NORM_PEAK_GT0
+        if cycles is not None:
+            x, lengths = heart_cycles.rebuild_batch(torchproc.abs_max_normalise(x, mode="numpy"), plan, crop, fade_n)
+            flags |= _lib.GEN_NO_NORM
         y = torch.empty((b, crop), device=x.device, dtype=torch.float32)
         c = torch.empty((b, crop), device=x.device, dtype=torch.float32) if want_chirp else None
-        _lib.check(_lib.lib().mpcg_gen_condition_f32(x.data_ptr(), y.data_ptr(), _lib.ptr(c), b, x.shape[1], crop, int(fade),
-                                                     float(fs), _lib.NORM_PEAK_GT0, _lib.stream_ptr(x)), "generator conditioning")
+        _lib.check(_lib.lib().mpcg_gen_condition_rows_f32(x.data_ptr(), y.data_ptr(), _lib.ptr(c), _lib.ptr(lengths), b,
+                                                          x.shape[1], crop, int(fade), float(fs), flags, _lib.stream_ptr(x)),
+                   "generator conditioning")
         return y, c
 
     ref_y, chirp_y = run(ref, chirp)
