@@ -13,7 +13,7 @@
 // once per call with the same kernels) is stored the same way.  Five launches per batch, each a read + write of the
 // [rows, M] complex workspace:
 //   columns (x w -> FFT -> twiddle) | rows (FFT * B -> IFFT) | columns (IFFT -> h conj -> FFT) | rows | columns (IFFT -> |.|)
-// Radix-2 shared-memory FFTs: decimation in time from a bit-reversed scatter, decimation in frequency into a
+// Shared-memory FFTs with radix-8 register butterflies: decimation in time from a bit-reversed scatter, decimation in frequency into a
 // bit-reversed gather, so no separate permutation pass.  flags & MPCG_ENV_LOG writes log(max(envelope, eps)), the input
 // of the homomorphic envelope's low-pass (envelopes.py:21-22).
 #include "common.cuh"
@@ -35,6 +35,11 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 
+// Shared-memory index padding (in 16-byte elements): one pad per 8 and per 64 elements, so that strides of 8 and of 64
+// elements -- the first merged pass and the bit-reversed scatter / gather -- fall on different banks within a quarter warp.
+__host__ __device__ __forceinline__ int ev_pad(int i) { return i + (i >> 3) + (i >> 6); }
+__host__ __device__ __forceinline__ int ev_seq_stride(int n) { return ev_pad(n) | 1; }
+
 __device__ __forceinline__ double2 ev_root(const double2* __restrict__ hi, const double2* __restrict__ lo, long long idx) {
   return cmul(hi[idx >> 10], lo[idx & (kEvLo - 1)]);
 }
@@ -43,42 +48,89 @@ __device__ __forceinline__ double2 ev_root(const double2* __restrict__ hi, const
 __device__ __forceinline__ void ev_fill_tw(double2* tw, int logn, const EvPlan& p, const double2* hi, const double2* lo) {
   const int half = 1 << (logn - 1);
   const long long step = p.m >> logn;
-  for (int j = threadIdx.x; j < half; j += kEvThreads) tw[j] = ev_root(hi, lo, (long long)j * step);
+  for (int j = threadIdx.x; j < half; j += kEvThreads) tw[ev_pad(j)] = ev_root(hi, lo, (long long)j * step);
 }
 
-// In-place radix-2 FFTs of `nf` sequences of length 1 << logn, sequence f at d + f * stride.
+// In-place FFTs of `nf` sequences of length 1 << logn, sequence f at d + f * stride.
 // DIT: input in bit-reversed positions, output in natural order.  DIF: natural in, bit-reversed out.
-__device__ __forceinline__ void ev_fft_dit(double2* d, int logn, int nf, int stride, const double2* tw) {
-  const int hl = logn - 1, halfn = 1 << hl;
-  for (int s = 0; s < logn; ++s) {
-    const int half = 1 << s;
-    for (int b = threadIdx.x; b < nf << hl; b += kEvThreads) {
-      const int f = b >> hl, j = b & (halfn - 1);
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) + pos;
-      double2* q = d + f * stride;
-      const double2 u = q[i0], v = cmul(q[i0 + half], tw[pos << (hl - s)]);
-      q[i0] = make_double2(u.x + v.x, u.y + v.y);
-      q[i0 + half] = make_double2(u.x - v.x, u.y - v.y);
+// Up to three radix-2 stages are merged per pass (a radix-8 butterfly held in registers): shared-memory traffic, not the
+// fp64 pipe, bounds a stage-per-pass transform.  Twiddles of a merged group: stage s+u needs
+// exp(-2 pi i (p + k 2^s) / 2^(s+u+1)) = base_u * (8th root of unity)^(k << (2-u)), base_u = omega_(s+u+1)^p, and
+// base_u = base_(u+1)^2 -- one table load per group.
+template <int E>
+__device__ __forceinline__ double2 ev_mul_root8(double2 z) {       // z * exp(-2 pi i E / 8)
+  constexpr double h = 0.70710678118654752440;
+  if (E == 0) return z;
+  if (E == 1) return make_double2((z.x + z.y) * h, (z.y - z.x) * h);
+  if (E == 2) return make_double2(z.y, -z.x);
+  return make_double2((z.y - z.x) * h, -(z.x + z.y) * h);            // E == 3
+}
+
+template <int Q, bool DIT, int U, int M>
+struct EvStage {                                                     // butterflies of merged stage U on local indices >= M
+  static __device__ __forceinline__ void run(double2 (&r)[1 << Q], const double2 (&base)[Q]) {
+    if constexpr (M < (1 << Q)) {
+      if constexpr ((M & (1 << U)) == 0) {
+        constexpr int K = M & ((1 << U) - 1);
+        const double2 w = ev_mul_root8<(K << (2 - U)) & 3>(base[U]);
+        if constexpr (DIT) {
+          const double2 a = r[M], b = cmul(r[M + (1 << U)], w);
+          r[M] = make_double2(a.x + b.x, a.y + b.y);
+          r[M + (1 << U)] = make_double2(a.x - b.x, a.y - b.y);
+        } else {
+          const double2 a = r[M], b = r[M + (1 << U)];
+          r[M] = make_double2(a.x + b.x, a.y + b.y);
+          r[M + (1 << U)] = cmul(make_double2(a.x - b.x, a.y - b.y), w);
+        }
+      }
+      EvStage<Q, DIT, U, M + 1>::run(r, base);
     }
-    __syncthreads();
   }
+};
+
+// One pass over stages s .. s+Q-1 of every sequence.
+template <int Q, bool DIT>
+__device__ __forceinline__ void ev_pass(double2* d, int logn, int nf, int stride, const double2* tw, int s) {
+  constexpr int R = 1 << Q;
+  const int hl = logn - 1, lg = logn - Q;                            // groups per sequence = 1 << lg
+  for (int b = threadIdx.x; b < nf << lg; b += kEvThreads) {
+    const int f = b >> lg, j = b & ((1 << lg) - 1);
+    const int p = j & ((1 << s) - 1);
+    double2* q = d + f * stride;
+    const int i0 = ((j >> s) << (s + Q)) + p;
+    double2 r[R], base[Q];
+#pragma unroll
+    for (int m = 0; m < R; ++m) r[m] = q[ev_pad(i0 + (m << s))];
+    base[Q - 1] = tw[ev_pad(p << (hl - (s + Q - 1)))];
+#pragma unroll
+    for (int u = Q - 2; u >= 0; --u) base[u] = cmul(base[u + 1], base[u + 1]);
+    if constexpr (DIT) {
+      EvStage<Q, true, 0, 0>::run(r, base);
+      if constexpr (Q > 1) EvStage<Q, true, 1, 0>::run(r, base);
+      if constexpr (Q > 2) EvStage<Q, true, 2, 0>::run(r, base);
+    } else {
+      if constexpr (Q > 2) EvStage<Q, false, 2, 0>::run(r, base);
+      if constexpr (Q > 1) EvStage<Q, false, 1, 0>::run(r, base);
+      EvStage<Q, false, 0, 0>::run(r, base);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) q[ev_pad(i0 + (m << s))] = r[m];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void ev_fft_dit(double2* d, int logn, int nf, int stride, const double2* tw) {
+  int s = 0;
+  for (; s + 3 <= logn; s += 3) ev_pass<3, true>(d, logn, nf, stride, tw, s);
+  if (logn - s == 2) ev_pass<2, true>(d, logn, nf, stride, tw, s);
+  else if (logn - s == 1) ev_pass<1, true>(d, logn, nf, stride, tw, s);
 }
 __device__ __forceinline__ void ev_fft_dif(double2* d, int logn, int nf, int stride, const double2* tw) {
-  const int hl = logn - 1, halfn = 1 << hl;
-  for (int s = hl; s >= 0; --s) {
-    const int half = 1 << s;
-    for (int b = threadIdx.x; b < nf << hl; b += kEvThreads) {
-      const int f = b >> hl, j = b & (halfn - 1);
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> s) << (s + 1)) + pos;
-      double2* q = d + f * stride;
-      const double2 u = q[i0], v = q[i0 + half];
-      q[i0] = make_double2(u.x + v.x, u.y + v.y);
-      q[i0 + half] = cmul(make_double2(u.x - v.x, u.y - v.y), tw[pos << (hl - s)]);
-    }
-    __syncthreads();
-  }
+  // the mirror image: the passes of the DIT transform in reverse order, each run backwards
+  const int rem = logn % 3, full = logn - rem;
+  if (rem == 2) ev_pass<2, false>(d, logn, nf, stride, tw, full);
+  else if (rem == 1) ev_pass<1, false>(d, logn, nf, stride, tw, full);
+  for (int s = full - 3; s >= 0; s -= 3) ev_pass<3, false>(d, logn, nf, stride, tw, s);
 }
 __device__ __forceinline__ int ev_rev(int i, int logn) { return (int)(__brev((unsigned)i) >> (32 - logn)); }
 
@@ -119,8 +171,8 @@ ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, flo
   extern __shared__ __align__(16) unsigned char ev_raw[];
   double2* tw = reinterpret_cast<double2*>(ev_raw);
   const int m1 = 1 << p.log1, m2 = 1 << p.log2;
-  double2* d = tw + (m1 >> 1);
-  const int stride = m1 + 1;
+  double2* d = tw + ev_pad(m1 >> 1) + 1;
+  const int stride = ev_seq_stride(m1);
   const long long row = blockIdx.y;
   const int c0 = blockIdx.x * p.cols;
   double2* ur = u + row * p.m;
@@ -141,7 +193,7 @@ ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, flo
       const double2 t = cmul(ur[n], cconj(ev_root(hi, lo, ((long long)n1 * (c0 + c)) & (p.m - 1))));
       v = cconj(t);
     }
-    d[c * stride + ev_rev(n1, p.log1)] = v;
+    d[c * stride + ev_pad(ev_rev(n1, p.log1))] = v;
   }
   __syncthreads();
   ev_fft_dit(d, p.log1, p.cols, stride, tw);
@@ -151,7 +203,7 @@ ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, flo
       const int n1 = e >> lc, c = e & (p.cols - 1);
       const long long n = (long long)n1 * m2 + c0 + c;
       if (n < p.n) {
-        const double2 v = d[c * stride + n1];
+        const double2 v = d[c * stride + ev_pad(n1)];
         double env = sqrt(v.x * v.x + v.y * v.y) * scale;
         if (flags & MPCG_ENV_LOG) env = log(fmax(env, 2.220446049250313e-16));
         y[row * p.n + n] = (float)env;
@@ -167,7 +219,7 @@ ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, flo
       const int n1 = e >> lc, c = e & (p.cols - 1);
       const long long n = (long long)n1 * m2 + c0 + c;
       const double h = n == 0 || n == nyq ? 1.0 : (n < top ? 2.0 : 0.0);
-      double2& v = d[c * stride + n1];
+      double2& v = d[c * stride + ev_pad(n1)];
       v = make_double2(v.x * h, v.y * h);
     }
     __syncthreads();
@@ -176,7 +228,7 @@ ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, flo
   // store with the forward twiddle exp(-2 pi i n2 k1 / M); after the DIF transform element k1 sits at rev(k1)
   for (int e = threadIdx.x; e < m1 << lc; e += kEvThreads) {
     const int k1 = e >> lc, c = e & (p.cols - 1);
-    const double2 v = d[c * stride + (MODE == EV_COL_MID ? ev_rev(k1, p.log1) : k1)];
+    const double2 v = d[c * stride + ev_pad(MODE == EV_COL_MID ? ev_rev(k1, p.log1) : k1)];
     ur[(long long)k1 * m2 + c0 + c] = cmul(v, ev_root(hi, lo, ((long long)k1 * (c0 + c)) & (p.m - 1)));
   }
 }
@@ -189,30 +241,30 @@ ev_row_kernel(const __grid_constant__ EvPlan p, double2* __restrict__ u, const d
   extern __shared__ __align__(16) unsigned char ev_raw[];
   double2* tw = reinterpret_cast<double2*>(ev_raw);
   const int m2 = 1 << p.log2;
-  double2* d = tw + (m2 >> 1);
-  const int stride = m2 + 1;
+  double2* d = tw + ev_pad(m2 >> 1) + 1;
+  const int stride = ev_seq_stride(m2);
   const long long base = (long long)blockIdx.x * p.rws * m2;
   double2* ur = u + (long long)blockIdx.y * p.m + base;
   ev_fill_tw(tw, p.log2, p, hi, lo);
   for (int e = threadIdx.x; e < p.rws << p.log2; e += kEvThreads) {
     const int r = e >> p.log2, i = e & (m2 - 1);
-    d[r * stride + ev_rev(i, p.log2)] = ur[e];
+    d[r * stride + ev_pad(ev_rev(i, p.log2))] = ur[e];
   }
   __syncthreads();
   ev_fft_dit(d, p.log2, p.rws, stride, tw);
   if (!conv) {
-    for (int e = threadIdx.x; e < p.rws << p.log2; e += kEvThreads) ur[e] = d[(e >> p.log2) * stride + (e & (m2 - 1))];
+    for (int e = threadIdx.x; e < p.rws << p.log2; e += kEvThreads) ur[e] = d[(e >> p.log2) * stride + ev_pad(e & (m2 - 1))];
     return;
   }
   for (int e = threadIdx.x; e < p.rws << p.log2; e += kEvThreads) {
-    double2& v = d[(e >> p.log2) * stride + (e & (m2 - 1))];
+    double2& v = d[(e >> p.log2) * stride + ev_pad(e & (m2 - 1))];
     v = cconj(cmul(v, bk[base + e]));
   }
   __syncthreads();
   ev_fft_dif(d, p.log2, p.rws, stride, tw);
   for (int e = threadIdx.x; e < p.rws << p.log2; e += kEvThreads) {
     const int r = e >> p.log2, i = e & (m2 - 1);
-    ur[e] = cconj(d[r * stride + ev_rev(i, p.log2)]);
+    ur[e] = cconj(d[r * stride + ev_pad(ev_rev(i, p.log2))]);
   }
 }
 
@@ -224,8 +276,9 @@ static bool ev_make_plan(long long n, EvPlan* p) {
   p->m = 1LL << lg;
   p->log1 = lg / 2;
   p->log2 = lg - p->log1;
-  p->cols = p->log1 >= 10 ? 4 : 8;
-  p->rws = 4;
+  // 4096 points per CTA (64 KB of fp64 pairs), at least 4 adjacent columns (64-byte runs) per column transform
+  p->cols = 1 << (p->log1 >= 10 ? 2 : (12 - p->log1 < p->log2 ? 12 - p->log1 : p->log2));
+  p->rws = 1 << (12 - p->log2 < p->log1 ? 12 - p->log2 : p->log1);
   return true;
 }
 static size_t ev_fixed_bytes(const EvPlan& p) {                     // chirp + root tables + kernel spectrum
@@ -259,8 +312,8 @@ extern "C" int mpcg_hilbert_envelope_f32(const float* x, float* y, void* work, i
   double2* bk = lo + kEvLo;
   double2* u = bk + p.m;
   const int m1 = 1 << p.log1, m2 = 1 << p.log2;
-  const size_t col_smem = ((size_t)(m1 >> 1) + (size_t)p.cols * (m1 + 1)) * sizeof(double2);
-  const size_t row_smem = ((size_t)(m2 >> 1) + (size_t)p.rws * (m2 + 1)) * sizeof(double2);
+  const size_t col_smem = ((size_t)ev_pad(m1 >> 1) + 1 + (size_t)p.cols * ev_seq_stride(m1)) * sizeof(double2);
+  const size_t row_smem = ((size_t)ev_pad(m2 >> 1) + 1 + (size_t)p.rws * ev_seq_stride(m2)) * sizeof(double2);
   cudaError_t e;
 #define EV_ATTR(k, bytes)                                                                      \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
