@@ -165,7 +165,7 @@ enum { EV_COL_PLAIN = 0, EV_COL_FIRST = 1, EV_COL_MID = 2, EV_COL_LAST = 3 };
 
 // Column transforms: CTA (blockIdx.x, blockIdx.y) owns columns n2 = blockIdx.x * cols .. + cols of row blockIdx.y.
 template <int MODE>
-__global__ void __launch_bounds__(kEvThreads)
+__global__ void __launch_bounds__(kEvThreads, 2)
 ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, float* __restrict__ y, double2* __restrict__ u,
               const double2* __restrict__ chirp, const double2* __restrict__ hi, const double2* __restrict__ lo, int flags) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
@@ -235,7 +235,7 @@ ev_col_kernel(const __grid_constant__ EvPlan p, const float* __restrict__ x, flo
 
 // Row transforms: CTA (blockIdx.x, blockIdx.y) owns rows k1 = blockIdx.x * rws .. + rws of signal blockIdx.y.
 // conv != 0: FFT, times the kernel spectrum, inverse FFT (unnormalised); conv == 0: FFT only (building the kernel spectrum).
-__global__ void __launch_bounds__(kEvThreads)
+__global__ void __launch_bounds__(kEvThreads, 2)
 ev_row_kernel(const __grid_constant__ EvPlan p, double2* __restrict__ u, const double2* __restrict__ bk,
               const double2* __restrict__ hi, const double2* __restrict__ lo, int conv) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
