@@ -8,7 +8,8 @@
 //
 // Layout: spectra are frame-major, S[row][frame][bin] (bin contiguous), so FFT output and the frequency median are
 // unit-stride and the time median is coalesced across bins.  FFTs are radix-2 in shared memory, one frame per
-// CTA; medians keep a sorted window per thread in shared memory and slide it (remove oldest, insert newest),
+// CTA; medians keep a sorted window per thread in shared memory and slide it (remove oldest, insert newest, one
+// branch-free pass over the k slots),
 // O(k) per output instead of a fresh selection.  Median results are bit-exact functions of the magnitudes:
 // window [i - k/2, i - k/2 + k - 1], half-sample-symmetric reflection, rank k/2 (upper median for even k).
 #include "common.cuh"
@@ -82,47 +83,187 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {       // d c b a | a 
 }
 
 // Each thread owns one line (a bin for the time median, a frame for the frequency median) and walks along it.
-// sorted[kk][thread] (shared, column per thread) holds the current window in ascending order.
-__global__ void __launch_bounds__(kMedThreads)
-hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time) {
-  extern __shared__ float med_sorted[];                          // [k][kMedThreads]
-  const long long row = blockIdx.y;
-  const int line = blockIdx.x * kMedThreads + threadIdx.x;
-  const int nlines = along_time ? bins : frames;
-  if (line >= nlines) return;
-  const int len = along_time ? frames : bins;
-  const long long stride = along_time ? bins : 1;
-  const float2* src = spec + (long long)row * frames * bins + (along_time ? line : (long long)line * bins);
-  float* dst = out + (long long)row * frames * bins + (along_time ? line : (long long)line * bins);
-  float* sw = med_sorted + threadIdx.x;
-  auto mag_at = [&](int i) {
-    const float2 v = src[(long long)reflect_idx(i, len) * stride];
+// The current window is kept sorted; ring[kk][thread] (shared) holds the same magnitudes in arrival order, so the sample
+// that leaves is not fetched and rooted again.  The slide -- drop one copy of `gone`, insert `come` -- is ONE uniform pass
+// over the slots with selects only (no data-dependent loop, the lanes of a warp never diverge):
+//   b[p]   = a[p] < gone ? a[p] : a[p+1]                 (the window without the first copy of `gone`;  a[k] = +inf)
+//   new[p] = max(b[p-1], min(b[p], come))                (insertion into a sorted list;  b[-1] = -inf)
+// Windows of up to 32 samples live in REGISTERS (K slots, K a multiple of 4): the k real samples are framed by -inf
+// sentinels below and +inf above so that the median always sits in slot K/2 -- no dynamic register index.  Larger
+// windows run the same pass over a shared-memory column per thread.
+struct MedLine {
+  const float2* src;
+  float* dst;
+  int len;
+  long long stride;
+  __device__ __forceinline__ float mag(int i) const {
+    const int j = (unsigned)i < (unsigned)len ? i : reflect_idx(i, len);
+    const float2 v = src[(long long)j * stride];
     return sqrtf(v.x * v.x + v.y * v.y);
-  };
-  const int left = k / 2;
-  // initial window for output 0: indices -left .. -left + k - 1, insertion sort
+  }
+};
+
+// first window (indices -left .. -left + k - 1) insertion-sorted into sw[], arrival order into ring[]
+__device__ __forceinline__ void med_first_window(const MedLine& ln, float* sw, float* ring, int k, int left) {
   for (int q = 0; q < k; ++q) {
-    const float v = mag_at(q - left);
+    const float v = ln.mag(q - left);
+    ring[q * kMedThreads] = v;
     int p = q;
     while (p > 0 && sw[(p - 1) * kMedThreads] > v) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
     sw[p * kMedThreads] = v;
   }
-  dst[0] = sw[left * kMedThreads];
-  for (int i = 1; i < len; ++i) {
-    const float gone = mag_at(i - 1 - left);                     // leaves the window
-    const float come = mag_at(i - left + k - 1);                 // enters it
-    if (gone != come) {
-      // remove one occurrence of `gone`, then insert `come`, keeping the array sorted
-      int p = 0;
-      while (p < k - 1 && sw[p * kMedThreads] != gone) ++p;      // present by construction (bounded for NaNs)
-      if (come > gone) {
-        while (p + 1 < k && sw[(p + 1) * kMedThreads] < come) { sw[p * kMedThreads] = sw[(p + 1) * kMedThreads]; ++p; }
-      } else {
-        while (p > 0 && sw[(p - 1) * kMedThreads] > come) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
-      }
-      sw[p * kMedThreads] = come;
+}
+
+__device__ __forceinline__ bool med_setup(MedLine& ln, const float2* spec, float* out, int frames, int bins, int along_time) {
+  const long long row = blockIdx.y;
+  const int line = blockIdx.x * kMedThreads + threadIdx.x;
+  if (line >= (along_time ? bins : frames)) return false;
+  ln.len = along_time ? frames : bins;
+  ln.stride = along_time ? bins : 1;
+  const long long off = (long long)row * frames * bins + (along_time ? line : (long long)line * bins);
+  ln.src = spec + off;
+  ln.dst = out + off;
+  return true;
+}
+
+template <int K>
+__device__ __forceinline__ void med_slide(float (&a)[K], float gone, float come) {
+  float below_b = -INFINITY;
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const float b = a[p] < gone ? a[p] : (p + 1 < K ? a[p + 1] : INFINITY);
+    a[p] = fmaxf(below_b, fminf(b, come));
+    below_b = b;
+  }
+}
+
+// Frequency direction (a thread owns a frame and walks along its bins): neighbouring threads are a whole frame apart in
+// memory, so the magnitudes are staged through shared memory -- every warp loads 32 consecutive bins of one frame
+// (256 contiguous bytes), the medians of a chunk go back the same way.  The walk consumes the reflected input stream
+// position by position: stream position s is bin s - k/2, output i is complete once position i + k - 1 has arrived.
+constexpr int kMedChunk = 32;
+template <int K>
+__global__ void __launch_bounds__(kMedThreads)
+hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k) {
+  extern __shared__ float med_sorted[];                          // sorted [k][T] | ring [k][T] | in [32][T+1] | out [32][T+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* sw = med_sorted + tid;
+  float* ring = med_sorted + k * kMedThreads + tid;
+  float* tin = med_sorted + 2 * k * kMedThreads;
+  float* tout = tin + kMedChunk * (kMedThreads + 1);
+  const long long row = blockIdx.y;
+  const int f0 = blockIdx.x * kMedThreads;
+  const float2* src = spec + ((long long)row * frames + f0) * bins;
+  float* dst = out + ((long long)row * frames + f0) * bins;
+  const int nf = min(kMedThreads, frames - f0);                  // frames of this CTA
+  const int left = k / 2, below = K / 2 - left;
+  // stage stream positions [s0, s0 + 32): magnitude of bin reflect(s - left) of every frame of the CTA
+  auto stage_in = [&](int s0) {
+    const int j = s0 + lane - left;
+    const int b = (unsigned)j < (unsigned)bins ? j : reflect_idx(j, bins);
+    for (int f = warp; f < kMedThreads; f += kMedThreads / 32) {
+      float m = 0.f;
+      if (f < nf) { const float2 v = src[(long long)f * bins + b]; m = sqrtf(v.x * v.x + v.y * v.y); }
+      tin[lane * (kMedThreads + 1) + f] = m;
     }
-    dst[(long long)i * stride] = sw[left * kMedThreads];
+  };
+  // first window: stream positions 0 .. k-1 (k <= 32: one staged chunk)
+  stage_in(0);
+  __syncthreads();
+  for (int q = 0; q < k; ++q) {
+    const float v = tin[q * (kMedThreads + 1) + tid];
+    ring[q * kMedThreads] = v;
+    int p = q;
+    while (p > 0 && sw[(p - 1) * kMedThreads] > v) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
+    sw[p * kMedThreads] = v;
+  }
+  float a[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const int q = p - below;
+    a[p] = q < 0 ? -INFINITY : (q < k ? sw[q * kMedThreads] : INFINITY);
+  }
+  if (tid < nf) dst[(long long)tid * bins] = a[K / 2];             // output 0
+  int slot = 0;
+  const int total = bins + k - 1;                                 // stream length
+  for (int s0 = k; s0 < total; s0 += kMedChunk) {
+    __syncthreads();
+    stage_in(s0);
+    __syncthreads();
+    const int n = min(kMedChunk, total - s0);
+    for (int c = 0; c < n; ++c) {
+      const float come = tin[c * (kMedThreads + 1) + tid];
+      const float gone = ring[slot * kMedThreads];
+      ring[slot * kMedThreads] = come;
+      slot = slot + 1 == k ? 0 : slot + 1;
+      med_slide<K>(a, gone, come);
+      tout[c * (kMedThreads + 1) + tid] = a[K / 2];                // output s0 + c - k + 1
+    }
+    __syncthreads();
+    const int i0 = s0 - k + 1;
+    for (int f = warp; f < nf; f += kMedThreads / 32)
+      if (lane < n) dst[(long long)f * bins + i0 + lane] = tout[lane * (kMedThreads + 1) + f];
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kMedThreads)
+hpss_median_reg_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time) {
+  extern __shared__ float med_sorted[];                          // [k][kMedThreads] first window + [k][kMedThreads] ring
+  MedLine ln;
+  if (!med_setup(ln, spec, out, frames, bins, along_time)) return;
+  float* sw = med_sorted + threadIdx.x;
+  float* ring = med_sorted + k * kMedThreads + threadIdx.x;
+  const int left = k / 2, below = K / 2 - left;                  // -inf sentinels under the window
+  med_first_window(ln, sw, ring, k, left);
+  float a[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const int q = p - below;
+    a[p] = q < 0 ? -INFINITY : (q < k ? sw[q * kMedThreads] : INFINITY);
+  }
+  ln.dst[0] = a[K / 2];
+  int slot = 0;                                                  // ring position of the oldest sample
+  float ahead = ln.mag(k - left);                                // the entering sample, fetched one step ahead
+  for (int i = 1; i < ln.len; ++i) {
+    const float gone = ring[slot * kMedThreads];
+    const float come = ahead;                                    // index i - left + k - 1
+    ahead = ln.mag(i - left + k);
+    ring[slot * kMedThreads] = come;
+    slot = slot + 1 == k ? 0 : slot + 1;
+    med_slide<K>(a, gone, come);
+    ln.dst[(long long)i * ln.stride] = a[K / 2];
+  }
+}
+
+__global__ void __launch_bounds__(kMedThreads)
+hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time) {
+  extern __shared__ float med_sorted[];                          // [k][kMedThreads] sorted + [k][kMedThreads] ring
+  MedLine ln;
+  if (!med_setup(ln, spec, out, frames, bins, along_time)) return;
+  float* sw = med_sorted + threadIdx.x;
+  float* ring = med_sorted + k * kMedThreads + threadIdx.x;
+  const int left = k / 2;
+  med_first_window(ln, sw, ring, k, left);
+  ln.dst[0] = sw[left * kMedThreads];
+  int slot = 0;
+  float ahead = ln.mag(k - left);
+  for (int i = 1; i < ln.len; ++i) {
+    const float gone = ring[slot * kMedThreads];
+    const float come = ahead;
+    ahead = ln.mag(i - left + k);
+    ring[slot * kMedThreads] = come;
+    slot = slot + 1 == k ? 0 : slot + 1;
+    float below_b = -INFINITY, cur = sw[0];
+#pragma unroll 4
+    for (int p = 0; p < k; ++p) {
+      const float nxt = p + 1 < k ? sw[(p + 1) * kMedThreads] : INFINITY;
+      const float b = cur < gone ? cur : nxt;
+      sw[p * kMedThreads] = fmaxf(below_b, fminf(b, come));
+      below_b = b;
+      cur = nxt;
+    }
+    ln.dst[(long long)i * ln.stride] = sw[left * kMedThreads];
   }
 }
 
@@ -312,10 +453,36 @@ extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows,
   if (!spec || !out) return MPCG_EINVAL;
   if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
   const int64_t nlines = along_time ? bins : frames;
-  const size_t smem = (size_t)k * kMedThreads * sizeof(float);
+  const size_t smem = 2 * (size_t)k * kMedThreads * sizeof(float);
   dim3 grid((unsigned)((nlines + kMedThreads - 1) / kMedThreads), (unsigned)rows);
-  hpss_median_kernel<<<grid, kMedThreads, smem, (cudaStream_t)stream>>>((const float2*)spec, out, (int)frames, bins, k,
-                                                                      along_time);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(hpss_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float2* sp = (const float2*)spec;
+  const size_t smem_f = smem + 2 * (size_t)kMedChunk * (kMedThreads + 1) * sizeof(float);
+#define MED_REG(KK)                                                                                                  \
+  if (along_time) {                                                                                                  \
+    hpss_median_reg_kernel<KK><<<grid, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, 1);                      \
+  } else {                                                                                                           \
+    cudaError_t e = cudaFuncSetAttribute(hpss_median_freq_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         (int)smem_f);                                                               \
+    if (e != cudaSuccess) return (int)e;                                                                             \
+    hpss_median_freq_kernel<KK><<<grid, kMedThreads, smem_f, st>>>(sp, out, (int)frames, bins, k);                     \
+  }
+  switch ((k + 3) / 4) {
+    case 1: MED_REG(4); break;
+    case 2: MED_REG(8); break;
+    case 3: MED_REG(12); break;
+    case 4: MED_REG(16); break;
+    case 5: MED_REG(20); break;
+    case 6: MED_REG(24); break;
+    case 7: MED_REG(28); break;
+    case 8: MED_REG(32); break;
+    default: hpss_median_kernel<<<grid, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, along_time);
+  }
+#undef MED_REG
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }
