@@ -7,7 +7,7 @@
 //   mpcg_hpss_mix_f32         the random re-weighting tail of hpss_recombine (two mixes, three normalisations)
 //
 // Layout: spectra are frame-major, S[row][frame][bin] (bin contiguous), so FFT output and the frequency median are
-// unit-stride and the time median is coalesced across bins.  FFTs are radix-2 in shared memory, one frame per
+// unit-stride and the time median is coalesced across bins.  FFTs run in shared memory with radix-8 / radix-4 register butterflies, one frame per
 // CTA; medians keep a sorted window per thread in shared memory and slide it (remove oldest, insert newest, one
 // branch-free pass over the k slots),
 // O(k) per output instead of a fresh selection.  Median results are bit-exact functions of the magnitudes:
@@ -20,24 +20,84 @@ constexpr int kFftThreads = 256;
 
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 
-// In-place radix-2 decimation-in-time FFT over a[0..n) (input already bit-reversed).  tw[k] = exp(-2 pi i k / n).
-__device__ __forceinline__ void fft_shared(float2* a, int n, int log2n, bool inverse, const float2* __restrict__ tw) {
-  for (int s = 1; s <= log2n; ++s) {
-    const int half = 1 << (s - 1);
-    const int tstep = n >> s;
-    for (int j = threadIdx.x; j < (n >> 1); j += kFftThreads) {
-      const int k = j & (half - 1);
-      const int i0 = ((j >> (s - 1)) << s) + k;
-      const int i1 = i0 + half;
-      float2 w = __ldg(tw + k * tstep);
-      if (inverse) w.y = -w.y;
-      const float2 b = a[i1], u = a[i0];
-      const float2 t = make_float2(w.x * b.x - w.y * b.y, w.x * b.y + w.y * b.x);
-      a[i0] = make_float2(u.x + t.x, u.y + t.y);
-      a[i1] = make_float2(u.x - t.x, u.y - t.y);
+// Shared-memory index padding (in float2 elements): one pad per 8 and per 64 elements keeps the stride-8 first pass and the
+// bit-reversed scatter of the callers off each other's banks.  Every index into the work buffer goes through fpad().
+__host__ __device__ __forceinline__ int fpad(int i) { return i + (i >> 3) + (i >> 6); }
+
+__device__ __forceinline__ float2 fmulc(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <int E>
+__device__ __forceinline__ float2 fmul_root8(float2 z) {            // z * exp(-2 pi i E / 8)
+  constexpr float h = 0.70710678118654752440f;
+  if (E == 0) return z;
+  if (E == 1) return make_float2((z.x + z.y) * h, (z.y - z.x) * h);
+  if (E == 2) return make_float2(z.y, -z.x);
+  return make_float2((z.y - z.x) * h, -(z.x + z.y) * h);
+}
+template <int E>
+__device__ __forceinline__ float2 fmul_root8c(float2 z) {           // z * exp(+2 pi i E / 8)
+  constexpr float h = 0.70710678118654752440f;
+  if (E == 0) return z;
+  if (E == 1) return make_float2((z.x - z.y) * h, (z.x + z.y) * h);
+  if (E == 2) return make_float2(-z.y, z.x);
+  return make_float2(-(z.x + z.y) * h, (z.x - z.y) * h);
+}
+
+// butterflies of merged stage U on local indices >= M (decimation in time; see fft_pass)
+template <int Q, bool INV, int U, int M>
+struct FftStage {
+  static __device__ __forceinline__ void run(float2 (&r)[1 << Q], const float2 (&base)[Q]) {
+    if constexpr (M < (1 << Q)) {
+      if constexpr ((M & (1 << U)) == 0) {
+        constexpr int K = M & ((1 << U) - 1);
+        constexpr int E = (K << (2 - U)) & 3;
+        const float2 w = INV ? fmul_root8c<E>(base[U]) : fmul_root8<E>(base[U]);
+        const float2 a = r[M], b = fmulc(r[M + (1 << U)], w);
+        r[M] = make_float2(a.x + b.x, a.y + b.y);
+        r[M + (1 << U)] = make_float2(a.x - b.x, a.y - b.y);
+      }
+      FftStage<Q, INV, U, M + 1>::run(r, base);
     }
-    __syncthreads();
   }
+};
+
+// Stages s .. s+Q-1 of the decimation-in-time transform in one pass: a radix-2^Q butterfly held in registers.  Stage
+// s+u needs exp(-+2 pi i (p + k 2^s) / 2^(s+u+1)) = base_u * (8th root)^(k << (2-u)), base_u = omega_(s+u+1)^p =
+// base_(u+1)^2: one twiddle load per group.
+template <int Q, bool INV>
+__device__ __forceinline__ void fft_pass(float2* a, int log2n, const float2* __restrict__ tw, int s) {
+  constexpr int R = 1 << Q;
+  const int hl = log2n - 1, lg = log2n - Q;
+  for (int j = threadIdx.x; j < (1 << lg); j += kFftThreads) {
+    const int p = j & ((1 << s) - 1);
+    const int i0 = ((j >> s) << (s + Q)) + p;
+    float2 r[R], base[Q];
+#pragma unroll
+    for (int m = 0; m < R; ++m) r[m] = a[fpad(i0 + (m << s))];
+    base[Q - 1] = __ldg(tw + (p << (hl - (s + Q - 1))));
+    if (INV) base[Q - 1].y = -base[Q - 1].y;
+#pragma unroll
+    for (int u = Q - 2; u >= 0; --u) base[u] = fmulc(base[u + 1], base[u + 1]);
+    FftStage<Q, INV, 0, 0>::run(r, base);
+    if constexpr (Q > 1) FftStage<Q, INV, 1, 0>::run(r, base);
+    if constexpr (Q > 2) FftStage<Q, INV, 2, 0>::run(r, base);
+#pragma unroll
+    for (int m = 0; m < R; ++m) a[fpad(i0 + (m << s))] = r[m];
+  }
+  __syncthreads();
+}
+
+// In-place decimation-in-time FFT over the padded buffer a (input already bit-reversed).  tw[k] = exp(-2 pi i k / n).
+// Radix-8 passes while more than four stages remain, then radix-4 / radix-2 (a 1024-point transform: 8, 8, 4, 4).
+template <bool INV>
+__device__ __forceinline__ void fft_shared_dir(float2* a, int log2n, const float2* __restrict__ tw) {
+  int s = 0;
+  while (log2n - s > 4 || log2n - s == 3) { fft_pass<3, INV>(a, log2n, tw, s); s += 3; }
+  while (log2n - s >= 2) { fft_pass<2, INV>(a, log2n, tw, s); s += 2; }
+  if (log2n - s == 1) fft_pass<1, INV>(a, log2n, tw, s);
+}
+__device__ __forceinline__ void fft_shared(float2* a, int n, int log2n, bool inverse, const float2* __restrict__ tw) {
+  (void)n;
+  if (inverse) fft_shared_dir<true>(a, log2n, tw); else fft_shared_dir<false>(a, log2n, tw);
 }
 
 // ---------------------------------------------------------------------------------------------- STFT
@@ -56,7 +116,7 @@ hpss_stft_kernel(const float* __restrict__ x, float2* __restrict__ spec, long lo
     const float w = __ldg(window + i);
     const float va = (j >= 0 && j < t) ? xr[j] * w : 0.f;
     const float vb = (two && j2 >= 0 && j2 < t) ? xr[j2] * w : 0.f;
-    fft_buf[bitrev((unsigned)i, log2n)] = make_float2(va, vb);
+    fft_buf[fpad(bitrev((unsigned)i, log2n))] = make_float2(va, vb);
   }
   __syncthreads();
   fft_shared(fft_buf, n_fft, log2n, false, tw);
@@ -64,7 +124,7 @@ hpss_stft_kernel(const float* __restrict__ x, float2* __restrict__ spec, long lo
   float2* out_a = spec + ((long long)row * frames + frame) * bins;
   float2* out_b = out_a + bins;
   for (int k = threadIdx.x; k < bins; k += kFftThreads) {
-    const float2 z = fft_buf[k], zc = fft_buf[(n_fft - k) & (n_fft - 1)];     // Z[k], Z[N-k] (N-0 -> 0)
+    const float2 z = fft_buf[fpad(k)], zc = fft_buf[fpad((n_fft - k) & (n_fft - 1))];     // Z[k], Z[N-k] (N-0 -> 0)
     out_a[k] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
     if (two) out_b[k] = make_float2(0.5f * (z.y + zc.y), 0.5f * (zc.x - z.x));
   }
@@ -276,44 +336,63 @@ __device__ __forceinline__ float softmask2(float x, float ref, bool split_zeros)
   return m / (m + r);
 }
 
+// A CTA transforms kIstftGroup consecutive frames of one row and overlap-adds them in shared memory first: with n_fft / hop
+// = 16 or 32 overlapping frames per sample, one global atomic per sample and FRAME was the bound of this kernel; now it is
+// one per sample and GROUP ((group - 1) hop + n_fft atomics instead of group * n_fft).
+constexpr int kIstftGroup = 16;                     // at most; fewer when (group - 1) hop + n_fft would not fit
 __global__ void __launch_bounds__(kFftThreads)
 hpss_istft_kernel(const float2* __restrict__ spec, const float* __restrict__ harm, const float* __restrict__ perc,
                   float* __restrict__ acc, int n_fft, int log2n, int hop, int frames, long long acc_len,
-                  float margin_h, float margin_p, const float* __restrict__ window, const float2* __restrict__ tw) {
-  extern __shared__ float2 fft_buf[];                            // [n_fft] work + [bins] frame spectrum + 2*[bins] masks
+                  float margin_h, float margin_p, const float* __restrict__ window, const float2* __restrict__ tw, int group) {
+  extern __shared__ float2 fft_buf[];            // [n_fft] work + [bins] frame spectrum + 2*[bins] masks + 2*[span] overlap-add
   const int bins = n_fft / 2 + 1;
-  float2* sp = fft_buf + n_fft;
+  float2* sp = fft_buf + fpad(n_fft);
   float* mh = reinterpret_cast<float*>(sp + bins);
   float* mp = mh + bins;
-  const int frame = blockIdx.x;
+  const int span = (group - 1) * hop + n_fft;
+  float* oh = mp + bins;
+  float* op = oh + span;
+  const int frame0 = blockIdx.x * group;
+  const int nfr = min(group, frames - frame0);
   const long long row = blockIdx.y;
-  const long long off = ((long long)row * frames + frame) * bins;
   const bool split = (margin_h == 1.f && margin_p == 1.f);
-  for (int k = threadIdx.x; k < bins; k += kFftThreads) {
-    sp[k] = spec[off + k];
-    const float h = harm[off + k], p = perc[off + k];
-    mh[k] = softmask2(h, p * margin_h, split);
-    mp[k] = softmask2(p, h * margin_p, split);
-  }
-  __syncthreads();
-  // ONE inverse FFT per frame: H and P are spectra of real signals, so ifft(H + i P) = h + i p (h, p real).  The
-  // residual needs no transform at all: istft is linear and istft(stft(x)) = x, hence r = x - h - p (finish kernel).
   const float scale = 1.f / (float)n_fft;
-  for (int k = threadIdx.x; k < bins; k += kFftThreads) {
-    const float2 sv = sp[k];
-    float2 hv = make_float2(sv.x * mh[k], sv.y * mh[k]), pv = make_float2(sv.x * mp[k], sv.y * mp[k]);
-    if (k == 0 || k == n_fft / 2) { hv.y = 0.f; pv.y = 0.f; }       // irfft ignores the imaginary part of DC / Nyquist
-    fft_buf[bitrev((unsigned)k, log2n)] = make_float2(hv.x - pv.y, hv.y + pv.x);
-    if (k > 0 && k < n_fft / 2) fft_buf[bitrev((unsigned)(n_fft - k), log2n)] = make_float2(hv.x + pv.y, pv.x - hv.y);
+  for (int i = threadIdx.x; i < 2 * span; i += kFftThreads) oh[i] = 0.f;
+  for (int f = 0; f < nfr; ++f) {
+    const long long off = ((long long)row * frames + frame0 + f) * bins;
+    for (int k = threadIdx.x; k < bins; k += kFftThreads) {
+      sp[k] = spec[off + k];
+      const float h = harm[off + k], p = perc[off + k];
+      mh[k] = softmask2(h, p * margin_h, split);
+      mp[k] = softmask2(p, h * margin_p, split);
+    }
+    __syncthreads();
+    // ONE inverse FFT per frame: H and P are spectra of real signals, so ifft(H + i P) = h + i p (h, p real).  The
+    // residual needs no transform at all: istft is linear and istft(stft(x)) = x, hence r = x - h - p (finish kernel).
+    for (int k = threadIdx.x; k < bins; k += kFftThreads) {
+      const float2 sv = sp[k];
+      float2 hv = make_float2(sv.x * mh[k], sv.y * mh[k]), pv = make_float2(sv.x * mp[k], sv.y * mp[k]);
+      if (k == 0 || k == n_fft / 2) { hv.y = 0.f; pv.y = 0.f; }       // irfft ignores the imaginary part of DC / Nyquist
+      fft_buf[fpad(bitrev((unsigned)k, log2n))] = make_float2(hv.x - pv.y, hv.y + pv.x);
+      if (k > 0 && k < n_fft / 2) fft_buf[fpad(bitrev((unsigned)(n_fft - k), log2n))] = make_float2(hv.x + pv.y, pv.x - hv.y);
+    }
+    __syncthreads();
+    fft_shared(fft_buf, n_fft, log2n, true, tw);
+    // frames are added one after the other (barriers above separate them), each thread on its own samples of the frame
+    for (int i = threadIdx.x; i < n_fft; i += kFftThreads) {
+      const float w = scale * __ldg(window + i);
+      const float2 v = fft_buf[fpad(i)];
+      oh[f * hop + i] += v.x * w;
+      op[f * hop + i] += v.y * w;
+    }
   }
   __syncthreads();
-  fft_shared(fft_buf, n_fft, log2n, true, tw);
-  float* dst_h = acc + ((long long)row * 3 + 0) * acc_len + (long long)frame * hop;
-  float* dst_p = acc + ((long long)row * 3 + 1) * acc_len + (long long)frame * hop;
-  for (int i = threadIdx.x; i < n_fft; i += kFftThreads) {
-    const float w = scale * __ldg(window + i);
-    atomicAdd(dst_h + i, fft_buf[i].x * w);
-    atomicAdd(dst_p + i, fft_buf[i].y * w);
+  const int used = (nfr - 1) * hop + n_fft;
+  float* dst_h = acc + ((long long)row * 3 + 0) * acc_len + (long long)frame0 * hop;
+  float* dst_p = acc + ((long long)row * 3 + 1) * acc_len + (long long)frame0 * hop;
+  for (int i = threadIdx.x; i < used; i += kFftThreads) {
+    atomicAdd(dst_h + i, oh[i]);
+    atomicAdd(dst_p + i, op[i]);
   }
 }
 
@@ -434,7 +513,7 @@ extern "C" int mpcg_hpss_stft_f32(const float* x, float* spec, int64_t rows, int
   if (rows == 0) return MPCG_OK;
   if (!x || !spec || !window || !twiddle) return MPCG_EINVAL;
   if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
-  const size_t smem = (size_t)n_fft * sizeof(float2);
+  const size_t smem = (size_t)fpad(n_fft) * sizeof(float2);
   cudaError_t e = cudaFuncSetAttribute(hpss_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)((frames + 1) / 2), (unsigned)rows);       // two frames per CTA (one packed complex FFT)
@@ -498,15 +577,19 @@ extern "C" int mpcg_hpss_istft_f32(const float* spec, const float* harm, const f
   if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
   const int bins = n_fft / 2 + 1;
   const long long acc_len = (long long)n_fft + (long long)hop * (frames - 1);
-  const size_t smem = (size_t)n_fft * sizeof(float2) + (size_t)bins * (sizeof(float2) + 2 * sizeof(float));
+  const size_t fixed = (size_t)fpad(n_fft) * sizeof(float2) + (size_t)bins * (sizeof(float2) + 2 * sizeof(float)) +
+                       2 * (size_t)n_fft * sizeof(float);
+  int group = kIstftGroup;
+  while (group > 1 && fixed + 2 * (size_t)(group - 1) * hop * sizeof(float) > 160 * 1024) --group;
+  const size_t smem = fixed + 2 * (size_t)(group - 1) * hop * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(hpss_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)rows * 3 * acc_len, (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((unsigned)frames, (unsigned)rows);
+  dim3 grid((unsigned)((frames + group - 1) / group), (unsigned)rows);
   hpss_istft_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream>>>((const float2*)spec, harm, perc, acc, n_fft, l2,
                                                                      hop, (int)frames, acc_len, margin_h, margin_p,
-                                                                     window, (const float2*)twiddle);
+                                                                     window, (const float2*)twiddle, group);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }
