@@ -243,12 +243,14 @@ int mpcg_row_normalise_f32(const float* x, float* y, double* stats, int64_t rows
                            double hi, int flags, void* stream);
 
 /* Tensor-core tier of the same transform (tcgen05, split-fp16 operands, fp32 accumulation in TMEM) for configurations
- * with n_fft = Q * hop (Q <= 8), win_length == n_fft and at most 126 weighted bins.  The GEMM is the rectangular-window
+ * with n_fft = Q * hop (Q <= 8), win_length == n_fft and at most 126 weighted bins per call.  The GEMM is the rectangular-window
  * partial DFT of every hop row; frames are assembled by a Q-term twiddle sum and the Hann window is applied in the
  * frequency domain.  basis_f16: device, [2 (hi, lo)][ncols * hop] fp16 in the canonical K-major core-matrix order
  * (byte offset of element (n, j): (n>>3)*hop*16 + (j>>3)*128 + (n&7)*16 + (j&7)*2), columns = cos then -sin of bins
  * k0-1 .. k0+nbins, zero padded to ncols (multiple of 16).  twq: device [Q][2] = cos, sin of -2 pi m / Q.
- * Returns MPCG_EUNSUPPORTED when the shape does not fit; the caller then uses mpcg_mel_f32. */
+ * Returns MPCG_EUNSUPPORTED when the shape does not fit; the caller then uses mpcg_mel_f32.
+ * log_map: bit 0 = fuse log_mel's dB map, bit 1 = add to the values already in `out` (presets with more weighted bins than
+ * one tile holds run as several calls over consecutive bin ranges; the last one applies the map). */
 int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int k0, int nbins, int ncols,
                     const void* basis_f16, const float* fb, const float* twq, float inv_norm, int n_mels, int64_t frames,
                     int log_map, void* stream);

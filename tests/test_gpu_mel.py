@@ -119,3 +119,25 @@ def test_tensor_core_tier(pkg, golden):
     short = torch.randn(3, 1000, device="cuda")                      # fewer frames than one tile, odd length
     assert float((pkg.log_mel(short, tr_tc) - pkg.log_mel(short, pkg.MelConfig(**kw).build())).abs().max()) < 1e-4
     assert pkg.MelConfig(**PRESETS["wg4k"]).build(fast=True).backend == "fma fp32"      # win < n_fft: not eligible
+
+
+def test_tensor_core_tier_many_bins(pkg, golden):
+    """The reference's own 4 kHz generator preset (n_fft 1024, hop 256, 127 weighted bins) needs more GEMM columns than
+    one tcgen05 tile holds: it runs as several launches over consecutive bin ranges whose partial mel sums accumulate.
+    Golden vectors of the reference, agreement with the fp64 tier on noise, and the generator crop shape."""
+    kw = PRESETS["dw4k"]
+    tr_tc = pkg.MelConfig(**kw).build(fast=True)
+    assert tr_tc.backend.startswith("tcgen05") and len(tr_tc._tc["passes"]) > 1
+    assert sum(pl["nbins"] for pl in tr_tc._tc["passes"]) == tr_tc.nbins == 127
+    g = golden("mel_presets.npz")
+    x = torch.from_numpy(g["x"]).cuda()
+    assert rel_err(tr_tc(x).cpu().numpy(), g["dw4k_mel"]) < 1e-5
+    assert np.abs(pkg.log_mel(x, tr_tc).cpu().numpy() - g["dw4k_logmel64"]).max() < 1e-5
+    rng = torch.Generator(device="cuda").manual_seed(1)
+    big = torch.randn(512, 24576, device="cuda", generator=rng)
+    a = pkg.log_mel(big, tr_tc)
+    b = pkg.log_mel(big, pkg.MelConfig(**kw).build())
+    assert a.shape == b.shape == (512, 80, 97)
+    d = (a - b).abs()
+    assert float(d.max()) < 1e-4 and float((d > 1e-5).float().mean()) < 1e-3
+    assert rel_err(tr_tc(big).cpu().numpy(), pkg.MelConfig(**kw).build()(big).cpu().numpy()) < 1e-5

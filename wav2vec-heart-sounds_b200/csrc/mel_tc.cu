@@ -339,7 +339,8 @@ mel_tc_kernel(const MelTcArgs a) {
         for (int m = gi; m < a.n_mels; m += ngrp) {
           float acc = 0.f;
           for (int k = mk0[m]; k <= mk1[m]; ++k) acc = fmaf(fbs[k * nm4 + m], mg[k], acc);
-          op[(long long)m * a.frames] = a.log_map ? mel_log_map(acc) : acc;
+          if (a.log_map & 2) acc += op[(long long)m * a.frames];   // partial sums of the earlier bin ranges
+          op[(long long)m * a.frames] = (a.log_map & 1) ? mel_log_map(acc) : acc;
         }
       }
     }

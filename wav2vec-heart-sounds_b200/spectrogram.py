@@ -54,40 +54,55 @@ class MelTransform:
         self._basis_host = torch.from_numpy(basis.astype(np.float32) if self.fast else basis)
         self._fb_host = fb[k0:k1].contiguous()
         self._dev = {}
-        # tensor-core tier (fast only): n_fft = Q * hop, full-length window, few enough weighted bins
+        # tensor-core tier (fast only): n_fft = Q * hop and a full-length window.  One launch takes as many weighted bins
+        # as its GEMM tile and shared memory hold (two window-neighbour bins ride along); presets with more bins -- the
+        # reference's own 4 kHz generator preset has 127 -- run as several launches over consecutive bin ranges whose
+        # partial mel sums accumulate in the output, the dB map applied by the last one.
         self._tc = None
         q = self.n_fft // self.hop_length if self.hop_length else 0
-        ncols = (2 * (self.nbins + 2) + 15) // 16 * 16
         if (self.fast and self.win_length == self.n_fft and q * self.hop_length == self.n_fft and 1 <= q <= 8
-                and self.hop_length % 16 == 0 and ncols <= 256
-                and (2 * 128 * self.hop_length * 2 + 2 * ncols * self.hop_length * 2 + 256
-                     + 1024 + self.nbins * ((self.n_mels + 3) // 4 * 4) * 4 + (self.nbins + 2) * q * 8 + 8 * self.n_mels) <= 227 * 1024
-                and (128 * (ncols + 1) * 4 + 128 * ((self.nbins + 1) | 1) * 4 + 2 * 128 * ((self.nbins + 2) | 1) * 4
-                     <= 2 * 128 * self.hop_length * 2)):
-            hop, nb2 = self.hop_length, self.nbins + 2
-            j = np.arange(hop, dtype=np.float64)[None, :]
-            kk = (k0 - 1 + np.arange(nb2, dtype=np.float64))[:, None]
-            ang = 2.0 * np.pi * ((kk * j) % self.n_fft) / self.n_fft
-            e = np.zeros((ncols, hop), dtype=np.float64)
-            e[:nb2] = np.cos(ang)
-            e[nb2:2 * nb2] = -np.sin(ang)
-            hi = e.astype(np.float16)
-            lo = (e - hi.astype(np.float64)).astype(np.float16)
-            packed = np.zeros((2, ncols * hop), dtype=np.float16)
-            n_idx, j_idx = np.meshgrid(np.arange(ncols), np.arange(hop), indexing="ij")
-            off = ((n_idx >> 3) * hop * 16 + (j_idx >> 3) * 128 + (n_idx & 7) * 16 + (j_idx & 7) * 2) // 2
-            packed[0, off.ravel()] = hi.ravel()
-            packed[1, off.ravel()] = lo.ravel()
-            m = np.arange(q, dtype=np.float64)
-            twq = np.stack([np.cos(-2 * np.pi * m / q), np.sin(-2 * np.pi * m / q)], axis=1).astype(np.float32)
-            wf = torch.hann_window(self.win_length, periodic=True).double().numpy()
-            self._tc = dict(q=q, ncols=ncols, basis=torch.from_numpy(packed), twq=torch.from_numpy(twq),
-                            inv_norm=float(1.0 / math.sqrt(float(np.sum(wf ** 2)))))
+                and self.hop_length % 16 == 0):
+            for parts in range(1, 9):
+                cuts = [k0 + (self.nbins * i) // parts for i in range(parts + 1)]
+                plans = [self._tc_plan(a, b - a, q, fb) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+                if all(pl is not None for pl in plans):
+                    m = np.arange(q, dtype=np.float64)
+                    twq = np.stack([np.cos(-2 * np.pi * m / q), np.sin(-2 * np.pi * m / q)], axis=1).astype(np.float32)
+                    self._tc = dict(q=q, passes=plans, twq=torch.from_numpy(twq), inv_norm=float(1.0 / norm))
+                    break
+
+    def _tc_plan(self, k0, nbins, q, fb):
+        """Tables of one tensor-core launch over bins [k0, k0 + nbins), or None when the tile does not fit."""
+        hop = self.hop_length
+        ncols = (2 * (nbins + 2) + 15) // 16 * 16
+        fits = (ncols <= 256
+                and (2 * 128 * hop * 2 + 2 * ncols * hop * 2 + 256 + 1024 + nbins * ((self.n_mels + 3) // 4 * 4) * 4
+                     + (nbins + 2) * q * 8 + 8 * self.n_mels) <= 227 * 1024
+                and (128 * (ncols + 1) * 4 + 128 * ((nbins + 1) | 1) * 4 + 2 * 128 * ((nbins + 2) | 1) * 4 <= 2 * 128 * hop * 2))
+        if not fits:
+            return None
+        nb2 = nbins + 2
+        j = np.arange(hop, dtype=np.float64)[None, :]
+        kk = (k0 - 1 + np.arange(nb2, dtype=np.float64))[:, None]
+        ang = 2.0 * np.pi * ((kk * j) % self.n_fft) / self.n_fft
+        e = np.zeros((ncols, hop), dtype=np.float64)
+        e[:nb2] = np.cos(ang)
+        e[nb2:2 * nb2] = -np.sin(ang)
+        hi = e.astype(np.float16)
+        lo = (e - hi.astype(np.float64)).astype(np.float16)
+        packed = np.zeros((2, ncols * hop), dtype=np.float16)
+        n_idx, j_idx = np.meshgrid(np.arange(ncols), np.arange(hop), indexing="ij")
+        off = ((n_idx >> 3) * hop * 16 + (j_idx >> 3) * 128 + (n_idx & 7) * 16 + (j_idx & 7) * 2) // 2
+        packed[0, off.ravel()] = hi.ravel()
+        packed[1, off.ravel()] = lo.ravel()
+        return dict(k0=int(k0), nbins=int(nbins), ncols=int(ncols), basis=torch.from_numpy(packed),
+                    fb=fb[k0:k0 + nbins].contiguous())
 
     def _tables(self, device):
         key = str(device)
         if key not in self._dev:
-            tc = None if self._tc is None else (self._tc["basis"].to(device), self._tc["twq"].to(device))
+            tc = None if self._tc is None else ([(pl["basis"].to(device), pl["fb"].to(device)) for pl in self._tc["passes"]],
+                                                self._tc["twq"].to(device))
             self._dev[key] = (self._basis_host.to(device), self._fb_host.to(device), tc)
         return self._dev[key]
 
@@ -108,10 +123,16 @@ class MelTransform:
         basis, fb, tc = self._tables(x.device)
         out = torch.empty((rows.shape[0], self.n_mels, frames), device=x.device, dtype=torch.float32)
         if tc is not None:
-            rc = _lib.lib().mpcg_mel_tc_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
-                                            self.k0, self.nbins, self._tc["ncols"], tc[0].data_ptr(), fb.data_ptr(),
-                                            tc[1].data_ptr(), self._tc["inv_norm"], self.n_mels, frames,
-                                            1 if log_map else 0, _lib.stream_ptr(x))
+            passes, rc = self._tc["passes"], 0
+            for i, (pl, (basis_tc, fb_tc)) in enumerate(zip(passes, tc[0])):
+                # flags: bit 0 = dB map (last launch only), bit 1 = add to what the earlier launches left in `out`
+                flags = (1 if (log_map and i == len(passes) - 1) else 0) | (2 if i else 0)
+                rc = _lib.lib().mpcg_mel_tc_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
+                                                pl["k0"], pl["nbins"], pl["ncols"], basis_tc.data_ptr(), fb_tc.data_ptr(),
+                                                tc[1].data_ptr(), self._tc["inv_norm"], self.n_mels, frames, flags,
+                                                _lib.stream_ptr(x))
+                if rc != 0:
+                    break
             if rc != _lib.EUNSUPPORTED:
                 _lib.check(rc, "mel (tensor cores)")
                 return out.reshape(*lead, self.n_mels, frames)
