@@ -80,6 +80,22 @@ __device__ __forceinline__ void rn_coeffs(int mode, int flags, double lo, double
   s = (hi - lo) / span;
 }
 
+// fn(x[i], c) for every i < t, the 16-byte aligned middle of the row as float4; c in 0..3 is the sample's slot in its
+// vector (a compile-time constant at each call site: callers keep one accumulator per slot to break the fp64 add chain)
+template <typename F>
+__device__ __forceinline__ void rn_sweep(const float* __restrict__ xr, long long t, int tid, int stride, F fn) {
+  const int head = (int)min((long long)(((16u - ((uintptr_t)xr & 15u)) & 15u) >> 2), t);
+  if (tid < head) fn(xr[tid], 0);
+  const long long nvec = (t - head) >> 2;
+  const float4* xv = reinterpret_cast<const float4*>(xr + head);
+  for (long long i = tid; i < nvec; i += stride) {
+    const float4 q = xv[i];
+    fn(q.x, 0); fn(q.y, 1); fn(q.z, 2); fn(q.w, 3);
+  }
+  const long long done = head + (nvec << 2);
+  if (tid < t - done) fn(xr[done + tid], 0);
+}
+
 __device__ __forceinline__ void rn_apply(const float* __restrict__ xr, float* __restrict__ yr, long long t, double a, double b,
                                          double s, bool isconst, int tid, int stride) {
   if (isconst) {
@@ -87,29 +103,46 @@ __device__ __forceinline__ void rn_apply(const float* __restrict__ xr, float* __
     for (long long i = tid; i < t; i += stride) yr[i] = c;
     return;
   }
-  for (long long i = tid; i < t; i += stride) yr[i] = (float)(a + ((double)xr[i] - b) * s);
+  auto map = [&](float v) { return (float)(a + ((double)v - b) * s); };
+  if ((((uintptr_t)xr ^ (uintptr_t)yr) & 15u) != 0) {
+    for (long long i = tid; i < t; i += stride) yr[i] = map(xr[i]);
+    return;
+  }
+  const int head = (int)min((long long)(((16u - ((uintptr_t)xr & 15u)) & 15u) >> 2), t);
+  if (tid < head) yr[tid] = map(xr[tid]);
+  const long long nvec = (t - head) >> 2;
+  const float4* xv = reinterpret_cast<const float4*>(xr + head);
+  float4* yv = reinterpret_cast<float4*>(yr + head);
+  for (long long i = tid; i < nvec; i += stride) {
+    float4 q = xv[i];
+    q.x = map(q.x); q.y = map(q.y); q.z = map(q.z); q.w = map(q.w);
+    st_stream4(yv + i, q);
+  }
+  const long long done = head + (nvec << 2);
+  if (tid < t - done) yr[done + tid] = map(xr[done + tid]);
 }
 
-__global__ void __launch_bounds__(kRnThreads)
+template <bool KPEAK>
+__global__ void __launch_bounds__(kRnThreads, KPEAK ? 1 : 2)
 row_normalise_kernel(const float* __restrict__ x, float* __restrict__ y, double* __restrict__ stats, long long t, int mode, int k,
                      double lo, double hi, int flags, int apply) {
   __shared__ RnShared sm;
   const int tid = threadIdx.x;
   const long long row = blockIdx.x;
   const float* xr = x + row * t;
-  const bool kpeak = mode == MPCG_RN_KPEAK;
+  constexpr bool kpeak = KPEAK;
   if (kpeak) {
     for (int i = tid; i < kRnBins; i += kRnThreads) { sm.hist_hi[i] = 0; sm.hist_lo[i] = 0; }
     __syncthreads();
   }
   // ---- sweep A
-  double s = 0.0;
+  double s4[4] = {0.0, 0.0, 0.0, 0.0};
   float mn = INFINITY, mx = -INFINITY;
-  for (long long i = tid; i < t; i += kRnThreads) {
-    const float v = xr[i];
-    s += (double)v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+  rn_sweep(xr, t, tid, kRnThreads, [&](float v, int c) {
+    s4[c] += (double)v; mn = fminf(mn, v); mx = fmaxf(mx, v);
     if (kpeak) atomicAdd(&sm.hist_hi[rn_key(v) >> 21], 1);
-  }
+  });
+  const double s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
   RnStats st;
   st.mean = block_sum<kRnThreads>(s, sm.dscr) / (double)t;
   st.mn = (double)block_min<kRnThreads>(mn, sm.fscr);
@@ -117,10 +150,10 @@ row_normalise_kernel(const float* __restrict__ x, float* __restrict__ y, double*
   st.sd = 0.0; st.hi_ref = st.mx; st.lo_ref = st.mn;
   if (mode == MPCG_RN_ZSCORE) {
     // ---- sweep B (z-score): population variance around the fp64 mean
-    double q = 0.0;
-    for (long long i = tid; i < t; i += kRnThreads) { const double d = (double)xr[i] - st.mean; q += d * d; }
-    st.sd = sqrt(block_sum<kRnThreads>(q, sm.dscr) / (double)t);
-  } else if (kpeak) {
+    double q4[4] = {0.0, 0.0, 0.0, 0.0};
+    rn_sweep(xr, t, tid, kRnThreads, [&](float v, int c) { const double d = (double)v - st.mean; q4[c] = fma(d, d, q4[c]); });
+    st.sd = sqrt(block_sum<kRnThreads>((q4[0] + q4[1]) + (q4[2] + q4[3]), sm.dscr) / (double)t);
+  } else if constexpr (KPEAK) {
     const long long kk = k < t ? k : t;
     __syncthreads();
     if (tid < 32) { rn_select(sm.hist_hi, kRnBins, kk, true, sm.sel); rn_select(sm.hist_hi, kRnBins, kk, false, sm.sel + 2); }
@@ -132,12 +165,11 @@ row_normalise_kernel(const float* __restrict__ x, float* __restrict__ y, double*
     __syncthreads();
     // ---- sweep B (k-peak)
     double s_hi = 0.0, s_lo = 0.0;
-    for (long long i = tid; i < t; i += kRnThreads) {
-      const float v = xr[i];
+    rn_sweep(xr, t, tid, kRnThreads, [&](float v, int) {
       const unsigned key = rn_key(v), p = key >> 21;
       if (p > b1_hi) s_hi += (double)v; else if (p == b1_hi) atomicAdd(&sm.hist_hi[(key >> 10) & 2047u], 1);
       if (p < b1_lo) s_lo += (double)v; else if (p == b1_lo) atomicAdd(&sm.hist_lo[(key >> 10) & 2047u], 1);
-    }
+    });
     __syncthreads();
     if (tid < 32) { rn_select(sm.hist_hi, kRnBins, need1_hi, true, sm.sel); rn_select(sm.hist_lo, kRnBins, need1_lo, false, sm.sel + 2); }
     __syncthreads();
@@ -147,12 +179,11 @@ row_normalise_kernel(const float* __restrict__ x, float* __restrict__ y, double*
     for (int i = tid; i < 1024; i += kRnThreads) { sm.hist_hi[i] = 0; sm.hist_lo[i] = 0; }
     __syncthreads();
     // ---- sweep C: inside the boundary bins of sweep A; beyond the 22-bit prefix -> sum, on it -> last 10 bits
-    for (long long i = tid; i < t; i += kRnThreads) {
-      const float v = xr[i];
+    rn_sweep(xr, t, tid, kRnThreads, [&](float v, int) {
       const unsigned key = rn_key(v), p = key >> 10;
       if ((p >> 11) == b1_hi) { if (p > p_hi) s_hi += (double)v; else if (p == p_hi) atomicAdd(&sm.hist_hi[key & 1023u], 1); }
       if ((p >> 11) == b1_lo) { if (p < p_lo) s_lo += (double)v; else if (p == p_lo) atomicAdd(&sm.hist_lo[key & 1023u], 1); }
-    }
+    });
     __syncthreads();
     if (tid < 32) { rn_select(sm.hist_hi, 1024, need2_hi, true, sm.sel); rn_select(sm.hist_lo, 1024, need2_lo, false, sm.sel + 2); }
     __syncthreads();
@@ -238,7 +269,10 @@ extern "C" int mpcg_row_normalise_f32(const float* x, float* y, double* stats, i
   if (!x || !y || (global && !stats)) return MPCG_EINVAL;
   if (rows > 0x7fffffffLL) return MPCG_ERANGE;
   cudaStream_t st = (cudaStream_t)stream;
-  row_normalise_kernel<<<(unsigned)rows, kRnThreads, 0, st>>>(x, y, stats, (long long)t, mode, k, lo, hi, flags, global ? 0 : 1);
+  if (mode == MPCG_RN_KPEAK)
+    row_normalise_kernel<true><<<(unsigned)rows, kRnThreads, 0, st>>>(x, y, stats, (long long)t, mode, k, lo, hi, flags, global ? 0 : 1);
+  else
+    row_normalise_kernel<false><<<(unsigned)rows, kRnThreads, 0, st>>>(x, y, stats, (long long)t, mode, k, lo, hi, flags, global ? 0 : 1);
   MPCG_LAUNCH_CHECK();
   if (global) {
     double* coef = stats + rows * 8;                                 // stats holds [rows + 1, 8] doubles in this scope
