@@ -116,3 +116,35 @@ def test_generator_conditioning_vs_golden(ds, golden):
         got = ds.condition_generator_batch(x, x, fs, tr, crop // 256, 256)
         assert np.abs(got["ref_audio"].cpu().numpy() - g[f"{tag}_y"]).max() < TOL
         assert np.abs(got["chirp_wave"].cpu().numpy() - g[f"{tag}_chirp"]).max() < 2e-5
+
+
+def test_fragment_dataset_augmented_copies(ds):
+    """FragmentTensorDataset with augmented copies (reference datasets/fragments.py:47-83): originals come back
+    untouched, augmented items are re-normalised rows of the fused chain (PCG column only for multichannel fragments),
+    a whole batch of indices costs one launch, and device_augment_fn plugs into the reference's per-item hook."""
+    import wav2vec_heart_sounds_b200 as pkg
+    recs = _records(True)[:3]
+    fb = ds.build_fragments_batched(recs, fs_out=4125, window=pkg.WindowSpec(2.0), ecg=True)
+    data = ds.FragmentTensorDataset(fb, augment_num=2)
+    assert len(data) > len(fb) and data.labels.count(0) > 0
+    torch.manual_seed(1); np.random.seed(1)
+    idx = list(range(len(data)))
+    got = data.get_batch(idx)
+    assert got["waveform"].shape == (len(data), 8250, 2) and len(got["patient"]) == len(data)
+    aug = data._aug
+    src = fb.windows[data._frag.to(fb.windows.device)]
+    assert torch.equal(got["waveform"][~aug.cuda()], src[~aug.cuda()])                    # originals
+    a = got["waveform"][aug.cuda()]
+    assert torch.equal(a[:, :, 1], src[aug.cuda()][:, :, 1])                               # ECG column passes through
+    assert torch.isfinite(a).all() and float(a[:, :, 0].abs().max()) <= 1.0
+    assert float((a[:, :, 0].amax(dim=1) - a[:, :, 0].amin(dim=1)).min()) > 0.5            # re-normalised rows
+    assert not torch.equal(a[:, :, 0], src[aug.cuda()][:, :, 0])
+    item = data[int(torch.nonzero(aug)[0])]
+    assert item["waveform"].shape == (8250, 2) and isinstance(item["label"], int)
+    mono = ds.FragmentTensorDataset(fb, channel=0, augment_num=1, balance=False)
+    assert mono.get_batch([0, 1, 2])["waveform"].shape == (3, 8250)
+    fn = ds.device_augment_fn()
+    w = fb.windows[0].cpu().numpy()
+    out = fn(w, 4125)
+    assert out.shape == w.shape and out.dtype == np.float32 and np.array_equal(out[:, 1], w[:, 1])
+    assert fn(w[:, 0], 4125).shape == (8250,)

@@ -141,3 +141,24 @@ def test_eq_band_design_closed_form_matches_scipy():
         got, want = design.eq_band_sos(fs, bands), design.eq_band_sos_scipy(fs, bands)
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= 4.5e-16 * max(1.0, np.abs(want).max())
+
+
+def test_fragment_dataset_item_list_matches_reference_rule():
+    """FragmentTensorDataset lists every fragment once followed by its augmented copies, balanced like the reference's
+    FragmentDataset (datasets/fragments.py:47-56); checked against the live reference when it is mounted."""
+    import torch
+    from wav2vec_heart_sounds_b200.datasets import FragmentBatch, FragmentTensorDataset
+    labels = [0, 0, 0, 0, 0, 1, 1, 0, 1, 0]
+    fb = FragmentBatch(torch.zeros(len(labels), 8), torch.tensor(labels), torch.arange(len(labels)), [f"p{i}" for i in range(len(labels))], 1000)
+    ds = FragmentTensorDataset(fb, augment_num=3)
+    # 7 of class 0, 3 of class 1: copies 3 and round(3 * 7 / 3) = 7
+    assert len(ds) == 7 * (1 + 3) + 3 * (1 + 7)
+    assert ds.labels[:4] == [0, 0, 0, 0] and ds._aug[:5].tolist() == [False, True, True, True, False]
+    assert len(FragmentTensorDataset(fb, augment_num=3, balance=False)) == 10 * 4
+    assert len(FragmentTensorDataset(fb)) == 10
+    from conftest import reference_modules
+    if reference_modules() is not None:
+        from mpcg_wav2vec.datasets.fragments import Fragment, FragmentDataset
+        ref = FragmentDataset([Fragment(np.zeros(8), lab, f"p{i}") for i, lab in enumerate(labels)], 1000, augment_num=3,
+                              augment_fn=lambda w, fs: w)
+        assert ref.labels == ds.labels and [a for _, a in ref._items] == ds._aug.tolist()

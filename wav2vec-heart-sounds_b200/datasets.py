@@ -107,24 +107,78 @@ def _numpy_out_len(t_in: int, fs_in: float, fs_out: float) -> int:
 
 
 class FragmentTensorDataset(torch.utils.data.Dataset):
-    """The reference's ``FragmentDataset`` items (``datasets/fragments.py:62-83``: ``waveform``, ``label``, ``patient``)
-    served from a :class:`FragmentBatch`; ``channel`` selects one column of multichannel fragments (-1 keeps all)."""
+    """The reference's ``FragmentDataset`` (``datasets/fragments.py:30-83``) served from a :class:`FragmentBatch`: the same
+    item dictionaries (``waveform``, ``label``, ``patient``), the same list of items -- every fragment once, followed by
+    its augmented copies, ``int(round(augment_num * max_count / count[label]))`` of them when ``balance`` is on
+    (``fragments.py:47-56``) -- and augmentation applied lazily, so every epoch sees fresh draws.  ``channel`` selects
+    one column of multichannel fragments (-1 keeps all).  Augmented items run the fused ``augment_pcg_batch`` chain on
+    the PCG column; :meth:`get_batch` does that for a whole batch of indices in ONE launch."""
 
-    def __init__(self, batch: FragmentBatch, channel: int = -1):
+    def __init__(self, batch: FragmentBatch, channel: int = -1, *, augment_num: int = 0, cfg=None, balance: bool = True,
+                 pcg_channel: int = 0, noise: str | None = "philox"):
         self.batch, self.channel = batch, channel
+        self.cfg, self.pcg_channel, self.noise = cfg, pcg_channel, noise
+        labels = batch.labels.tolist()
+        counts: dict = {}
+        for lab in labels:
+            counts[lab] = counts.get(lab, 0) + 1
+        top = max(counts.values()) if counts else 1
+        frag, aug = [], []
+        for i, lab in enumerate(labels):
+            copies = 0
+            if augment_num > 0:
+                copies = int(round(augment_num * top / counts[lab])) if balance else augment_num
+            frag.extend([i] * (1 + copies))
+            aug.extend([False] + [True] * copies)
+        self._frag = torch.tensor(frag, dtype=torch.int64)
+        self._aug = torch.tensor(aug, dtype=torch.bool)
 
     @property
     def labels(self) -> list:
-        return self.batch.labels.tolist()
+        return self.batch.labels[self._frag.to(self.batch.labels.device)].tolist()
 
     def __len__(self) -> int:
-        return len(self.batch)
+        return int(self._frag.numel())
+
+    def get_batch(self, indices) -> dict:
+        """Items ``indices`` as one batch: ``waveform`` ``[B, win]`` or ``[B, win, C]`` on the fragments' device, the
+        augmented ones through one fused launch."""
+        idx = torch.as_tensor(indices, dtype=torch.int64)
+        frag = self._frag[idx]
+        dev = self.batch.windows.device
+        w = self.batch.windows[frag.to(dev)].clone()
+        todo = torch.nonzero(self._aug[idx]).flatten().to(dev)
+        if todo.numel():
+            if w.dim() == 2:
+                w[todo] = torchaug.augment_pcg_batch(w[todo].contiguous(), self.batch.fs, self.cfg, noise=self.noise)
+            else:
+                col = w[todo][:, :, self.pcg_channel].contiguous()
+                w[todo, :, self.pcg_channel] = torchaug.augment_pcg_batch(col, self.batch.fs, self.cfg, noise=self.noise)
+        if w.dim() == 3 and self.channel != -1:
+            w = w[:, :, self.channel]
+        rec = self.batch.record[frag.to(self.batch.record.device)].tolist()
+        return {"waveform": w, "label": self.batch.labels[frag.to(self.batch.labels.device)],
+                "patient": [self.batch.patients[r] for r in rec]}
 
     def __getitem__(self, idx: int) -> dict:
-        w = self.batch.windows[idx]
-        if w.dim() == 2 and self.channel != -1:
-            w = w[:, self.channel]
-        return {"waveform": w, "label": int(self.batch.labels[idx]), "patient": self.batch.patients[int(self.batch.record[idx])]}
+        one = self.get_batch([int(idx)])
+        return {"waveform": one["waveform"][0], "label": int(one["label"][0]), "patient": one["patient"][0]}
+
+
+def device_augment_fn(cfg=None, *, pcg_channel: int = 0, noise: str | None = "philox", device="cuda"):
+    """An ``augment_fn`` for the reference's own ``FragmentDataset`` (``datasets/fragments.py:19,36,68-72``:
+    ``Callable[[np.ndarray, int], np.ndarray]``): one window ``[T]`` or ``[T, C]`` goes to the device, its PCG column
+    through the fused chain, and comes back as float32 -- the drop-in for callers that keep the per-item dataset."""
+
+    def fn(wave: np.ndarray, fs: int) -> np.ndarray:
+        x = torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32)).to(device)
+        if x.dim() == 1:
+            return torchaug.augment_pcg_batch(x[None], int(fs), cfg, noise=noise)[0].cpu().numpy()
+        out = x.clone()
+        out[:, pcg_channel] = torchaug.augment_pcg_batch(x[:, pcg_channel][None].contiguous(), int(fs), cfg, noise=noise)[0]
+        return out.cpu().numpy()
+
+    return fn
 
 
 def device_batch_transform(fs: int, cfg=None, *, pcg_channel: int = 0, noise: str | None = "philox"):
