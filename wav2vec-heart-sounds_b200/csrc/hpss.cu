@@ -205,12 +205,12 @@ constexpr int kMedChunk = 32;
 template <int K>
 __global__ void __launch_bounds__(kMedThreads)
 hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k) {
-  extern __shared__ float med_sorted[];                          // sorted [k][T] | ring [k][T] | in [32][T+1] | out [32][T+1]
+  extern __shared__ float med_sorted[];                          // ring [k][T] | in [32][T+1] | out [32][T+1] (first-window sort inside out)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* sw = med_sorted + tid;
-  float* ring = med_sorted + k * kMedThreads + tid;
-  float* tin = med_sorted + 2 * k * kMedThreads;
+  float* ring = med_sorted + tid;
+  float* tin = med_sorted + k * kMedThreads;
   float* tout = tin + kMedChunk * (kMedThreads + 1);
+  float* sw = tout + tid;                                        // first-window scratch: dead before tout is written
   const long long row = blockIdx.y;
   const int f0 = blockIdx.x * kMedThreads;
   const float2* src = spec + ((long long)row * frames + f0) * bins;
@@ -284,11 +284,13 @@ hpss_median_reg_kernel(const float2* __restrict__ spec, float* __restrict__ out,
   }
   ln.dst[0] = a[K / 2];
   int slot = 0;                                                  // ring position of the oldest sample
-  float ahead = ln.mag(k - left);                                // the entering sample, fetched one step ahead
+  // the entering samples are fetched three steps ahead: a step is ~130 instructions, a miss in L2 several hundred cycles
+  float ahead0 = ln.mag(k - left), ahead1 = ln.mag(k - left + 1), ahead2 = ln.mag(k - left + 2);
   for (int i = 1; i < ln.len; ++i) {
     const float gone = ring[slot * kMedThreads];
-    const float come = ahead;                                    // index i - left + k - 1
-    ahead = ln.mag(i - left + k);
+    const float come = ahead0;                                   // index i - left + k - 1
+    ahead0 = ahead1; ahead1 = ahead2;
+    ahead2 = ln.mag(i - left + k + 2);
     ring[slot * kMedThreads] = come;
     slot = slot + 1 == k ? 0 : slot + 1;
     med_slide<K>(a, gone, come);
@@ -540,7 +542,7 @@ extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows,
   }
   cudaStream_t st = (cudaStream_t)stream;
   const float2* sp = (const float2*)spec;
-  const size_t smem_f = smem + 2 * (size_t)kMedChunk * (kMedThreads + 1) * sizeof(float);
+  const size_t smem_f = (size_t)k * kMedThreads * sizeof(float) + 2 * (size_t)kMedChunk * (kMedThreads + 1) * sizeof(float);
 #define MED_REG(KK)                                                                                                  \
   if (along_time) {                                                                                                  \
     hpss_median_reg_kernel<KK><<<grid, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, 1);                      \
