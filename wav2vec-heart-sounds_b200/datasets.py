@@ -223,7 +223,10 @@ def condition_generator_batch(reference: torch.Tensor, conditioning: torch.Tenso
         from . import heart_cycles, torchproc
         if len(cycles) != b:
             raise ValueError("cycles needs one entry per row")
-        plan = [list(c) if c is not None and len(c) >= 2 else None for c in cycles]
+        if ref.shape[1] != con.shape[1]:
+            raise ValueError("reference and conditioning must have the same length to be cut at the same joins")
+        plan = heart_cycles.CyclePlan([list(c) if c is not None and len(c) >= 2 else None for c in cycles], ref.shape[1],
+                                      ref.device)
         fade_n = int(round(fade_ms / 1000.0 * fs))
 
     def run(x, want_chirp):

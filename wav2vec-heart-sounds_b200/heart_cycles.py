@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["load_join_indices", "cycle_bounds", "rearrange_order", "rebuild_batch", "rebuild"]
+__all__ = ["load_join_indices", "cycle_bounds", "rearrange_order", "CyclePlan", "rebuild_batch", "rebuild"]
 
 
 def load_join_indices(seg_path, fs_out: float) -> list[int]:
@@ -60,39 +60,55 @@ def rearrange_order(num: int, *, prob_contiguous: float = 0.0, random_start: boo
     return [i for block in blocks for i in block]
 
 
-def rebuild_batch(x: torch.Tensor, cycles: Sequence[Sequence[tuple[int, int]] | None], target_len: int,
-                  fade_samples: int) -> tuple[torch.Tensor, torch.Tensor]:
+class CyclePlan:
+    """Device tables of one batch's cycle lists (``starts`` / ``lens`` ``[B, kmax]`` int32, ``counts`` ``[B]``), built
+    once and shared by every signal that is cut at the same joins (reference and conditioning waveforms,
+    ``datasets/generative.py:65-66``)."""
+
+    def __init__(self, cycles: Sequence[Sequence[tuple[int, int]] | None], t: int, device):
+        b = len(cycles)
+        self.kmax = max([len(c) for c in cycles if c] + [1])
+        starts = np.zeros((b, self.kmax), dtype=np.int32)
+        lens = np.zeros((b, self.kmax), dtype=np.int32)
+        counts = np.zeros(b, dtype=np.int32)
+        for r, row in enumerate(cycles):
+            if not row:
+                continue
+            for c, (lo, hi) in enumerate(row):                      # plain loops: a dozen pairs per row, NumPy calls cost more
+                if not (0 <= lo <= hi <= t):
+                    raise ValueError(f"row {r}: cycle ({lo}, {hi}) is outside the signal of {t} samples")
+                starts[r, c], lens[r, c] = lo, hi - lo
+            counts[r] = len(row)
+        self.rows, self.t = b, int(t)
+        self.longest = int(lens.max()) if b else 0
+        self.passthrough = bool((counts == 0).any())
+        self.starts, self.lens, self.counts = (torch.from_numpy(a).to(device) for a in (starts, lens, counts))
+
+
+def rebuild_batch(x: torch.Tensor, cycles, target_len: int, fade_samples: int) -> tuple[torch.Tensor, torch.Tensor]:
     """``rebuild`` (``heart_cycles.py:55-69``) for every row of ``x [B, T]``: ``cycles[r]`` lists row r's cycles as
-    ``(start, end)`` index pairs in joining order (``None`` or empty: the row passes through unchanged).  Returns
-    ``(y [B, cap], length [B] int64)``; row r is valid up to ``length[r]`` (at least ``target_len`` unless the
-    reference's loop guard stops first), the rest of the row is unspecified."""
+    ``(start, end)`` index pairs in joining order (``None`` or empty: the row passes through unchanged); a prepared
+    :class:`CyclePlan` is accepted in its place.  Returns ``(y [B, cap], length [B] int64)``; row r is valid up to
+    ``length[r]`` (at least ``target_len`` unless the reference's loop guard stops first), the rest of the row is
+    unspecified."""
     x = _lib.require_cuda_f32(x)
-    if x.dim() != 2 or len(cycles) != x.shape[0]:
-        raise ValueError("x must be [B, T] with one cycle list per row")
+    if x.dim() != 2:
+        raise ValueError("x must be [B, T]")
     b, t = int(x.shape[0]), int(x.shape[1])
-    kmax = max([len(c) for c in cycles if c] + [1])
-    starts = np.zeros((b, kmax), dtype=np.int32)
-    lens = np.zeros((b, kmax), dtype=np.int32)
-    counts = np.zeros(b, dtype=np.int32)
-    longest = 0
-    for r, row in enumerate(cycles):
-        if not row:
-            continue
-        for c, (lo, hi) in enumerate(row):
-            if not (0 <= lo <= hi <= t):
-                raise ValueError(f"row {r}: cycle ({lo}, {hi}) is outside the signal")
-            starts[r, c], lens[r, c] = lo, hi - lo
-            longest = max(longest, hi - lo)
-        counts[r] = len(row)
-    cap = max(int(target_len) + longest, t if (counts == 0).any() else 0, 1)
-    dev = x.device
-    y = torch.empty((b, cap), device=dev, dtype=torch.float32)
-    length = torch.empty(b, device=dev, dtype=torch.int64)
-    d_st, d_ln, d_ct = (torch.from_numpy(a).to(dev) for a in (starts, lens, counts))
+    plan = cycles if isinstance(cycles, CyclePlan) else None
+    if plan is None:
+        if len(cycles) != b:
+            raise ValueError("x must be [B, T] with one cycle list per row")
+        plan = CyclePlan(cycles, t, x.device)
+    if plan.rows != b or plan.t != t:
+        raise ValueError("the cycle plan was built for another batch shape")
+    cap = max(int(target_len) + plan.longest, t if plan.passthrough else 0, 1)
+    y = torch.empty((b, cap), device=x.device, dtype=torch.float32)
+    length = torch.empty(b, device=x.device, dtype=torch.int64)
     xc = x.contiguous()
-    _lib.check(_lib.lib().mpcg_cycle_rebuild_f32(xc.data_ptr(), y.data_ptr(), length.data_ptr(), d_st.data_ptr(), d_ln.data_ptr(),
-                                                 d_ct.data_ptr(), b, t, cap, kmax, int(target_len), int(fade_samples),
-                                                 _lib.stream_ptr(x)), "cycle rebuild")
+    _lib.check(_lib.lib().mpcg_cycle_rebuild_f32(xc.data_ptr(), y.data_ptr(), length.data_ptr(), plan.starts.data_ptr(),
+                                                 plan.lens.data_ptr(), plan.counts.data_ptr(), b, t, cap, plan.kmax,
+                                                 int(target_len), int(fade_samples), _lib.stream_ptr(x)), "cycle rebuild")
     return y, length
 
 
