@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPCG_ABI_VERSION 1
+#define MPCG_ABI_VERSION 2
 
 #define MPCG_OK 0
 #define MPCG_EINVAL (-1)
@@ -97,11 +97,12 @@ int mpcg_segment_f32(const float* x, float* out, int64_t rows, int64_t channels,
 int64_t mpcg_window_count(int64_t t, int64_t start, int64_t win, int64_t hop);
 
 /* ---- fused chain ---------------------------------------------------------------------------------
- * One kernel for  resample -> [despike] -> low-pass + high-pass -> abs-max normalise -> windows, i.e.
+ * One launch for  resample -> [despike] -> low-pass + high-pass -> abs-max normalise -> windows, i.e.
  * torchproc.preprocess_pcg / preprocess_ecg followed by torchproc.segment (signalproc/torchproc.py:101-129;
  * NumPy twins signalproc/preprocess.py:24-37 + signalproc/segment.py:40-52; loader call sites
- * datasets/cinc.py:86-94,115 and datasets/vest.py:50-51,84).  Raw samples are read from HBM once and the
- * windows written once; every intermediate stays in shared memory of a thread-block cluster. */
+ * datasets/cinc.py:86-94,115 and datasets/vest.py:50-51,84).  Persistent CTAs stream whole rows through shared
+ * memory tile by tile: raw samples are read from HBM once, windows leave once; a row may have any length
+ * (30 s at 16 kHz = 480 000 samples) and, with the row tables below, every recording its own length. */
 typedef struct mpcg_chain_kind {
   int despike;        /* 1: Schmidt despike before the band filter (PCG); 0: none (ECG)            */
   int n_sections;     /* 1 or 2 second-order sections, applied in order                            */
@@ -109,7 +110,8 @@ typedef struct mpcg_chain_kind {
 } mpcg_chain_kind;
 
 typedef struct mpcg_chain_desc {
-  int64_t t_in, t_out;          /* samples per row before / after resampling                         */
+  int64_t t_in, t_out;          /* samples per row before / after resampling (ragged batch: the row pitch */
+                                /*   of x and the longest resampled row)                              */
   int up, down, taps_per_phase; /* resampler in dense frame form (see mpcg_resample_f32); up == down  */
   int64_t offset;               /*   means "no resampling" and taps may be NULL                       */
   const float* taps;            /* HOST pointer, up * taps_per_phase floats                           */
@@ -123,15 +125,31 @@ typedef struct mpcg_chain_desc {
   int n_kinds;                  /* 1 or 2 distinct channel recipes                                    */
   mpcg_chain_kind kinds[2];
   uint8_t kind_of_channel[8];   /* recipe index of each channel (channels <= 8)                       */
+  /* Ragged batch (all three NULL = every recording has t_in / t_out samples): DEVICE tables indexed by
+   * recording -- valid samples of its rows in x, their resampled length, and the element offset in `out` of
+   * the recording's block (its windows in the chosen layout; layout 2: offset inside a channel plane).  The
+   * kernel derives each recording's window count with mpcg_window_count's rule; seg_n is ignored. */
+  const int32_t* row_t_in;
+  const int32_t* row_t_out;
+  const int64_t* row_out_offset;
+  int64_t plane_elems;          /* layout 2 only: elements per channel plane (0 = recordings * seg_n * seg_win) */
 } mpcg_chain_desc;
 
-/* x: [recordings, channels, t_in] -> out (layout above).  edits / trace as in mpcg_despike_f32, indexed by
- * row = recording * channels + channel.  Returns MPCG_EUNSUPPORTED when the geometry does not fit the fused
- * kernel (row too long for an 8-CTA cluster, unknown resampling ratio, > 2 sections): the caller then chains
- * the stand-alone entry points above, which accept everything. */
+/* Bytes of device scratch mpcg_preprocess_segment_f32 needs for rows of up to t_out_max resampled samples on the
+ * current device: a ticket counter plus one row buffer per persistent CTA (despiked rows are parked there between
+ * the frame-maxima pass and the filter pass; it is reused row after row and therefore lives in L2).  < 0 = error. */
+int64_t mpcg_preprocess_segment_work_bytes(int64_t t_out_max);
+
+/* x: [recordings, channels, t_in] -> out (layout above).  work: 16-byte aligned device scratch of at least
+ * mpcg_preprocess_segment_work_bytes(desc->t_out) bytes, private to this call until it has finished (launches that
+ * may overlap on different streams need a workspace each).  edits / trace as in mpcg_despike_f32, indexed by
+ * row = recording * channels + channel; the passes always run in the reference's order.
+ * Returns MPCG_EUNSUPPORTED for a resampling ratio without a baked tap set, > 2 sections, a despike frame longer
+ * than one tile or more than 1024 despike frames per row: the caller then chains the stand-alone entry points above,
+ * which accept everything. */
 int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t recordings, int channels,
-                                const mpcg_chain_desc* desc, int32_t* edits, int32_t* trace, int trace_cap,
-                                void* stream);
+                                const mpcg_chain_desc* desc, void* work, int64_t work_bytes, int32_t* edits,
+                                int32_t* trace, int trace_cap, void* stream);
 
 /* ---- augmentation (augment/torchaug.py) ----------------------------------------------------------
  * Random draws are made by the caller (the Python mirror draws them with torch in the reference's call

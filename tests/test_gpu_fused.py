@@ -53,6 +53,48 @@ def test_fused_pcg_vs_float64_oracle(pkg, fs_in, fs_out, n, ws):
         _check_trace(tr[r], int(edits[r]), [t[1:] for t in trace if t[0] == r])
 
 
+@pytest.mark.parametrize("mode", ["torch", "numpy"])
+def test_long_rows_config0_full_length(pkg, mode):
+    """configs[0] rows at full length: 30 s at 2 kHz -> 16 kHz = 480 000 samples per row (27 tiles streamed through one
+    CTA, 8000-sample despike frames fetched into the frame cache), 4 s windows, against the float64 oracle of the mode;
+    despike decisions bit for bit (signalproc/preprocess.py:24-37, segment.py:40-52, torchproc.py:101-129)."""
+    x = _spiky(2, 60000, seed=61, spikes=4)
+    x[1, 30000:30003] += 30.0
+    got, edits, tr = pkg.preprocess_segment(_dev(x), 2000, 16000, pkg.WindowSpec(4.0), mode=mode, fused=True,
+                                            return_trace=True)
+    assert got.shape == (2, 7, 64000)
+    got, edits, tr = got.cpu().numpy(), edits.cpu().numpy(), tr.cpu().numpy()
+    if mode == "torch":
+        want, trace = _oracle_torch(x, 2000, 16000, 4.0)
+        assert rel_err(got, want) < TOL
+        for r in range(2):
+            _check_trace(tr[r], int(edits[r]), [t[1:] for t in trace if t[0] == r])
+    else:
+        spec = onp.WindowSpec(4.0)
+        for r in range(2):
+            trace = []
+            v = onp.remove_spikes(onp.resample(x[r].astype(np.float64), 2000, 16000), 16000, trace=trace)
+            want = onp.segment(onp.abs_max_normalise(onp.bandpass_cascade(v, 16000, *onp.PCG_BAND)), 16000, spec)
+            assert rel_err(got[r], want) < TOL
+            _check_trace(tr[r], int(edits[r]), trace)
+    assert int(edits.sum()) >= 4
+
+
+def test_long_ecg_rows_and_row_independence(pkg):
+    """ECG rows of 480 000 samples (pole radius 0.9997 at 16 kHz carried across 27 tiles) and a batch larger than the
+    persistent grid: every row must equal the same row processed alone."""
+    rng = np.random.default_rng(62)
+    t = np.arange(60000)
+    ecg = (np.sin(t[None] / rng.uniform(200, 400, (3, 1))) + 0.3 + 0.05 * rng.standard_normal((3, 60000))).astype(np.float32)
+    want, _ = _oracle_torch(ecg, 2000, 16000, 4.0, "ecg")
+    got = pkg.preprocess_segment(_dev(ecg), 2000, 16000, pkg.WindowSpec(4.0), kinds=("ecg",), fused=True)
+    assert rel_err(got.cpu().numpy(), want) < TOL
+    big = _dev(_spiky(700, 9000, seed=63))                     # more rows than resident CTAs: tickets wrap around
+    a = pkg.preprocess_segment(big, 2000, 4125, pkg.WindowSpec(1.0), fused=True)
+    b = pkg.preprocess_segment(big[690:].contiguous(), 2000, 4125, pkg.WindowSpec(1.0), fused=True)
+    assert torch.equal(a[690:], b)
+
+
 def test_fused_equals_chained_kernels(pkg):
     x = _dev(_spiky(5, 60000, seed=22))
     spec = pkg.WindowSpec(4.0)

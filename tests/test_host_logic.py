@@ -101,7 +101,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for n in sorted(names):
         assert hasattr(handle, n), f"{n} declared in include/mpcg_b200.h but not exported"
     assert names == set(built_lib.declared_symbols())
-    assert handle.mpcg_abi_version() == 1
+    assert handle.mpcg_abi_version() == 2
 
 
 def test_argument_errors_are_reported_without_a_gpu(built_lib):

@@ -35,8 +35,9 @@ _SIGNATURES = {
     "mpcg_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
                                  ctypes.c_void_p]),
     "mpcg_window_count": (c_i64, [c_i64, c_i64, c_i64, c_i64]),
-    "mpcg_preprocess_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p,
-                                            ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_preprocess_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p, c_i64,
+                                            ctypes.c_void_p, ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_preprocess_segment_work_bytes": (c_i64, [c_i64]),
     "mpcg_debug_set_phase_clock_buffer": (None, [ctypes.c_void_p]),
     "mpcg_mel_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p,
                              c_int, c_f32p, c_int, c_i64, c_int, ctypes.c_void_p]),
@@ -77,6 +78,7 @@ _SIGNATURES = {
     "mpcg_aug_eq_mix_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_int, ctypes.c_void_p]),
 }
 EUNSUPPORTED = -3
+ABI_VERSION = 2
 
 class ChainKind(ctypes.Structure):
     """mpcg_chain_kind (include/mpcg_b200.h)."""
@@ -90,7 +92,8 @@ class ChainDesc(ctypes.Structure):
                 ("despike_threshold", ctypes.c_double), ("despike_max_iterations", c_int), ("median_mode", c_int),
                 ("norm_flags", c_int), ("seg_start", c_i64), ("seg_win", c_i64), ("seg_hop", c_i64),
                 ("seg_n", c_i64), ("channels_last", c_int), ("n_kinds", c_int), ("kinds", ChainKind * 2),
-                ("kind_of_channel", ctypes.c_uint8 * 8)]
+                ("kind_of_channel", ctypes.c_uint8 * 8), ("row_t_in", ctypes.c_void_p), ("row_t_out", ctypes.c_void_p),
+                ("row_out_offset", ctypes.c_void_p), ("plane_elems", c_i64)]
 
 
 MEDIAN_LOWER, MEDIAN_MEAN = 0, 1
@@ -131,7 +134,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)           # AttributeError here = header and library disagree
             fn.restype = res
             fn.argtypes = args
-        if handle.mpcg_abi_version() != 1:
+        if handle.mpcg_abi_version() != ABI_VERSION:
             raise RuntimeError("libmpcg_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib
@@ -162,3 +165,17 @@ def stream_ptr(x: torch.Tensor) -> int:
 
 def ptr(x) -> int:
     return 0 if x is None else x.data_ptr()
+
+
+_workspaces: dict = {}
+
+
+def workspace(x: torch.Tensor, nbytes: int) -> torch.Tensor:
+    """Device scratch for entry points that take a caller-provided workspace (the C ABI never allocates).  One grow-only
+    buffer per (device, current stream): launches that may overlap on different streams never share scratch."""
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=x.device)
+        _workspaces[key] = buf
+    return buf

@@ -1,4 +1,4 @@
-// extern "C" entry: mpcg_preprocess_segment_f32 -- planner + dispatcher.  The kernel template lives in
+// tools-only entry: mpcg_preprocess_segment_cluster_f32 -- the round-1 cluster kernel, kept for A/B timing against stream.cu.  The kernel template lives in
 // fused_kernel.cuh; each resampler instance is compiled in its own translation unit (fused_inst_*.cu) so the
 // seven heavily unrolled instantiations build in parallel.
 #include "fused_kernel.cuh"
@@ -132,9 +132,9 @@ static int fz_resident_plan(const mpcg::FzKind (&kinds)[2], cudaStream_t stream,
 
 // tools/ only: device buffer [ctas, 16] that receives clock64 stamps per phase (NULL = off).
 static void* g_fz_debug = nullptr;
-extern "C" void mpcg_debug_set_phase_clock_buffer(void* dev_ptr) { g_fz_debug = dev_ptr; }
+extern "C" void mpcg_debug_set_phase_clock_buffer_cluster(void* dev_ptr) { g_fz_debug = dev_ptr; }
 
-extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t recordings, int channels,
+extern "C" int mpcg_preprocess_segment_cluster_f32(const float* x, float* out, int64_t recordings, int channels,
                                            const mpcg_chain_desc* d, int32_t* edits, int32_t* trace, int trace_cap,
                                            void* stream_) {
   using namespace mpcg;

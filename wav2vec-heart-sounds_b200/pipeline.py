@@ -107,8 +107,10 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
                 out = torch.empty(shape, device=x.device, dtype=torch.float32)
             elif tuple(out.shape) != tuple(shape) or not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous():
                 raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {tuple(shape)}")
+            nbytes = int(_lib.lib().mpcg_preprocess_segment_work_bytes(max(int(t_out), 1)))
+            work = _lib.workspace(v, nbytes)
             rc = _lib.lib().mpcg_preprocess_segment_f32(v.data_ptr(), out.data_ptr(), b, c, ctypes.byref(d),
-                                                        _lib.ptr(edits), _lib.ptr(trace),
+                                                        work.data_ptr(), work.numel(), _lib.ptr(edits), _lib.ptr(trace),
                                                         trace_cap if return_trace else 0, _lib.stream_ptr(v))
             if rc != _lib.EUNSUPPORTED:
                 _lib.check(rc, "fused preprocess+segment")
