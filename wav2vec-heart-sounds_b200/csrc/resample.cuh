@@ -209,6 +209,185 @@ struct RsTeam {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Vector form of the team resampler (fused kernel, rows whose first sample is 16-byte aligned): the staged block is
+// moved and read in 16-byte chunks.  A lane owns FR consecutive frames with FR * DOWN a multiple of 4, so every
+// lane's first input sits at the same offset SH inside its chunk and all register indices are compile-time:
+//   global -> registers (128-bit loads, prefetched one block ahead) -> shared (128-bit stores, one pad chunk per
+//   eight so that the lanes' 128-bit reads, LS chunks apart, are free of bank conflicts) -> 128-bit reads of only
+//   the chunks a phase group touches -> FFMA with immediate taps -> the UP outputs of each frame.
+template <int UP, int DOWN, int D, int PS>
+struct RsVec {
+  using Taps = BakedTaps<UP, DOWN, D>;
+  static constexpr int FR = (DOWN % 4 == 0) ? 1 : ((DOWN % 2 == 0) ? 2 : 4);   // frames per lane
+  static constexpr int FB = 32 * FR;                    // frames per block
+  static constexpr int LS = FR * DOWN / 4;              // chunks between neighbouring lanes
+  static constexpr int SH = (int)(((Taps::kOffset % 4) + 4) % 4);
+  static constexpr int NCH = ((FR - 1) * DOWN + D + SH + 3) / 4;       // chunks one lane may read
+  static constexpr int NCH_BLK = 31 * LS + NCH;         // chunks per staged block
+  __host__ __device__ static constexpr int skew(int c) { return (LS & 1) ? c : c + (c >> 3); }
+  static constexpr int WORDS = 4 * (skew(NCH_BLK - 1) + 1);
+  static constexpr int TEAM = PS * 32;
+  static constexpr int NPRE = (NCH_BLK + TEAM - 1) / TEAM;
+  static constexpr int PB = 4;                          // outputs accumulated side by side
+  static constexpr int ALIGN_F = (DOWN % 4 == 0) ? 1 : (4 / (DOWN % 2 == 0 ? 2 : 1));   // frame alignment of a block start
+
+  __host__ __device__ static constexpr int p_begin(int g) { return (g * UP) / PS; }
+  __host__ __device__ static constexpr int d_lo(int p0, int p1) {
+    int m = D - 1;
+    for (int p = p0; p < p1; ++p) m = Taps::first[p] < m ? Taps::first[p] : m;
+    return m;
+  }
+  __host__ __device__ static constexpr int d_hi(int p0, int p1) {
+    int m = 0;
+    for (int p = p0; p < p1; ++p) m = Taps::last[p] > m ? Taps::last[p] : m;
+    return m;
+  }
+
+  // chunks of the block whose first frame is f0 (f0 * DOWN a multiple of 4) -> registers; zero outside the row.
+  // 32-bit index arithmetic (rows are shorter than 2^30 samples); a block that lies inside the row takes no
+  // per-chunk range checks.
+  __device__ static __forceinline__ void fetch(float4 (&pre)[NPRE], const float* __restrict__ x_row, int f0, int t_in, int tt) {
+    const int a0 = f0 * DOWN + (int)Taps::kOffset - SH;       // a multiple of 4
+    const float* p = x_row + a0 + 4 * tt;
+    if (a0 >= 0 && a0 + 4 * NCH_BLK <= t_in) {                // block-uniform: interior block
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        if ((k + 1) * TEAM <= NCH_BLK || tt + k * TEAM < NCH_BLK)
+          pre[k] = ld_stream4(reinterpret_cast<const float4*>(p + 4 * k * TEAM));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        const int c = tt + k * TEAM;
+        const int idx = a0 + 4 * c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < NCH_BLK && idx >= 0 && idx < t_in) {
+          if (idx + 4 <= t_in) {
+            v = ld_stream4(reinterpret_cast<const float4*>(x_row + idx));
+          } else {                                            // the chunk holding the end of a row whose length is not a multiple of 4
+            v.x = ld_stream(x_row + idx);
+            if (idx + 1 < t_in) v.y = ld_stream(x_row + idx + 1);
+            if (idx + 2 < t_in) v.z = ld_stream(x_row + idx + 2);
+          }
+        }
+        pre[k] = v;
+      }
+    }
+  }
+  __device__ static __forceinline__ void commit(float* xs, const float4 (&pre)[NPRE], int tt) {
+    float4* dst = reinterpret_cast<float4*>(xs);
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int c = tt + k * TEAM;
+      if ((k + 1) * TEAM <= NCH_BLK || c < NCH_BLK) dst[skew(c)] = pre[k];
+    }
+  }
+
+  // phases [P0, P1) of the lane's FR frames; dst points at phase 0 of the lane's first frame.
+  template <int P0, int P1>
+  __device__ static __forceinline__ void phases(const float* xs, int lane, float* dst) {
+    constexpr int DLO = d_lo(P0, P1), DHI = d_hi(P0, P1);
+    constexpr int C0 = (SH + DLO) / 4, C1 = (SH + (FR - 1) * DOWN + DHI) / 4;      // chunks this phase group reads
+    float in[4 * (C1 - C0 + 1)];
+    const float4* xc = reinterpret_cast<const float4*>(xs);
+    rs_for<C0, C1 + 1>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      const float4 v = xc[skew(lane * LS + c)];
+      in[4 * (c - C0)] = v.x; in[4 * (c - C0) + 1] = v.y; in[4 * (c - C0) + 2] = v.z; in[4 * (c - C0) + 3] = v.w;
+    });
+    rs_for<0, FR>([&](auto frc) {
+      constexpr int fr = decltype(frc)::value;
+      rs_for<0, (P1 - P0 + PB - 1) / PB>([&](auto gc) {
+        constexpr int p = P0 + decltype(gc)::value * PB;
+        float acc[PB];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) acc[k] = 0.f;
+        rs_for<DLO, DHI + 1>([&](auto dc) {
+          constexpr int d = decltype(dc)::value;
+          rs_for<0, PB>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            if constexpr (p + k < P1) {
+              constexpr float t = Taps::g[p + k][d];
+              if constexpr (t != 0.f) acc[k] = fmaf(in[SH + fr * DOWN + d - 4 * C0], t, acc[k]);
+            }
+          });
+        });
+        rs_for<0, PB>([&](auto kc) {
+          constexpr int k = decltype(kc)::value;
+          if constexpr (p + k < P1) dst[fr * UP + p + k] = acc[k];
+        });
+      });
+    });
+  }
+  template <int G>
+  __device__ static __forceinline__ void dispatch(int grp, const float* xs, int lane, float* dst) {
+    if constexpr (G < PS) {
+      if (grp == G) phases<p_begin(G), p_begin(G + 1)>(xs, lane, dst);
+      else dispatch<G + 1>(grp, xs, lane, dst);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Run form for integer up-sampling (DOWN == 1, UP a multiple of 4): a lane owns a RUN of FR = 5 consecutive frames,
+// i.e. 5 * UP consecutive outputs, computed from FR - 1 + D staged inputs held in registers and stored with 128-bit
+// stores.  The odd run length keeps the lanes' scalar input reads free of bank conflicts and spreads their 128-bit
+// stores over the banks (lane stride 5 * UP * 4 bytes: two-way at worst).  One warp per block, warp-private staging.
+template <int UP, int D>
+struct RsRun {
+  using Taps = BakedTaps<UP, 1, D>;
+  static_assert(UP % 4 == 0, "the run form stores whole 16-byte groups of outputs");
+  static constexpr int FR = 5;
+  static constexpr int FB = 32 * FR;                    // frames per block
+  static constexpr int NIN = FB - 1 + D;                // staged inputs per block
+  static constexpr int WORDS = (NIN + 3) & ~3;
+  static constexpr int NPRE = (NIN + 31) / 32;
+  static constexpr int PER_LANE = FR - 1 + D;
+
+  __device__ static __forceinline__ void fetch(float (&pre)[NPRE], const float* __restrict__ x_row, long long f0, int t_in,
+                                               int lane) {
+    const long long in0 = f0 + Taps::kOffset;
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int m = lane + 32 * k;
+      const long long src = in0 + m;
+      pre[k] = (m < NIN && src >= 0 && src < t_in) ? ld_stream(x_row + src) : 0.f;
+    }
+  }
+  __device__ static __forceinline__ void commit(float* xs, const float (&pre)[NPRE], int lane) {
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int m = lane + 32 * k;
+      if (m < NIN) xs[m] = pre[k];
+    }
+  }
+  // dst: 16-byte aligned address of phase 0 of the lane's first frame
+  __device__ static __forceinline__ void run(const float* xs, int lane, float* dst) {
+    float in[PER_LANE];
+    rs_for<0, PER_LANE>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      in[j] = xs[lane * FR + j];
+    });
+    rs_for<0, FR>([&](auto frc) {
+      constexpr int fr = decltype(frc)::value;
+      rs_for<0, UP / 4>([&](auto gc) {
+        constexpr int p = decltype(gc)::value * 4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        rs_for<0, D>([&](auto dc) {
+          constexpr int d = decltype(dc)::value;
+          rs_for<0, 4>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr float t = Taps::g[p + k][d];
+            if constexpr (t != 0.f) acc[k] = fmaf(in[fr + d], t, acc[k]);
+          });
+        });
+        *reinterpret_cast<float4*>(dst + fr * UP + p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      });
+    });
+  }
+};
+
 // Does the host-supplied tap matrix equal the baked instance bit for bit?
 template <int UP, int DOWN, int D>
 static inline bool rs_taps_match(const float* taps, long long off) {

@@ -37,7 +37,7 @@ static int sk_fill_kind(const mpcg_chain_kind& in, SkKind* k) {
   return MPCG_OK;
 }
 
-// Persistent grid: two CTAs per SM (the kernel's shared memory and register budget), cached per device.
+// Persistent grid: as many CTAs per SM as the kernel's shared memory and register budget allows, cached per device.
 static int sk_grid_ctas(int* out) {
   static int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -47,7 +47,7 @@ static int sk_grid_ctas(int* out) {
     int sms = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return (int)e;
-    cached = 2 * sms;
+    cached = kSkCtasPerSm * sms;
     cached_dev = dev;
   }
   if (const char* env = getenv("MPCG_SK_CTAS")) {           // experiments: override the grid size
@@ -135,6 +135,10 @@ extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t r
   P.norm_flags = d->norm_flags;
   P.start = (int)d->seg_start; P.win = (int)d->seg_win; P.hop = (int)d->seg_hop; P.n = (int)d->seg_n;
   P.layout = d->channels_last;
+  {
+    const char* e = getenv("MPCG_FZ_DESPIKE_SERIAL");       // tests: force the reference-order despike path
+    P.serial_despike = (e && atoi(e) != 0) ? 1 : 0;
+  }
   P.plane = d->plane_elems > 0 ? d->plane_elems : (long long)recordings * d->seg_n * d->seg_win;
   {                                                           // despiked channels first: the longest rows start first
     int k = 0;

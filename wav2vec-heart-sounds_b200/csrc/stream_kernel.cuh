@@ -30,18 +30,25 @@
 
 namespace mpcg {
 
-constexpr int kSkThreads = 512;
+#ifndef MPCG_SK_THREADS
+#define MPCG_SK_THREADS 512                       // threads per CTA: 512 (two CTAs per SM) or 1024 (one)
+#endif
+constexpr int kSkThreads = MPCG_SK_THREADS;
 constexpr int kSkWarps = kSkThreads / 32;
+constexpr int kSkCtasPerSm = 1024 / kSkThreads;
+constexpr int kSkWarpLevels = kSkWarps == 32 ? 5 : 4;      // Hillis-Steele levels of the cross-warp scan
 constexpr int kSkL = 36;                          // samples per filter chunk; 4 x odd: 128-bit shared accesses without bank conflicts
 constexpr int kSkTile = kSkThreads * kSkL;        // samples per tile (18 432)
 constexpr int kSkGuard = 40;                      // floats before and after the tile that edge frames of the resampler spill into
-constexpr int kSkStageWords = 4608;               // resampler input staging: teams x buffers x block
+constexpr int kSkStageWords = 9 * kSkThreads + 128;   // resampler input staging: teams x block
 constexpr int kSkMaxFrames = 1024;                // despike frames per row (a 30 s recording has 60)
 constexpr int kSkSlots = 8;                       // despike frame cache (streamed rows)
 constexpr int kSkBmWords = 1536;                  // 32-sample block maxima of the cached frames
 constexpr int kSkWorkHeader = 64;                 // floats at the start of the workspace (ticket counter)
+constexpr int kSkFastFrames = 64;                 // frames per row the parallel despike rounds take
+constexpr int kSkLogCap = 16;                     // passes per frame and round they log before handing over to the serial order
 static_assert(kSkL % 4 == 0 && ((kSkL / 4) & 1) == 1, "chunk length must be 4 x odd");
-static_assert(kSkWarps == 16, "the cross-warp scan is written for 16 warps");
+static_assert(kSkWarps == 16 || kSkWarps == 32, "the cross-warp scan is written for 16 or 32 warps");
 
 struct SkKind {                                   // per channel kind (PCG / ECG): despike on/off + its filter
   int despike;
@@ -75,6 +82,7 @@ struct SkParams {
   int max_iter, median_mode, norm_flags;
   int start, win, hop, n;                         // window geometry (n: windows of a uniform row)
   int layout;                                     // 0: out[rec, ch, k, j]  1: out[rec, k, j, ch]  2: out[ch, rec, k, j]
+  int serial_despike;                             // 1: always take the serial (reference-order) despike path
   unsigned char kind_of_channel[8];
   unsigned char chan_order[8];                    // channels in processing order: despiked kinds first (longest rows first)
   SkKind kinds[2];
@@ -86,9 +94,23 @@ struct SkShared {
     struct {                                      //   despike
       float bm[kSkBmWords];
       SpikeSorted sorted;
+      // parallel rounds (see the kernel): outcome and pass log of every frame above the round's threshold
+      float xtop[kSkFastFrames];                  //   maximum the frame ended the round with
+      int xmeta[kSkFastFrames];                   //   passes | stuck << 8 | log full << 9
+      int xj[kSkFastFrames];                      //   passes that count after a stuck round
+      float seq[kSkFastFrames][kSkLogCap + 1];    //   maximum after j logged passes
+      unsigned short span[kSkFastFrames][kSkLogCap][2];   // [lo, hi) of every logged pass
+      unsigned char act[kSkFastFrames];           //   slot -> frame
+      int nact, verdict, total;
+      float cutf, lo_mid, hi_mid;
+      double cutd;
+      unsigned long long kstar;
     } d;
   };
+  unsigned long long bulk_bar;                    // mbarrier of the bulk (TMA) tile loads
+  unsigned long long pad2_;
   float tops[kSkMaxFrames];                       // frame maxima of the current row
+  float spanmax[kSkTile / 128];                   // maxima of the tile's aligned 128-sample spans
   double mtab[16][32];                            // M^lane of the current kind, element-major
   double wagg[kSkWarps][4];                       // warp aggregates
   double wcar[kSkWarps][4];                       // state at the start of each warp's first chunk
@@ -101,6 +123,7 @@ struct SkShared {
   unsigned int ticket;
   int pad_;
 };
+static_assert(sizeof(((SkShared*)0)->d) <= sizeof(float) * kSkStageWords, "despike scratch must fit behind the staging area");
 static_assert(sizeof(SkShared) % 16 == 0, "the sample tile behind SkShared must stay 16-byte aligned");
 
 __device__ __forceinline__ float4 ld_cg4(const float4* p) {      // re-read of data this CTA wrote: L2, not L1
@@ -113,47 +136,122 @@ __device__ __forceinline__ float ld_cg(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+// ---- bulk asynchronous copies (TMA, cp.async.bulk): a whole tile moves with one instruction issued by one thread
+__device__ __forceinline__ uint32_t sk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sk_bulk_load(void* smem_dst, const void* g, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sk_smem(smem_dst)),
+               "l"(g), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void sk_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sk_bulk_store(void* g, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(sk_smem(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sk_bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sk_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sk_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// un-normalised windows are written now and read back once by the rescale pass of the same row: ask L2 to keep them
+__device__ __forceinline__ unsigned long long sk_policy_keep() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep4(float4* p, float4 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(float* p, float v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void sk_team_sync(int team, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(count) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Resample samples [t0, t0 + n) of the row into sig[0, n).  Teams of PS warps walk the tile in blocks of 32 frames:
-// coalesced loads -> registers (prefetched one block ahead) -> skewed staging -> each warp of the team computes
-// its phase group.  Edge frames spill into the guard floats around the tile.  Ends with a CTA barrier.
+// Resample samples [t0, t0 + n) of the row into sig[0, n).  Teams of PS warps walk the tile in blocks of frames:
+// coalesced loads -> registers (prefetched one block ahead) -> staging in shared memory -> each warp of the team
+// computes its phase group.  Edge frames spill into the guard floats around the tile.  Rows that start on a
+// 16-byte boundary take the vector form (RsVec: 128-bit loads, stores and staged reads), others the scalar one.
+// Ends with a CTA barrier.  Not inlined: the kernel calls it from two places.
 template <int UP, int DOWN, int D, int PS>
-__device__ __forceinline__ void sk_resample_tile(float* sig, float* xs_all, const float* __restrict__ xr, int t_in, int off,
-                                                 int t0, int n) {
+__device__ __noinline__ void sk_resample_tile(float* sig, float* xs_all, const float* __restrict__ xr, int t_in, int off,
+                                              int t0, int n) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if constexpr (UP == DOWN) {
     for (int i = tid; i < n; i += kSkThreads) sig[i] = ld_stream(xr + t0 + i);
   } else {
-    using T = RsTeam<UP, DOWN, D, PS>;
     constexpr int NTEAMS = kSkWarps / PS;
-    constexpr int NBUF = (NTEAMS * 2 * T::WORDS <= kSkStageWords) ? 2 : 1;
     static_assert(kSkWarps % PS == 0 && (PS == 1 || NTEAMS <= 15), "teams map onto named barriers 1..15");
-    static_assert(NTEAMS * NBUF * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
     static_assert(UP - 1 <= kSkGuard, "guard too small");
-    const int team = warp / PS, grp = warp - team * PS, tt = tid - team * T::TEAM;
-    float* xs_team = xs_all + team * (NBUF * T::WORDS);
-    const int f_lo = t0 / UP, f_hi = (t0 + n - 1) / UP;
-    const int nblk = (f_hi - f_lo + T::FB) / T::FB;
-    float pre[T::NPRE];
-    int blk = team, buf = 0;
-    if (blk < nblk) T::fetch(pre, xr, (long long)(f_lo + blk * T::FB) * DOWN + off, t_in, tt);
-    for (; blk < nblk; blk += NTEAMS) {
-      float* xs = xs_team + buf * T::WORDS;
-      T::commit(xs, pre, tt);
-      if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
-      if (blk + NTEAMS < nblk)                            // next block's loads fly while this one is computed
-        T::fetch(pre, xr, (long long)(f_lo + (blk + NTEAMS) * T::FB) * DOWN + off, t_in, tt);
-      const int f = f_lo + blk * T::FB + lane;
-      if (f <= f_hi) T::template dispatch<0>(grp, xs, lane, sig + (f * UP - t0));
-      if constexpr (NBUF == 2) buf ^= 1;
-      else if constexpr (PS == 1) __syncwarp();
-      else sk_team_sync(team, T::TEAM);
+    const int team = warp / PS, grp = warp - team * PS;
+    if constexpr (DOWN == 1 && UP % 4 == 0) {             // integer up-sampling: runs of five frames per lane
+      using T = RsRun<UP, D>;
+      static_assert(kSkWarps * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
+      static_assert(T::FR * UP - 1 <= kSkGuard && kSkTile % UP == 0, "guard too small for a run past the tile end");
+      float* xs = xs_all + warp * T::WORDS;
+      const int f_lo = t0 / UP, f_hi = (t0 + n - 1) / UP;
+      const int nblk = (f_hi - f_lo + T::FB) / T::FB;
+      float pre[T::NPRE];
+      int blk = warp;
+      if (blk < nblk) T::fetch(pre, xr, (long long)(f_lo + blk * T::FB), t_in, lane);
+      for (; blk < nblk; blk += kSkWarps) {
+        T::commit(xs, pre, lane);
+        __syncwarp();
+        if (blk + kSkWarps < nblk) T::fetch(pre, xr, (long long)(f_lo + (blk + kSkWarps) * T::FB), t_in, lane);
+        const int f = f_lo + blk * T::FB + lane * T::FR;
+        if (f <= f_hi) T::run(xs, lane, sig + (f * UP - t0));
+        __syncwarp();
+      }
+    } else if ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {
+      using T = RsVec<UP, DOWN, D, PS>;
+      static_assert(NTEAMS * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
+      static_assert((T::ALIGN_F - 1) * UP + UP - 1 <= kSkGuard, "guard too small for the aligned block start");
+      const int tt = tid - team * T::TEAM;
+      float* xs = xs_all + team * T::WORDS;
+      const int f_lo = (t0 / UP) & ~(T::ALIGN_F - 1), f_hi = (t0 + n - 1) / UP;
+      const int nblk = (f_hi - f_lo + T::FB) / T::FB;
+      float4 pre[T::NPRE];
+      int blk = team;
+      if (blk < nblk) T::fetch(pre, xr, f_lo + blk * T::FB, t_in, tt);
+      for (; blk < nblk; blk += NTEAMS) {
+        T::commit(xs, pre, tt);
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+        if (blk + NTEAMS < nblk)                          // next block's loads fly while this one is computed
+          T::fetch(pre, xr, f_lo + (blk + NTEAMS) * T::FB, t_in, tt);
+        const int f = f_lo + blk * T::FB + lane * T::FR;
+        if (f <= f_hi) T::template dispatch<0>(grp, xs, lane, sig + (f * UP - t0));
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+      }
+    } else {
+      using T = RsTeam<UP, DOWN, D, PS>;
+      static_assert(NTEAMS * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
+      const int tt = tid - team * T::TEAM;
+      float* xs = xs_all + team * T::WORDS;
+      const int f_lo = t0 / UP, f_hi = (t0 + n - 1) / UP;
+      const int nblk = (f_hi - f_lo + T::FB) / T::FB;
+      float pre[T::NPRE];
+      int blk = team;
+      if (blk < nblk) T::fetch(pre, xr, (long long)(f_lo + blk * T::FB) * DOWN + off, t_in, tt);
+      for (; blk < nblk; blk += NTEAMS) {
+        T::commit(xs, pre, tt);
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+        if (blk + NTEAMS < nblk)
+          T::fetch(pre, xr, (long long)(f_lo + (blk + NTEAMS) * T::FB) * DOWN + off, t_in, tt);
+        const int f = f_lo + blk * T::FB + lane;
+        if (f <= f_hi) T::template dispatch<0>(grp, xs, lane, sig + (f * UP - t0));
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+      }
     }
   }
+  sk_fence_async_smem();                                  // the tile may leave through a bulk (async-proxy) store
   __syncthreads();
 }
 
@@ -233,6 +331,7 @@ __device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, 
     _Pragma("unroll") for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, v[s], 1 << DD); \
     if (lane >= (1 << DD)) sk_mv_acc<K, 5 + DD>(P, u, v);
     MPCG_SK_LEVEL(0) MPCG_SK_LEVEL(1) MPCG_SK_LEVEL(2) MPCG_SK_LEVEL(3)
+    if constexpr (kSkWarpLevels == 5) { MPCG_SK_LEVEL(4) }
 #undef MPCG_SK_LEVEL
     __syncwarp();
 #pragma unroll
@@ -340,18 +439,35 @@ __device__ __forceinline__ void sk_build_mtab(const SkParams& P, SkShared& sm, i
 }
 
 // Copy the part of every window that intersects samples [s0, s0 + n) of the row (held in sig[0, n)) to `obase`.
-// so_j == 1 takes 64-bit stores; the data is read again by the rescale pass, so plain (L2-resident) stores.
+// so_j == 1: 128-bit stores to 16-byte aligned destinations; the shared-memory side is read as the two aligned
+// 16-byte chunks around each group of four and shifted in registers (the shift is uniform per window and tile).
+// The data is read again by the rescale pass, so plain (L2-resident) stores.
+template <int SHIFT>
+__device__ __forceinline__ void sk_copy_shifted(const float4* __restrict__ s4, float4* __restrict__ d4, int nvec,
+                                                unsigned long long pol) {
+  for (int i = threadIdx.x; i < nvec; i += kSkThreads) {
+    const float4 a = s4[i];
+    float4 o;
+    if constexpr (SHIFT == 0) {
+      o = a;
+    } else {
+      const float4 b = s4[i + 1];
+      if constexpr (SHIFT == 1) o = make_float4(a.y, a.z, a.w, b.x);
+      else if constexpr (SHIFT == 2) o = make_float4(a.z, a.w, b.x, b.y);
+      else o = make_float4(a.w, b.x, b.y, b.z);
+    }
+    st_keep4(d4 + i, o, pol);
+  }
+}
+// kf: first window that may still intersect the tile (the caller carries it from tile to tile, so no division here)
 __device__ __forceinline__ void sk_store_windows(const float* sig, float* obase, int s0, int n, int start, int win, int hop,
-                                                 int nwin, long long so_k, long long so_j) {
+                                                 int nwin, long long so_k, long long so_j, int& kf, unsigned long long pol) {
   const int tid = threadIdx.x;
   const int s1 = s0 + n;
-  int k_first = s0 - start - win + 1;
-  k_first = k_first > 0 ? (k_first + hop - 1) / hop : 0;
-  int k_last = s1 - 1 - start;
-  k_last = k_last < 0 ? -1 : k_last / hop;
-  if (k_last > nwin - 1) k_last = nwin - 1;
-  for (int k = k_first; k <= k_last; ++k) {
+  while (kf < nwin && start + kf * hop + win <= s0) ++kf;
+  for (int k = kf; k < nwin; ++k) {
     const int w0 = start + k * hop;
+    if (w0 >= s1) break;
     const int a = w0 > s0 ? w0 : s0;
     const int w1 = w0 + win;
     const int b = w1 < s1 ? w1 : s1;
@@ -360,31 +476,21 @@ __device__ __forceinline__ void sk_store_windows(const float* sig, float* obase,
     const float* sp = sig + (a - s0);
     if (so_j == 1) {
       float* dp = obase + k * so_k + (a - w0);
-      int head = (int)((reinterpret_cast<uintptr_t>(dp) >> 2) & 1u);
+      int head = (int)(((16u - ((uintptr_t)dp & 15u)) & 15u) >> 2);      // scalars up to the first aligned destination
       if (head > len) head = len;
-      if (head && tid == 0) dp[0] = sp[0];
-      const int npair = (len - head) >> 1;
-      const float* sq = sp + head;
-      float2* dq = reinterpret_cast<float2*>(dp + head);
-      if ((reinterpret_cast<uintptr_t>(sq) & 7u) == 0) {
-        const float2* sq2 = reinterpret_cast<const float2*>(sq);
-        int i = tid;
-        for (; i + kSkThreads < npair; i += 2 * kSkThreads) {
-          const float2 p0 = sq2[i], p1 = sq2[i + kSkThreads];
-          dq[i] = p0;
-          dq[i + kSkThreads] = p1;
-        }
-        for (; i < npair; i += kSkThreads) dq[i] = sq2[i];
-      } else {
-        int i = tid;
-        for (; i + kSkThreads < npair; i += 2 * kSkThreads) {
-          const float a0 = sq[2 * i], a1 = sq[2 * i + 1], b0 = sq[2 * (i + kSkThreads)], b1 = sq[2 * (i + kSkThreads) + 1];
-          dq[i] = make_float2(a0, a1);
-          dq[i + kSkThreads] = make_float2(b0, b1);
-        }
-        for (; i < npair; i += kSkThreads) dq[i] = make_float2(sq[2 * i], sq[2 * i + 1]);
+      if (tid < head) st_keep(dp + tid, sp[tid], pol);
+      const int nvec = (len - head) >> 2;
+      const int src = (a - s0) + head;                                   // tile-relative index of the first body sample
+      const float4* s4 = reinterpret_cast<const float4*>(sig) + (src >> 2);
+      float4* d4 = reinterpret_cast<float4*>(dp + head);
+      switch (src & 3) {
+        case 0: sk_copy_shifted<0>(s4, d4, nvec, pol); break;
+        case 1: sk_copy_shifted<1>(s4, d4, nvec, pol); break;
+        case 2: sk_copy_shifted<2>(s4, d4, nvec, pol); break;
+        default: sk_copy_shifted<3>(s4, d4, nvec, pol); break;
       }
-      if (((len - head) & 1) && tid == 32) dp[len - 1] = sp[len - 1];
+      const int done = head + (nvec << 2);
+      if (tid >= 32 && tid - 32 < len - done) st_keep(dp + done + tid - 32, sp[done + tid - 32], pol);
     } else {
       float* dp = obase + k * so_k + (long long)(a - w0) * so_j;
       for (int i = tid; i < len; i += kSkThreads) dp[(long long)i * so_j] = sp[i];
@@ -392,8 +498,89 @@ __device__ __forceinline__ void sk_store_windows(const float* sig, float* obase,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Parallel despike rounds, one frame by one warp.  The frame is fetched from the row buffer into the warp's slot and
+// flattened there pass after pass while its maximum exceeds the round's threshold; every pass logs its span and the
+// maximum it leaves behind.  Which of the logged passes the reference's serial order really performs is decided
+// after all frames of the round are done (see the kernel); those spans are then filled in the row buffer.
+struct SkCut {                             // "frame maximum exceeds threshold * median" in the oracle's arithmetic
+  int mode;
+  float cutf;                              // tensor path: fp32 product, fp32 compare
+  double cutd;                             // NumPy path: float64 product and compare
+  __device__ __forceinline__ bool exceeds(float top) const {
+    return mode == MPCG_MEDIAN_LOWER ? (top > cutf) : ((double)top > cutd);
+  }
+};
+__device__ __forceinline__ void sk_fast_frame(SkShared& sm, float* slot_buf, float* bm, const float* g, int win, float top,
+                                              int slot, const SkCut& cut) {
+  const int lane = threadIdx.x & 31;
+  float* fr = slot_buf + phase_of(g);
+  {                                                          // fetch: 128-bit loads, four in flight
+    int head = (int)(((16u - ((uintptr_t)g & 15u)) & 15u) >> 2);
+    if (head > win) head = win;
+    if (lane < head) fr[lane] = ld_cg(g + lane);
+    const int nvec = (win - head) >> 2;
+    const float4* gv = reinterpret_cast<const float4*>(g + head);
+    float4* sv = reinterpret_cast<float4*>(fr + head);
+    int i = lane;
+    for (; i + 96 < nvec; i += 128) {
+      const float4 a = ld_cg4(gv + i), b = ld_cg4(gv + i + 32), c = ld_cg4(gv + i + 64), d = ld_cg4(gv + i + 96);
+      sv[i] = a; sv[i + 32] = b; sv[i + 64] = c; sv[i + 96] = d;
+    }
+    for (; i < nvec; i += 32) sv[i] = ld_cg4(gv + i);
+    const int done = head + (nvec << 2);
+    if (lane < win - done) fr[done + lane] = ld_cg(g + done + lane);
+  }
+  __syncwarp();
+  const int nblk = (win + 31) >> 5;
+  for (int b0 = 0; b0 < nblk; b0 += 4) {                     // block maxima, four blocks in flight
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = (b0 + u) * 32 + lane;
+      v[u] = i < win ? fabsf(fr[i]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(v[u], 0.f)));   // fmaxf drops NaN
+      if (lane == 0 && b0 + u < nblk) bm[b0 + u] = __uint_as_float(m);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) sm.d.seq[slot][0] = top;
+  int k = 0, stuck = 0, over = 0;
+  while (cut.exceeds(top)) {
+    if (k == kSkLogCap) { over = 1; break; }
+    int peak, lo, hi;
+    spike_find_span(fr, win, bm, nblk, top, peak, lo, hi);
+    bool changed;
+    float new_top;
+    spike_fill_span(fr, win, bm, nblk, lo, hi, changed, new_top);
+    if (!changed) { stuck = 1; break; }      // a pass that moves nothing: the reference repeats it until max_iterations
+    ++k;
+    top = new_top;
+    if (lane == 0) {
+      sm.d.span[slot][k - 1][0] = (unsigned short)lo;
+      sm.d.span[slot][k - 1][1] = (unsigned short)hi;
+      sm.d.seq[slot][k] = top;
+    }
+  }
+  if (lane == 0) {
+    sm.d.xtop[slot] = top;
+    sm.d.xmeta[slot] = k | (stuck << 8) | (over << 9);
+  }
+}
+__device__ __forceinline__ unsigned long long sk_warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long u = __shfl_xor_sync(kFull, v, o);
+    v = u > v ? u : v;
+  }
+  return v;
+}
+
 template <int UP, int DOWN, int D, int PS>
-__global__ void __launch_bounds__(kSkThreads, 2)
+__global__ void __launch_bounds__(kSkThreads, kSkCtasPerSm)
 fused_stream_kernel(const __grid_constant__ SkParams P) {
   extern __shared__ __align__(16) unsigned char sk_raw[];
   SkShared& sm = *reinterpret_cast<SkShared*>(sk_raw);
@@ -402,7 +589,14 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
   float* rowbuf = P.work_rows + (long long)blockIdx.x * P.work_stride;
   const unsigned long long total_rows = (unsigned long long)P.recordings * (unsigned)P.channels;
   const bool fix_nan = (P.norm_flags & MPCG_NORM_NAN_TO_NUM) != 0;
+  const uint32_t bar = sk_smem(&sm.bulk_bar);
+  uint32_t bulk_phase = 0;
   int cur_kind = -1;
+  const unsigned long long pol_keep = sk_policy_keep();
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 #if defined(MPCG_FZ_PHASE_CLOCKS) && MPCG_FZ_PHASE_CLOCKS
   long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long ph_last = clock64();
@@ -462,135 +656,292 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
       for (int tile = 0; tile < ntiles; ++tile) {
         const int t0 = tile * kSkTile;
         const int n = min(kSkTile, t_r - t0);
-        sk_resample_tile<UP, DOWN, D, PS>(sig, sm.xs, xr, t_in_r, P.off, t0, n);
-        if (!single) {                                    // park the tile in the row buffer
-          const int nv = (n + 3) >> 2;
-          const float4* s4 = reinterpret_cast<const float4*>(sig);
-          float4* g4 = reinterpret_cast<float4*>(rowbuf + t0);
-          for (int i = tid; i < nv; i += kSkThreads) g4[i] = s4[i];
+        if (tile > 0) {                                   // the previous tile's bulk store has read the tile
+          if (tid == 0) sk_bulk_store_wait();
+          __syncthreads();
         }
-        {                                                 // maxima of the frame pieces inside my warp's share of the tile
+        sk_resample_tile<UP, DOWN, D, PS>(sig, sm.xs, xr, t_in_r, P.off, t0, n);
+        if (!single && tid == 0)                          // park the tile in the row buffer: one bulk copy
+          sk_bulk_store(rowbuf + t0, sig, (uint32_t)((n + 3) >> 2) * 16u);
+        // frame maxima in two steps: every aligned 128-sample span of the tile (branch-free sweep), then one warp
+        // per frame folds its whole spans and rescans only the ragged ends
+        {
           const int ra = warp * (kSkTile / kSkWarps);
-          const int rb = min(ra + kSkTile / kSkWarps, n);
-          int i = ra;
-          while (i < rb) {
-            const int f = (t0 + i) / win_d;
-            if (f >= nframes) break;
-            const int seg_end = min(rb, (f + 1) * win_d - t0);
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
-            int j = i + lane;
-            for (; j + 96 < seg_end; j += 128) {
-              m0 = fmaxf(m0, fabsf(sig[j])); m1 = fmaxf(m1, fabsf(sig[j + 32]));
-              m2 = fmaxf(m2, fabsf(sig[j + 64])); m3 = fmaxf(m3, fabsf(sig[j + 96]));
+#pragma unroll
+          for (int it = 0; it < kSkTile / kSkWarps / 128; ++it) {
+            const float4 v = *reinterpret_cast<const float4*>(sig + ra + it * 128 + 4 * lane);
+            const float m4 = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(m4, 0.f)));   // fmaxf drops NaN
+            if (lane == 0) sm.spanmax[(ra >> 7) + it] = __uint_as_float(m);
+          }
+        }
+        __syncthreads();
+        {
+          const int f_first = t0 / win_d;
+          int f_last = (t0 + n - 1) / win_d;
+          if (f_last > nframes - 1) f_last = nframes - 1;
+          for (int f = f_first + warp; f <= f_last; f += kSkWarps) {
+            const int lo = max(f * win_d - t0, 0), hi = min((f + 1) * win_d - t0, n);
+            const int s_lo = (lo + 127) >> 7, s_hi = hi >> 7;
+            float m = 0.f;
+            if (s_lo < s_hi) {
+              for (int q = s_lo + lane; q < s_hi; q += 32) m = fmaxf(m, sm.spanmax[q]);
+              for (int j = lo + lane; j < (s_lo << 7); j += 32) m = fmaxf(m, fabsf(sig[j]));
+              for (int j = (s_hi << 7) + lane; j < hi; j += 32) m = fmaxf(m, fabsf(sig[j]));
+            } else {
+              for (int j = lo + lane; j < hi; j += 32) m = fmaxf(m, fabsf(sig[j]));
             }
-            for (; j < seg_end; j += 32) m0 = fmaxf(m0, fabsf(sig[j]));
-            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3))));
-            if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(&sm.tops[f]), m);
-            i = seg_end;
+            const unsigned mu = __reduce_max_sync(kFull, __float_as_uint(m));
+            if (lane == 0) sm.tops[f] = fmaxf(sm.tops[f], __uint_as_float(mu));
           }
         }
         __syncthreads();
       }
+      if (!single) {                                      // the parked row is complete and visible
+        if (tid == 0) sk_bulk_store_wait();
+        __syncthreads();
+      }
       SK_STAMP(1);
-      // ---- the Schmidt passes in the reference's order.  Warp 0 decides and flattens; frames it needs that are
-      // not resident are fetched by the whole CTA.  A pass that moves nothing is a fixed point (the reference
-      // would repeat it until max_iterations) and ends the row.
       const int nblk = (win_d + 31) >> 5;
       const int slot_stride = (win_d + 7) & ~3;           // room for the 16-byte phase match
       int nslots = kSkTile / slot_stride;
       if (nslots > kSkSlots) nslots = kSkSlots;
       if (nslots * nblk > kSkBmWords) nslots = kSkBmWords / nblk;
-      if (tid < kSkSlots) sm.slot_frame[tid] = -1;
-      if (tid == 0) sm.victim = 0;
-      if (single) {                                       // every frame is resident: block maxima of all of them
-        for (int q = warp; q < nframes * nblk; q += kSkWarps) {
-          const int f = q / nblk, b = q - f * nblk;
-          const int i = b * 32 + lane;
-          const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(sig[f * win_d + i]) : 0.f, 0.f)));
-          if (lane == 0) sm.d.bm[q] = __uint_as_float(m);
-        }
-      }
-      __syncthreads();
-      const bool sorted_mode = nframes <= 64;
-      if (warp == 0 && sorted_mode) spike_sort_init(sm.d.sorted, sm.tops, nframes);
-      for (;;) {
-        if (warp == 0) {
-          int req = -2;                                   // -2: the row is finished
-          while (passes < P.max_iter) {
-            const SpikeDecision dec = sorted_mode ? spike_sort_decide(sm.d.sorted, nframes, P.threshold, P.median_mode)
-                                                  : spike_decide_warp(sm.tops, nframes, P.threshold, P.median_mode);
-            if (!dec.active) break;
-            float* fr;
-            float* bmf;
-            if (single) {
-              fr = sig + dec.worst * win_d;
-              bmf = sm.d.bm + dec.worst * nblk;
-            } else {
-              int slot = -1;
-              for (int s = 0; s < nslots; ++s)
-                if (sm.slot_frame[s] == dec.worst) slot = s;
-              if (slot < 0) { req = dec.worst; break; }
-              fr = sig + slot * slot_stride + phase_of(rowbuf + (long long)dec.worst * win_d);
-              bmf = sm.d.bm + slot * nblk;
+      bool serial = single || P.trace != nullptr || P.serial_despike || nframes > kSkFastFrames || win_d < 2 ||
+                    win_d > 65535;
+      // ---------------------------------------------------------- parallel rounds
+      // The reference flattens one span per pass, always in the frame holding the largest maximum, until no frame
+      // exceeds threshold * median.  A pass only changes its own frame, and the threshold can only fall, so the
+      // ORDER of the passes does not matter for the samples: every frame above the current threshold must be
+      // flattened until it is not, whatever happens elsewhere.  Rounds: (1) warp 0 derives the threshold and the
+      // list of frames above it from the frame maxima; (2) one warp per listed frame fetches it from the row buffer
+      // and flattens it in its slot, logging each pass; (3) warp 0 judges the outcome and the passes that the
+      // serial order really performs are filled in the row buffer.  All of them are, except when some frame got
+      // STUCK (a pass that moves nothing, e.g. a one-sample spike between two sign flips: the reference then
+      // repeats that pass until max_iterations): the serial order reaches the stuck state with the largest
+      // (maximum, first index) key K* and never leaves it, so exactly the logged passes that started from a key
+      // above K* happen, and the row is finished.  Anything the logs cannot settle exactly (pass budget in reach,
+      // log full) continues on the serial path from the committed state, which is always a state of the serial order.
+      if (!serial) {
+        for (int round = 0;; ++round) {
+          if (warp == 0) {                                  // threshold + frames above it
+            const int nf = nframes;
+            const float v0 = lane < nf ? sm.tops[lane] : -1.f, v1 = lane + 32 < nf ? sm.tops[lane + 32] : -1.f;
+            int less0 = 0, leq0 = 0, less1 = 0, leq1 = 0;
+#pragma unroll 4
+            for (int j = 0; j < nf; ++j) {
+              const float vj = sm.tops[j];
+              less0 += (vj < v0); leq0 += (vj <= v0);
+              less1 += (vj < v1); leq1 += (vj <= v1);
             }
-            const float old_top = sm.tops[dec.worst];
-            int peak, lo, hi;
-            bool changed;
-            float new_top;
-            spike_pass_warp(fr, win_d, bmf, nblk, old_top, peak, lo, hi, changed, new_top);
-            if (!single) {                                // write the flattened span through to the row buffer
-              float* g = rowbuf + (long long)dec.worst * win_d;
-              for (int i = lo + lane; i < hi; i += 32) g[i] = kSpikeFill;
+            const int k_lo = (nf - 1) >> 1, k_hi = nf >> 1;
+            float c_lo = -1.f, c_hi = -1.f;                 // maxima are >= 0, so -1 means "not mine"
+            if (lane < nf) {
+              if (less0 <= k_lo && k_lo < leq0) c_lo = v0;
+              if (less0 <= k_hi && k_hi < leq0) c_hi = v0;
+            }
+            if (lane + 32 < nf) {
+              if (less1 <= k_lo && k_lo < leq1) c_lo = fmaxf(c_lo, v1);
+              if (less1 <= k_hi && k_hi < leq1) c_hi = fmaxf(c_hi, v1);
+            }
+            const float lo_mid = warp_max(c_lo), hi_mid = warp_max(c_hi);
+            SkCut cut;
+            cut.mode = P.median_mode;
+            cut.cutf = __fmul_rn((float)P.threshold, lo_mid);
+            const double med = ((double)lo_mid + (double)hi_mid) * 0.5;
+            cut.cutd = P.threshold * med;
+            const bool open = passes < P.max_iter && (P.median_mode == MPCG_MEDIAN_LOWER || med != 0.0);
+            const bool a0 = open && lane < nf && cut.exceeds(v0), a1 = open && lane + 32 < nf && cut.exceeds(v1);
+            const unsigned m0 = __ballot_sync(kFull, a0), m1 = __ballot_sync(kFull, a1);
+            const unsigned below = (1u << lane) - 1u;
+            if (a0) sm.d.act[__popc(m0 & below)] = (unsigned char)lane;
+            if (a1) sm.d.act[__popc(m0) + __popc(m1 & below)] = (unsigned char)(lane + 32);
+            if (lane == 0) {
+              sm.d.nact = __popc(m0) + __popc(m1); sm.d.cutf = cut.cutf; sm.d.cutd = cut.cutd;
+              sm.d.lo_mid = lo_mid; sm.d.hi_mid = hi_mid;
+            }
+          }
+          __syncthreads();
+          const int nact = sm.d.nact;
+          if (nact == 0) break;
+          {                                                 // the listed frames, nslots at a time, one warp each
+            SkCut cut;
+            cut.mode = P.median_mode; cut.cutf = sm.d.cutf; cut.cutd = sm.d.cutd;
+            if (warp < nslots)
+              for (int slot = warp; slot < nact; slot += nslots) {
+                const int f = sm.d.act[slot];
+                sk_fast_frame(sm, sig + warp * slot_stride, sm.d.bm + warp * nblk, rowbuf + (long long)f * win_d, win_d,
+                              sm.tops[f], slot, cut);
+              }
+          }
+          __syncthreads();
+          if (warp == 0) {                                  // the round's outcome
+            const bool h0 = lane < nact, h1 = lane + 32 < nact;
+            const int me0 = h0 ? sm.d.xmeta[lane] : 0, me1 = h1 ? sm.d.xmeta[lane + 32] : 0;
+            const bool over = __any_sync(kFull, ((me0 | me1) >> 9) & 1);
+            unsigned long long ks = 0ull;
+            if ((me0 >> 8) & 1) ks = spike_key(sm.d.xtop[lane], sm.d.act[lane]);
+            if ((me1 >> 8) & 1) {
+              const unsigned long long k1 = spike_key(sm.d.xtop[lane + 32], sm.d.act[lane + 32]);
+              ks = k1 > ks ? k1 : ks;
+            }
+            const unsigned long long kstar = sk_warp_max_u64(ks);
+            int total = (me0 & 0xff) + (me1 & 0xff);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+            // (with a stuck frame fewer passes may count, plus the stuck pass itself: total + 1 bounds both cases)
+            const bool hand_over = over || (long long)passes + total + (kstar != 0ull ? 1 : 0) > (long long)P.max_iter;
+            // If no flattened frame fell below the old middle value(s), the median and with it the threshold are what
+            // they were: nothing else can exceed it and the row is finished without another round.
+            const float floor_v = P.median_mode == MPCG_MEDIAN_LOWER ? sm.d.lo_mid : sm.d.hi_mid;
+            const bool same_median = __all_sync(kFull, (!h0 || sm.d.xtop[lane] >= floor_v) &&
+                                                           (!h1 || sm.d.xtop[lane + 32] >= floor_v));
+            if (!hand_over && kstar == 0ull) {
+              if (h0) sm.tops[sm.d.act[lane]] = sm.d.xtop[lane];
+              if (h1) sm.tops[sm.d.act[lane + 32]] = sm.d.xtop[lane + 32];
             }
             if (lane == 0) {
-              sm.tops[dec.worst] = new_top;
-              if (P.trace && passes < P.trace_cap) {
-                int* tr = P.trace + ((long long)row * P.trace_cap + passes) * 4;
-                tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
-              }
+              sm.d.verdict = hand_over ? 2 : (kstar != 0ull ? 1 : (same_median ? 3 : 0));
+              sm.d.total = total;
+              sm.d.kstar = kstar;
             }
-            __syncwarp();
-            ++passes;
-            if (!changed) break;
-            if (sorted_mode) {
-              if (new_top <= old_top) spike_sort_update(sm.d.sorted, dec.worst, old_top, new_top);
-              else spike_sort_init(sm.d.sorted, sm.tops, nframes);      // the fill raised a tiny frame: sort afresh
-            }
-          }
-          if (lane == 0) sm.req = req;
-        }
-        __syncthreads();
-        const int req = sm.req;
-        if (req < 0) break;
-        {                                                 // fetch frame `req` into the next cache slot
-          const int slot = sm.victim;
-          const float* g = rowbuf + (long long)req * win_d;
-          float* fr = sig + slot * slot_stride + phase_of(g);
-          {
-            int head = (int)(((16u - ((uintptr_t)g & 15u)) & 15u) >> 2);
-            if (head > win_d) head = win_d;
-            if (tid < head) fr[tid] = ld_cg(g + tid);
-            const int nvec = (win_d - head) >> 2;
-            const float4* gv = reinterpret_cast<const float4*>(g + head);
-            float4* sv = reinterpret_cast<float4*>(fr + head);
-            for (int i = tid; i < nvec; i += kSkThreads) sv[i] = ld_cg4(gv + i);
-            const int done = head + (nvec << 2);
-            if (tid < win_d - done) fr[done + tid] = ld_cg(g + done + tid);
           }
           __syncthreads();
-          for (int b = warp; b < nblk; b += kSkWarps) {
-            const int i = b * 32 + lane;
-            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(fr[i]) : 0.f, 0.f)));
-            if (lane == 0) sm.d.bm[slot * nblk + b] = __uint_as_float(m);
+          const int verdict = sm.d.verdict;
+          const unsigned long long kstar = sm.d.kstar;
+          if (verdict != 2) {
+            for (int slot = warp; slot < nact; slot += kSkWarps) {   // fill the spans of the passes that happen
+              const int f = sm.d.act[slot];
+              const int k = sm.d.xmeta[slot] & 0xff;
+              int jc = k;
+              if (verdict == 1) {                             // only passes that started above K* (all of the stuck frame's)
+                if (spike_key(sm.d.seq[slot][k], f) != kstar)
+                  jc = __popc(__ballot_sync(kFull, lane < k && spike_key(sm.d.seq[slot][lane < k ? lane : 0], f) > kstar));
+                if (lane == 0) sm.d.xj[slot] = jc;
+              }
+              float* g = rowbuf + (long long)f * win_d;
+              for (int j = 0; j < jc; ++j) {
+                const int lo = sm.d.span[slot][j][0], hi = sm.d.span[slot][j][1];
+                for (int i = lo + lane; i < hi; i += 32) g[i] = kSpikeFill;
+              }
+            }
           }
-          if (tid == 0) {
-            sm.slot_frame[slot] = req;
-            sm.victim = (slot + 1) % nslots;
+          if (verdict == 2) { serial = true; break; }
+          if (verdict == 1) {                                 // exact pass count: what really counted + the pass that moves nothing
+            __syncthreads();
+            if (warp == 0) {
+              int t = (lane < nact ? sm.d.xj[lane] : 0) + (lane + 32 < nact ? sm.d.xj[lane + 32] : 0);
+#pragma unroll
+              for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+              if (lane == 0) sm.d.total = t + 1;
+            }
+            __syncthreads();
+            passes += sm.d.total;
+            break;
           }
+          passes += sm.d.total;
+          if (verdict == 3) break;
           __syncthreads();
         }
       }
-      if (P.edits && tid == 0) P.edits[row] = passes;     // (warp 0 counted them)
+      // ---------------------------------------------------------- serial path (reference order, pass by pass)
+      // Warp 0 decides and flattens; frames it needs that are not resident are fetched by the whole CTA.  A pass
+      // that moves nothing is a fixed point (the reference would repeat it until max_iterations) and ends the row.
+      if (serial) {
+        __syncthreads();
+        if (tid < kSkSlots) sm.slot_frame[tid] = -1;
+        if (tid == 0) sm.victim = 0;
+        if (single) {                                     // every frame is resident: block maxima of all of them
+          for (int q = warp; q < nframes * nblk; q += kSkWarps) {
+            const int f = q / nblk, b = q - f * nblk;
+            const int i = b * 32 + lane;
+            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(sig[f * win_d + i]) : 0.f, 0.f)));
+            if (lane == 0) sm.d.bm[q] = __uint_as_float(m);
+          }
+        }
+        __syncthreads();
+        const bool sorted_mode = nframes <= 64;
+        if (warp == 0 && sorted_mode) spike_sort_init(sm.d.sorted, sm.tops, nframes);
+        for (;;) {
+          if (warp == 0) {
+            int req = -2;                                 // -2: the row is finished
+            while (passes < P.max_iter) {
+              const SpikeDecision dec = sorted_mode ? spike_sort_decide(sm.d.sorted, nframes, P.threshold, P.median_mode)
+                                                    : spike_decide_warp(sm.tops, nframes, P.threshold, P.median_mode);
+              if (!dec.active) break;
+              float* fr;
+              float* bmf;
+              if (single) {
+                fr = sig + dec.worst * win_d;
+                bmf = sm.d.bm + dec.worst * nblk;
+              } else {
+                int slot = -1;
+                for (int s = 0; s < nslots; ++s)
+                  if (sm.slot_frame[s] == dec.worst) slot = s;
+                if (slot < 0) { req = dec.worst; break; }
+                fr = sig + slot * slot_stride + phase_of(rowbuf + (long long)dec.worst * win_d);
+                bmf = sm.d.bm + slot * nblk;
+              }
+              const float old_top = sm.tops[dec.worst];
+              int peak, lo, hi;
+              bool changed;
+              float new_top;
+              spike_pass_warp(fr, win_d, bmf, nblk, old_top, peak, lo, hi, changed, new_top);
+              if (!single) {                              // write the flattened span through to the row buffer
+                float* g = rowbuf + (long long)dec.worst * win_d;
+                for (int i = lo + lane; i < hi; i += 32) g[i] = kSpikeFill;
+              }
+              if (lane == 0) {
+                sm.tops[dec.worst] = new_top;
+                if (P.trace && passes < P.trace_cap) {
+                  int* tr = P.trace + ((long long)row * P.trace_cap + passes) * 4;
+                  tr[0] = dec.worst; tr[1] = peak; tr[2] = lo; tr[3] = hi;
+                }
+              }
+              __syncwarp();
+              ++passes;
+              if (!changed) break;
+              if (sorted_mode) {
+                if (new_top <= old_top) spike_sort_update(sm.d.sorted, dec.worst, old_top, new_top);
+                else spike_sort_init(sm.d.sorted, sm.tops, nframes);    // the fill raised a tiny frame: sort afresh
+              }
+            }
+            if (lane == 0) sm.req = req;
+          }
+          __syncthreads();
+          const int req = sm.req;
+          if (req < 0) break;
+          {                                               // fetch frame `req` into the next cache slot
+            const int slot = sm.victim;
+            const float* g = rowbuf + (long long)req * win_d;
+            float* fr = sig + slot * slot_stride + phase_of(g);
+            {
+              int head = (int)(((16u - ((uintptr_t)g & 15u)) & 15u) >> 2);
+              if (head > win_d) head = win_d;
+              if (tid < head) fr[tid] = ld_cg(g + tid);
+              const int nvec = (win_d - head) >> 2;
+              const float4* gv = reinterpret_cast<const float4*>(g + head);
+              float4* sv = reinterpret_cast<float4*>(fr + head);
+              for (int i = tid; i < nvec; i += kSkThreads) sv[i] = ld_cg4(gv + i);
+              const int done = head + (nvec << 2);
+              if (tid < win_d - done) fr[done + tid] = ld_cg(g + done + tid);
+            }
+            __syncthreads();
+            for (int b = warp; b < nblk; b += kSkWarps) {
+              const int i = b * 32 + lane;
+              const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(fr[i]) : 0.f, 0.f)));
+              if (lane == 0) sm.d.bm[slot * nblk + b] = __uint_as_float(m);
+            }
+            if (tid == 0) {
+              sm.slot_frame[slot] = req;
+              sm.victim = (slot + 1) % nslots;
+            }
+            __syncthreads();
+          }
+        }
+      }
+      if (P.edits && tid == 0) P.edits[row] = passes;     // (thread 0 counted on either path)
+      if (!single) sk_fence_async_global();               // the filled spans are read back by bulk (async-proxy) loads
       SK_STAMP(2);
     } else if (P.edits && tid == 0) {
       P.edits[row] = 0;
@@ -600,17 +951,17 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     double lsum = 0.0;
     float lmin = INFINITY, lmax = -INFINITY;
     if (tid < 4) sm.carry[tid] = 0.0;
+    int kf = 0;                                           // first window that may still intersect the coming tiles
     for (int tile = 0; tile < ntiles; ++tile) {
       const int t0 = tile * kSkTile;
       const int n = min(kSkTile, t_r - t0);
       if (nframes > 0) {
-        if (!single) {                                    // the despiked tile comes back from the row buffer
+        if (!single) {                                    // the despiked tile comes back from the row buffer: one bulk copy
+          sk_fence_async_smem();
           __syncthreads();                                // (the previous tile's window stores have left shared memory)
-          const int nv = (n + 3) >> 2;
-          const float4* g4 = reinterpret_cast<const float4*>(rowbuf + t0);
-          float4* s4 = reinterpret_cast<float4*>(sig);
-          for (int i = tid; i < nv; i += kSkThreads) s4[i] = ld_cg4(g4 + i);
-          __syncthreads();
+          if (tid == 0) sk_bulk_load(sig, rowbuf + t0, (uint32_t)((n + 3) >> 2) * 16u, bar);
+          sk_bar_wait(bar, bulk_phase);
+          bulk_phase ^= 1u;
         }
       } else {
         __syncthreads();
@@ -623,7 +974,7 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
       else sk_filter_tile<1>(P, sm, sig, n, fix_nan, lsum, lmin, lmax);
       __syncthreads();
       SK_STAMP(4);
-      if (!single) sk_store_windows(sig, obase, t0, n, P.start, P.win, P.hop, nwin, so_k, so_j);
+      if (!single) sk_store_windows(sig, obase, t0, n, P.start, P.win, P.hop, nwin, so_k, so_j, kf, pol_keep);
       SK_STAMP(5);
     }
 
@@ -651,6 +1002,10 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     __syncthreads();
     const float inv_f = sm.fscr[0], shift_f = sm.fscr[1];
     auto scaled = [&](float s) { return fminf(fmaxf(fmaf(s, inv_f, shift_f), -1.f), 1.f); };
+    auto scaled4 = [&](float4 a) {
+      a.x = scaled(a.x); a.y = scaled(a.y); a.z = scaled(a.z); a.w = scaled(a.w);
+      return a;
+    };
 
     // ------------------------------------------------------------ C. normalise the row's windows
     // samples of the row that the windows hold: all of every window, except a short row's single zero-padded window
@@ -675,18 +1030,14 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
       const long long nvec = (valid - head) >> 2;
       float4* p4 = reinterpret_cast<float4*>(p + head);
       long long i = tid;
-      for (; i + kSkThreads < nvec; i += 2 * kSkThreads) {
-        float4 a = ld_cg4(p4 + i), b = ld_cg4(p4 + i + kSkThreads);
-        a.x = scaled(a.x); a.y = scaled(a.y); a.z = scaled(a.z); a.w = scaled(a.w);
-        b.x = scaled(b.x); b.y = scaled(b.y); b.z = scaled(b.z); b.w = scaled(b.w);
-        st_stream4(p4 + i, a);
-        st_stream4(p4 + i + kSkThreads, b);
+      for (; i + 7 * kSkThreads < nvec; i += 8 * kSkThreads) {          // eight 128-bit loads in flight per thread
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld_cg4(p4 + i + u * kSkThreads);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) st_stream4(p4 + i + u * kSkThreads, scaled4(v[u]));
       }
-      for (; i < nvec; i += kSkThreads) {
-        float4 a = ld_cg4(p4 + i);
-        a.x = scaled(a.x); a.y = scaled(a.y); a.z = scaled(a.z); a.w = scaled(a.w);
-        st_stream4(p4 + i, a);
-      }
+      for (; i < nvec; i += kSkThreads) st_stream4(p4 + i, scaled4(ld_cg4(p4 + i)));
       const long long done = head + (nvec << 2);
       if (tid < valid - done) st_stream(p + done + tid, scaled(ld_cg(p + done + tid)));
     } else {
