@@ -10,8 +10,8 @@ from wav2vec_heart_sounds_b200 import _lib
 from wav2vec_heart_sounds_b200.synth import synth_pair
 spec = pkg.WindowSpec(4.0)
 x = synth_pair(1024, 60000, 2000, seed=1234, device="cuda")
-names = ["row setup", "A: resample+maxima+park", "A: despike passes", "B: tile load/resample", "B: filter", "B: window store",
-         "stats + C: rescale"]
+names = ["row setup", "A: resample+maxima+park", "A: despike passes", "B: tile load/resample", "B: filter", "B: park un-normalised",
+         "stats + C: windows"]
 cases = {"pcg+ecg": (x, ("pcg", "ecg")), "pcg only": (x[:, :1].contiguous(), ("pcg",)), "ecg only": (x[:, 1:].contiguous(), ("ecg",))}
 for label, (xx, kinds) in cases.items():
     out, edits = pkg.preprocess_segment(xx, 2000, 4125, spec, kinds=kinds, fused=True, return_edits=True)

@@ -5,7 +5,7 @@
 #include <stdlib.h>
 
 namespace mpcg {
-#include "fused_instances.h"
+#include "stream_instances.h"
 #define MPCG_SK_EXTERN_(...) MPCG_SK_EXTERN(__VA_ARGS__)
 #define MPCG_SK_EXTERN(U, DN, DD, PS) extern template int sk_launch<U, DN, DD, PS>(const SkParams&, size_t, int, cudaStream_t);
 MPCG_SK_EXTERN_(1, 1, 1, 1)
@@ -106,7 +106,7 @@ extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t r
   if (any_despike && d->despike_win >= 1) {
     if (d->despike_win > 0x3fffffff) return MPCG_ERANGE;
     // the frame cache holds whole frames; the frame-maxima table holds kSkMaxFrames entries
-    if (d->t_out > kSkTile && d->despike_win + 7 > kSkTile) return MPCG_EUNSUPPORTED;
+    if (d->t_out > kSkTile && d->despike_win + 7 > kSkGroups * kSkBuf) return MPCG_EUNSUPPORTED;
     if (d->t_out / d->despike_win > kSkMaxFrames) return MPCG_EUNSUPPORTED;
     if ((d->despike_win + 31) / 32 > kSkBmWords) return MPCG_EUNSUPPORTED;
   }
@@ -156,7 +156,7 @@ extern "C" int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t r
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(float) * kSkWorkHeader, stream);
   if (e != cudaSuccess) return (int)e;
   if ((long long)ctas > rows) ctas = (int)rows;
-  const size_t smem = sizeof(SkShared) + (size_t)(kSkTile + 2 * kSkGuard + 8) * sizeof(float);
+  const size_t smem = sizeof(SkShared) + (size_t)kSkGroups * kSkBuf * sizeof(float);
 
   if (identity) return sk_launch<1, 1, 1, 1>(P, smem, ctas, stream);
   const int D = d->taps_per_phase;

@@ -31,24 +31,30 @@
 namespace mpcg {
 
 #ifndef MPCG_SK_THREADS
-#define MPCG_SK_THREADS 512                       // threads per CTA: 512 (two CTAs per SM) or 1024 (one)
+#define MPCG_SK_THREADS 512                       // threads per CTA: 512 (one tile group, two CTAs per SM) or 1024 (two groups, one CTA per SM)
 #endif
 constexpr int kSkThreads = MPCG_SK_THREADS;
+constexpr int kSkGT = 512;                        // threads of a tile group
+constexpr int kSkGW = kSkGT / 32;                 // warps of a tile group
+constexpr int kSkGroups = kSkThreads / kSkGT;     // tile groups per CTA: they take alternate tiles of the row
 constexpr int kSkWarps = kSkThreads / 32;
 constexpr int kSkCtasPerSm = 1024 / kSkThreads;
-constexpr int kSkWarpLevels = kSkWarps == 32 ? 5 : 4;      // Hillis-Steele levels of the cross-warp scan
 constexpr int kSkL = 36;                          // samples per filter chunk; 4 x odd: 128-bit shared accesses without bank conflicts
-constexpr int kSkTile = kSkThreads * kSkL;        // samples per tile (18 432)
+constexpr int kSkTile = kSkGT * kSkL;             // samples per tile (18 432)
 constexpr int kSkGuard = 40;                      // floats before and after the tile that edge frames of the resampler spill into
-constexpr int kSkStageWords = 9 * kSkThreads + 128;   // resampler input staging: teams x block
+constexpr int kSkBuf = kSkTile + 2 * kSkGuard + 8;    // floats of one group's tile buffer
+constexpr int kSkStageWords = 9 * kSkGT + 128;    // resampler input staging of one group: teams x block
 constexpr int kSkMaxFrames = 1024;                // despike frames per row (a 30 s recording has 60)
-constexpr int kSkSlots = 8;                       // despike frame cache (streamed rows)
+constexpr int kSkSlots = 16;                      // despike frame cache (streamed rows)
 constexpr int kSkBmWords = 1536;                  // 32-sample block maxima of the cached frames
 constexpr int kSkWorkHeader = 64;                 // floats at the start of the workspace (ticket counter)
 constexpr int kSkFastFrames = 64;                 // frames per row the parallel despike rounds take
 constexpr int kSkLogCap = 16;                     // passes per frame and round they log before handing over to the serial order
+// named barriers: 0 = CTA, 1..8 = resampler teams, 9.. = tile groups, 11.. = carry hand-over between groups
+constexpr int kSkBarGroup = 9;
+constexpr int kSkBarCarry = 11;
 static_assert(kSkL % 4 == 0 && ((kSkL / 4) & 1) == 1, "chunk length must be 4 x odd");
-static_assert(kSkWarps == 16 || kSkWarps == 32, "the cross-warp scan is written for 16 or 32 warps");
+static_assert(kSkGroups == 1 || kSkGroups == 2, "one or two tile groups");
 
 struct SkKind {                                   // per channel kind (PCG / ECG): despike on/off + its filter
   int despike;
@@ -88,10 +94,10 @@ struct SkParams {
   SkKind kinds[2];
 };
 
-struct SkShared {
+struct SkGroupShared {                            // private to one tile group
   union {                                         // phases that follow one another share this space:
     float xs[kSkStageWords];                      //   resampler input staging
-    struct {                                      //   despike
+    struct {                                      //   despike (group 0's copy is the CTA's)
       float bm[kSkBmWords];
       SpikeSorted sorted;
       // parallel rounds (see the kernel): outcome and pass log of every frame above the round's threshold
@@ -107,14 +113,17 @@ struct SkShared {
       unsigned long long kstar;
     } d;
   };
-  unsigned long long bulk_bar;                    // mbarrier of the bulk (TMA) tile loads
-  unsigned long long pad2_;
-  float tops[kSkMaxFrames];                       // frame maxima of the current row
+  double wagg[kSkGW][4];                          // warp aggregates
+  double wcar[kSkGW][4];                          // state at the start of each warp's first chunk
   float spanmax[kSkTile / 128];                   // maxima of the tile's aligned 128-sample spans
+  unsigned long long bulk_bar;                    // mbarrier of this group's bulk (TMA) tile loads
+  unsigned long long pad_;
+};
+struct SkShared {
+  SkGroupShared grp[kSkGroups];
+  float tops[kSkMaxFrames];                       // frame maxima of the current row
   double mtab[16][32];                            // M^lane of the current kind, element-major
-  double wagg[kSkWarps][4];                       // warp aggregates
-  double wcar[kSkWarps][4];                       // state at the start of each warp's first chunk
-  double carry[4];                                // state at the start of the next tile
+  double carry[4];                                // filter state at the start of the next tile
   double rsum[kSkWarps];
   float rlo[kSkWarps], rhi[kSkWarps];
   float fscr[8];
@@ -123,8 +132,19 @@ struct SkShared {
   unsigned int ticket;
   int pad_;
 };
-static_assert(sizeof(((SkShared*)0)->d) <= sizeof(float) * kSkStageWords, "despike scratch must fit behind the staging area");
-static_assert(sizeof(SkShared) % 16 == 0, "the sample tile behind SkShared must stay 16-byte aligned");
+static_assert(sizeof(((SkGroupShared*)0)->d) <= sizeof(float) * kSkStageWords, "despike scratch must fit behind the staging area");
+static_assert(sizeof(SkShared) % 16 == 0 && sizeof(SkGroupShared) % 16 == 0, "the sample tiles behind SkShared must stay 16-byte aligned");
+
+// What a thread needs to know about its tile group.
+struct SkCtx {
+  int g, gt, gw, lane;                            // group, thread / warp inside the group, lane
+  float* sig;                                     // the group's tile buffer (past its leading guard)
+  SkGroupShared* gs;
+  __device__ __forceinline__ void sync() const {  // barrier of the group
+    if constexpr (kSkGroups == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(kSkBarGroup + g), "r"(kSkGT) : "memory");
+  }
+};
 
 __device__ __forceinline__ float4 ld_cg4(const float4* p) {      // re-read of data this CTA wrote: L2, not L1
   float4 v;
@@ -158,54 +178,44 @@ __device__ __forceinline__ void sk_bulk_store_wait() { asm volatile("cp.async.bu
 __device__ __forceinline__ void sk_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sk_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// un-normalised windows are written now and read back once by the rescale pass of the same row: ask L2 to keep them
-__device__ __forceinline__ unsigned long long sk_policy_keep() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void st_keep4(float4* p, float4 v, unsigned long long pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void st_keep(float* p, float v, unsigned long long pol) {
-  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
-}
-
-__device__ __forceinline__ void sk_team_sync(int team, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(count) : "memory");
+__device__ __forceinline__ void sk_team_sync(int bar_id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(count) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Resample samples [t0, t0 + n) of the row into sig[0, n).  Teams of PS warps walk the tile in blocks of frames:
-// coalesced loads -> registers (prefetched one block ahead) -> staging in shared memory -> each warp of the team
-// computes its phase group.  Edge frames spill into the guard floats around the tile.  Rows that start on a
-// 16-byte boundary take the vector form (RsVec: 128-bit loads, stores and staged reads), others the scalar one.
-// Ends with a CTA barrier.  Not inlined: the kernel calls it from two places.
+// Resample samples [t0, t0 + n) of the row into the group's tile.  Teams of PS warps walk the tile in blocks of
+// frames: coalesced loads -> registers (prefetched one block ahead) -> staging in shared memory -> each warp of the
+// team computes its phase group.  Edge frames spill into the guard floats around the tile.  Rows that start on a
+// 16-byte boundary take the vector form (RsVec: 128-bit loads, stores and staged reads), others the scalar one;
+// integer up-sampling takes the run form (RsRun).  Ends with a group barrier.  Not inlined: two call sites.
 template <int UP, int DOWN, int D, int PS>
-__device__ __noinline__ void sk_resample_tile(float* sig, float* xs_all, const float* __restrict__ xr, int t_in, int off,
-                                              int t0, int n) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __noinline__ void sk_resample_tile(const SkCtx c, const float* __restrict__ xr, int t_in, int off, int t0, int n) {
+  const int gt = c.gt, lane = c.lane, gw = c.gw;
+  // (the pointers arrive through a struct in a non-inlined call: tell the compiler again that they are shared memory)
+  float* sig = reinterpret_cast<float*>(__cvta_shared_to_generic(__cvta_generic_to_shared(c.sig)));
+  float* xs_all = reinterpret_cast<float*>(__cvta_shared_to_generic(__cvta_generic_to_shared(c.gs->xs)));
   if constexpr (UP == DOWN) {
-    for (int i = tid; i < n; i += kSkThreads) sig[i] = ld_stream(xr + t0 + i);
+    for (int i = gt; i < n; i += kSkGT) sig[i] = ld_stream(xr + t0 + i);
   } else {
-    constexpr int NTEAMS = kSkWarps / PS;
-    static_assert(kSkWarps % PS == 0 && (PS == 1 || NTEAMS <= 15), "teams map onto named barriers 1..15");
+    constexpr int NTEAMS = kSkGW / PS;
+    static_assert(kSkGW % PS == 0 && (PS == 1 || kSkGroups * NTEAMS <= 8), "teams map onto named barriers 1..8");
     static_assert(UP - 1 <= kSkGuard, "guard too small");
-    const int team = warp / PS, grp = warp - team * PS;
+    const int team = gw / PS, grp = gw - team * PS;
+    const int team_bar = 1 + c.g * NTEAMS + team;
     if constexpr (DOWN == 1 && UP % 4 == 0) {             // integer up-sampling: runs of five frames per lane
       using T = RsRun<UP, D>;
-      static_assert(kSkWarps * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
+      static_assert(kSkGW * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
       static_assert(T::FR * UP - 1 <= kSkGuard && kSkTile % UP == 0, "guard too small for a run past the tile end");
-      float* xs = xs_all + warp * T::WORDS;
+      float* xs = xs_all + gw * T::WORDS;
       const int f_lo = t0 / UP, f_hi = (t0 + n - 1) / UP;
       const int nblk = (f_hi - f_lo + T::FB) / T::FB;
       float pre[T::NPRE];
-      int blk = warp;
+      int blk = gw;
       if (blk < nblk) T::fetch(pre, xr, (long long)(f_lo + blk * T::FB), t_in, lane);
-      for (; blk < nblk; blk += kSkWarps) {
+      for (; blk < nblk; blk += kSkGW) {
         T::commit(xs, pre, lane);
         __syncwarp();
-        if (blk + kSkWarps < nblk) T::fetch(pre, xr, (long long)(f_lo + (blk + kSkWarps) * T::FB), t_in, lane);
+        if (blk + kSkGW < nblk) T::fetch(pre, xr, (long long)(f_lo + (blk + kSkGW) * T::FB), t_in, lane);
         const int f = f_lo + blk * T::FB + lane * T::FR;
         if (f <= f_hi) T::run(xs, lane, sig + (f * UP - t0));
         __syncwarp();
@@ -214,7 +224,7 @@ __device__ __noinline__ void sk_resample_tile(float* sig, float* xs_all, const f
       using T = RsVec<UP, DOWN, D, PS>;
       static_assert(NTEAMS * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
       static_assert((T::ALIGN_F - 1) * UP + UP - 1 <= kSkGuard, "guard too small for the aligned block start");
-      const int tt = tid - team * T::TEAM;
+      const int tt = gt - team * T::TEAM;
       float* xs = xs_all + team * T::WORDS;
       const int f_lo = (t0 / UP) & ~(T::ALIGN_F - 1), f_hi = (t0 + n - 1) / UP;
       const int nblk = (f_hi - f_lo + T::FB) / T::FB;
@@ -223,17 +233,17 @@ __device__ __noinline__ void sk_resample_tile(float* sig, float* xs_all, const f
       if (blk < nblk) T::fetch(pre, xr, f_lo + blk * T::FB, t_in, tt);
       for (; blk < nblk; blk += NTEAMS) {
         T::commit(xs, pre, tt);
-        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team_bar, T::TEAM);
         if (blk + NTEAMS < nblk)                          // next block's loads fly while this one is computed
           T::fetch(pre, xr, f_lo + (blk + NTEAMS) * T::FB, t_in, tt);
         const int f = f_lo + blk * T::FB + lane * T::FR;
         if (f <= f_hi) T::template dispatch<0>(grp, xs, lane, sig + (f * UP - t0));
-        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team_bar, T::TEAM);
       }
     } else {
       using T = RsTeam<UP, DOWN, D, PS>;
       static_assert(NTEAMS * T::WORDS <= kSkStageWords, "staging buffer too small for this resampler instance");
-      const int tt = tid - team * T::TEAM;
+      const int tt = gt - team * T::TEAM;
       float* xs = xs_all + team * T::WORDS;
       const int f_lo = t0 / UP, f_hi = (t0 + n - 1) / UP;
       const int nblk = (f_hi - f_lo + T::FB) / T::FB;
@@ -242,17 +252,17 @@ __device__ __noinline__ void sk_resample_tile(float* sig, float* xs_all, const f
       if (blk < nblk) T::fetch(pre, xr, (long long)(f_lo + blk * T::FB) * DOWN + off, t_in, tt);
       for (; blk < nblk; blk += NTEAMS) {
         T::commit(xs, pre, tt);
-        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team_bar, T::TEAM);
         if (blk + NTEAMS < nblk)
           T::fetch(pre, xr, (long long)(f_lo + (blk + NTEAMS) * T::FB) * DOWN + off, t_in, tt);
         const int f = f_lo + blk * T::FB + lane;
         if (f <= f_hi) T::template dispatch<0>(grp, xs, lane, sig + (f * UP - t0));
-        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team, T::TEAM);
+        if constexpr (PS == 1) __syncwarp(); else sk_team_sync(team_bar, T::TEAM);
       }
     }
   }
   sk_fence_async_smem();                                  // the tile may leave through a bulk (async-proxy) store
-  __syncthreads();
+  c.sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -282,14 +292,18 @@ __device__ __forceinline__ float sk_fix(float v) {        // torch.nan_to_num
   return v;
 }
 
-// Low-pass + high-pass of the tile in place: sig[0, kSkTile) holds the samples (zero beyond the row), of which the
-// first n_valid belong to the row.  The state enters and leaves through sm.carry.  (sum, min, max) of the valid
-// outputs are added to the caller's running statistics.  Ends WITHOUT a barrier after the last write.
+// Low-pass + high-pass of the group's tile in place: sig[0, kSkTile) holds the samples (zero beyond the row), of
+// which the first n_valid belong to the row.  The filter state enters and leaves through sm.carry; with two tile
+// groups the tiles of a row alternate between them, and the group working on tile t receives the state from the
+// group that owns tile t - 1 over a named barrier (only the two scanning warps meet there: the state is known as
+// soon as that tile's chunk aggregates are scanned, long before its samples are written).  (sum, min, max) of the
+// valid outputs are added to the caller's running statistics.  Ends WITHOUT a barrier after the last write.
 template <int K>
-__device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, float* sig, int n_valid, bool fix_nan,
-                                               double& lsum, float& lmin, float& lmax) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* mine = sig + tid * kSkL;
+__device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, const SkCtx c, int tile, int ntiles, int tile_warps,
+                                               int n_valid, bool fix_nan, double& lsum, float& lmin, float& lmax) {
+  const int gt = c.gt, lane = c.lane, gw = c.gw;
+  SkGroupShared& gs = *c.gs;
+  float* mine = c.sig + gt * kSkL;
   // ---- pass 1: zero-state end state of my chunk, p = sum_j A^(L-1-j) B x[j]
   double p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -314,34 +328,38 @@ __device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, 
   }
   if (lane == 31) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) sm.wagg[warp][s] = p[s];
+    for (int s = 0; s < 4; ++s) gs.wagg[gw][s] = p[s];
   }
-  __syncthreads();
-  // ---- warp 0 chains the 16 warp aggregates: S_w = M^32 S_(w-1) + agg_w, S_(-1) = the state carried into the tile
-  if (warp == 0) {
+  c.sync();
+  // ---- the group's warp 0 chains the 16 warp aggregates: S_w = M^32 S_(w-1) + agg_w, S_(-1) = the state carried in
+  if (gw == 0) {
     double v[4], c0[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      v[s] = (lane < kSkWarps) ? sm.wagg[lane][s] : 0.0;
-      c0[s] = sm.carry[s];
-    }
+    for (int s = 0; s < 4; ++s) v[s] = (lane < kSkGW) ? gs.wagg[lane][s] : 0.0;
+    if (kSkGroups > 1 && tile > 0)                        // the state after tile - 1, from the other group's scanning warp
+      asm volatile("bar.sync %0, 64;" ::"r"(kSkBarCarry + (tile & 1)) : "memory");
+#pragma unroll
+    for (int s = 0; s < 4; ++s) c0[s] = sm.carry[s];
     if (lane == 0) sk_mv_acc<K, 5>(P, c0, v);
     double u[4];
 #define MPCG_SK_LEVEL(DD)                                                        \
     _Pragma("unroll") for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, v[s], 1 << DD); \
     if (lane >= (1 << DD)) sk_mv_acc<K, 5 + DD>(P, u, v);
     MPCG_SK_LEVEL(0) MPCG_SK_LEVEL(1) MPCG_SK_LEVEL(2) MPCG_SK_LEVEL(3)
-    if constexpr (kSkWarpLevels == 5) { MPCG_SK_LEVEL(4) }
 #undef MPCG_SK_LEVEL
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const double e = __shfl_up_sync(kFull, v[s], 1);
-      if (lane < kSkWarps) sm.wcar[lane][s] = lane ? e : c0[s];
-      if (lane == kSkWarps - 1) sm.carry[s] = v[s];
+      if (lane < kSkGW) gs.wcar[lane][s] = lane ? e : c0[s];
+      if (lane == tile_warps - 1) sm.carry[s] = v[s];       // the state where the next tile begins
+    }
+    if (kSkGroups > 1 && tile + 1 < ntiles) {             // hand the state to the group that owns tile + 1
+      __syncwarp();
+      asm volatile("bar.arrive %0, 64;" ::"r"(kSkBarCarry + ((tile + 1) & 1)) : "memory");
     }
   }
-  __syncthreads();
+  c.sync();
   // ---- true start state of my chunk = (exclusive scan inside the warp) + M^lane (state at the warp's first chunk)
   double z[4];
 #pragma unroll
@@ -352,17 +370,17 @@ __device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, 
   {
     double wc[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) wc[s] = sm.wcar[warp][s];
+    for (int s = 0; s < 4; ++s) wc[s] = gs.wcar[gw][s];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       double a = z[r];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) a = fma(sm.mtab[r * 4 + c][lane], wc[c], a);
+      for (int cc = 0; cc < 4; ++cc) a = fma(sm.mtab[r * 4 + cc][lane], wc[cc], a);
       z[r] = a;
     }
   }
   // ---- pass 2: re-run my chunk from its true state; statistics of the valid outputs ride along
-  int lim = n_valid - tid * kSkL;
+  int lim = n_valid - gt * kSkL;
   lim = lim < 0 ? 0 : (lim > kSkL ? kSkL : lim);
   if (lim == kSkL) {
     float tmin = INFINITY, tmax = -INFINITY;
@@ -410,7 +428,7 @@ __device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, 
   }
 }
 
-// M^lane of kind `kind` -> sm.mtab (warp 0; binary powers of the scan matrices)
+// M^lane of kind `kind` -> sm.mtab (one warp; binary powers of the scan matrices)
 __device__ __forceinline__ void sk_build_mtab(const SkParams& P, SkShared& sm, int kind) {
   const int lane = threadIdx.x & 31;
   double acc[16];
@@ -438,14 +456,15 @@ __device__ __forceinline__ void sk_build_mtab(const SkParams& P, SkShared& sm, i
   for (int i = 0; i < 16; ++i) sm.mtab[i][lane] = acc[i];
 }
 
-// Copy the part of every window that intersects samples [s0, s0 + n) of the row (held in sig[0, n)) to `obase`.
-// so_j == 1: 128-bit stores to 16-byte aligned destinations; the shared-memory side is read as the two aligned
-// 16-byte chunks around each group of four and shifted in registers (the shift is uniform per window and tile).
-// The data is read again by the rescale pass, so plain (L2-resident) stores.
-template <int SHIFT>
-__device__ __forceinline__ void sk_copy_shifted(const float4* __restrict__ s4, float4* __restrict__ d4, int nvec,
-                                                unsigned long long pol) {
-  for (int i = threadIdx.x; i < nvec; i += kSkThreads) {
+// Normalise and write the part of every window that intersects samples [s0, s0 + n) of the row (held, filtered, in
+// sig[0, n)).  so_j == 1: 128-bit streaming stores to 16-byte aligned destinations; the shared-memory side is read as
+// the two aligned 16-byte chunks around each group of four and shifted in registers (the shift is uniform per window
+// and tile).  `tid` / `nthr`: the calling thread's index among the nthr threads that share the tile.
+// kf: first window that may still intersect the tile (carried from tile to tile by the caller: no division here).
+template <int SHIFT, class F>
+__device__ __forceinline__ void sk_copy_shifted(const float4* __restrict__ s4, float4* __restrict__ d4, int nvec, int tid,
+                                                int nthr, const F& f) {
+  for (int i = tid; i < nvec; i += nthr) {
     const float4 a = s4[i];
     float4 o;
     if constexpr (SHIFT == 0) {
@@ -456,13 +475,13 @@ __device__ __forceinline__ void sk_copy_shifted(const float4* __restrict__ s4, f
       else if constexpr (SHIFT == 2) o = make_float4(a.z, a.w, b.x, b.y);
       else o = make_float4(a.w, b.x, b.y, b.z);
     }
-    st_keep4(d4 + i, o, pol);
+    st_stream4(d4 + i, make_float4(f(o.x), f(o.y), f(o.z), f(o.w)));
   }
 }
-// kf: first window that may still intersect the tile (the caller carries it from tile to tile, so no division here)
+template <class F>
 __device__ __forceinline__ void sk_store_windows(const float* sig, float* obase, int s0, int n, int start, int win, int hop,
-                                                 int nwin, long long so_k, long long so_j, int& kf, unsigned long long pol) {
-  const int tid = threadIdx.x;
+                                                 int nwin, long long so_k, long long so_j, int& kf, int tid, int nthr,
+                                                 const F& f) {
   const int s1 = s0 + n;
   while (kf < nwin && start + kf * hop + win <= s0) ++kf;
   for (int k = kf; k < nwin; ++k) {
@@ -478,22 +497,22 @@ __device__ __forceinline__ void sk_store_windows(const float* sig, float* obase,
       float* dp = obase + k * so_k + (a - w0);
       int head = (int)(((16u - ((uintptr_t)dp & 15u)) & 15u) >> 2);      // scalars up to the first aligned destination
       if (head > len) head = len;
-      if (tid < head) st_keep(dp + tid, sp[tid], pol);
+      if (tid < head) st_stream(dp + tid, f(sp[tid]));
       const int nvec = (len - head) >> 2;
       const int src = (a - s0) + head;                                   // tile-relative index of the first body sample
       const float4* s4 = reinterpret_cast<const float4*>(sig) + (src >> 2);
       float4* d4 = reinterpret_cast<float4*>(dp + head);
       switch (src & 3) {
-        case 0: sk_copy_shifted<0>(s4, d4, nvec, pol); break;
-        case 1: sk_copy_shifted<1>(s4, d4, nvec, pol); break;
-        case 2: sk_copy_shifted<2>(s4, d4, nvec, pol); break;
-        default: sk_copy_shifted<3>(s4, d4, nvec, pol); break;
+        case 0: sk_copy_shifted<0>(s4, d4, nvec, tid, nthr, f); break;
+        case 1: sk_copy_shifted<1>(s4, d4, nvec, tid, nthr, f); break;
+        case 2: sk_copy_shifted<2>(s4, d4, nvec, tid, nthr, f); break;
+        default: sk_copy_shifted<3>(s4, d4, nvec, tid, nthr, f); break;
       }
       const int done = head + (nvec << 2);
-      if (tid >= 32 && tid - 32 < len - done) st_keep(dp + done + tid - 32, sp[done + tid - 32], pol);
+      if (tid >= 32 && tid - 32 < len - done) st_stream(dp + done + tid - 32, f(sp[done + tid - 32]));
     } else {
       float* dp = obase + k * so_k + (long long)(a - w0) * so_j;
-      for (int i = tid; i < len; i += kSkThreads) dp[(long long)i * so_j] = sp[i];
+      for (int i = tid; i < len; i += nthr) dp[(long long)i * so_j] = f(sp[i]);
     }
   }
 }
@@ -511,8 +530,9 @@ struct SkCut {                             // "frame maximum exceeds threshold *
     return mode == MPCG_MEDIAN_LOWER ? (top > cutf) : ((double)top > cutd);
   }
 };
-__device__ __forceinline__ void sk_fast_frame(SkShared& sm, float* slot_buf, float* bm, const float* g, int win, float top,
-                                              int slot, const SkCut& cut) {
+template <class D>
+__device__ __forceinline__ void sk_fast_frame(D& d, float* slot_buf, float* bm, const float* g, int win, float top, int slot,
+                                              const SkCut& cut) {
   const int lane = threadIdx.x & 31;
   float* fr = slot_buf + phase_of(g);
   {                                                          // fetch: 128-bit loads, four in flight
@@ -524,8 +544,8 @@ __device__ __forceinline__ void sk_fast_frame(SkShared& sm, float* slot_buf, flo
     float4* sv = reinterpret_cast<float4*>(fr + head);
     int i = lane;
     for (; i + 96 < nvec; i += 128) {
-      const float4 a = ld_cg4(gv + i), b = ld_cg4(gv + i + 32), c = ld_cg4(gv + i + 64), d = ld_cg4(gv + i + 96);
-      sv[i] = a; sv[i + 32] = b; sv[i + 64] = c; sv[i + 96] = d;
+      const float4 a = ld_cg4(gv + i), b = ld_cg4(gv + i + 32), c = ld_cg4(gv + i + 64), e = ld_cg4(gv + i + 96);
+      sv[i] = a; sv[i + 32] = b; sv[i + 64] = c; sv[i + 96] = e;
     }
     for (; i < nvec; i += 32) sv[i] = ld_cg4(gv + i);
     const int done = head + (nvec << 2);
@@ -547,7 +567,7 @@ __device__ __forceinline__ void sk_fast_frame(SkShared& sm, float* slot_buf, flo
     }
   }
   __syncwarp();
-  if (lane == 0) sm.d.seq[slot][0] = top;
+  if (lane == 0) d.seq[slot][0] = top;
   int k = 0, stuck = 0, over = 0;
   while (cut.exceeds(top)) {
     if (k == kSkLogCap) { over = 1; break; }
@@ -560,14 +580,14 @@ __device__ __forceinline__ void sk_fast_frame(SkShared& sm, float* slot_buf, flo
     ++k;
     top = new_top;
     if (lane == 0) {
-      sm.d.span[slot][k - 1][0] = (unsigned short)lo;
-      sm.d.span[slot][k - 1][1] = (unsigned short)hi;
-      sm.d.seq[slot][k] = top;
+      d.span[slot][k - 1][0] = (unsigned short)lo;
+      d.span[slot][k - 1][1] = (unsigned short)hi;
+      d.seq[slot][k] = top;
     }
   }
   if (lane == 0) {
-    sm.d.xtop[slot] = top;
-    sm.d.xmeta[slot] = k | (stuck << 8) | (over << 9);
+    d.xtop[slot] = top;
+    d.xmeta[slot] = k | (stuck << 8) | (over << 9);
   }
 }
 __device__ __forceinline__ unsigned long long sk_warp_max_u64(unsigned long long v) {
@@ -584,16 +604,20 @@ __global__ void __launch_bounds__(kSkThreads, kSkCtasPerSm)
 fused_stream_kernel(const __grid_constant__ SkParams P) {
   extern __shared__ __align__(16) unsigned char sk_raw[];
   SkShared& sm = *reinterpret_cast<SkShared*>(sk_raw);
-  float* sig = reinterpret_cast<float*>(sk_raw + sizeof(SkShared)) + kSkGuard;
+  float* pool = reinterpret_cast<float*>(sk_raw + sizeof(SkShared));          // the groups' tile buffers, back to back
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SkCtx cx;
+  cx.g = tid / kSkGT; cx.gt = tid - cx.g * kSkGT; cx.gw = cx.gt >> 5; cx.lane = lane;
+  cx.sig = pool + cx.g * kSkBuf + kSkGuard;
+  cx.gs = &sm.grp[cx.g];
+  auto& dsp = sm.grp[0].d;                                // despike scratch (behind group 0's staging area)
   float* rowbuf = P.work_rows + (long long)blockIdx.x * P.work_stride;
   const unsigned long long total_rows = (unsigned long long)P.recordings * (unsigned)P.channels;
   const bool fix_nan = (P.norm_flags & MPCG_NORM_NAN_TO_NUM) != 0;
-  const uint32_t bar = sk_smem(&sm.bulk_bar);
+  const uint32_t bar = sk_smem(&cx.gs->bulk_bar);
   uint32_t bulk_phase = 0;
   int cur_kind = -1;
-  const unsigned long long pol_keep = sk_policy_keep();
-  if (tid == 0) {
+  if (cx.gt == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -645,68 +669,81 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     }
     const int win_d = P.win_d;
     const int nframes = (P.kinds[kind].despike && win_d >= 1 && t_r >= win_d) ? t_r / win_d : 0;
-    const int ntiles = (t_r + kSkTile - 1) / kSkTile;
-    const bool single = ntiles <= 1;
+    // tiles: as many as the row needs, rounded up to a multiple of the group count so that the groups get equal
+    // shares; the tile length is a whole number of warp shares (32 chunks), so a tile ends on a chunk boundary
+    int ntiles = (t_r + kSkTile - 1) / kSkTile;
+    int tl = kSkTile;
+    if (ntiles > 1 && kSkGroups > 1) {
+      ntiles = (ntiles + kSkGroups - 1) / kSkGroups * kSkGroups;
+      const int share = 32 * kSkL;
+      tl = ((t_r + ntiles - 1) / ntiles + share - 1) / share * share;
+      ntiles = (t_r + tl - 1) / tl;
+    }
+    const int tile_warps = tl / (32 * kSkL);              // warps whose chunks lie inside a full tile
+    const bool single = ntiles <= 1;                      // the whole row fits group 0's tile: it never leaves shared memory
     int passes = 0;
     SK_STAMP(0);
 
     // ------------------------------------------------------------ A. resample, frame maxima, Schmidt despike
     if (nframes > 0) {
       for (int i = tid; i < nframes; i += kSkThreads) sm.tops[i] = 0.f;
-      for (int tile = 0; tile < ntiles; ++tile) {
-        const int t0 = tile * kSkTile;
-        const int n = min(kSkTile, t_r - t0);
-        if (tile > 0) {                                   // the previous tile's bulk store has read the tile
-          if (tid == 0) sk_bulk_store_wait();
-          __syncthreads();
+      __syncthreads();
+      bool parked = false;
+      for (int tile = cx.g; tile < ntiles; tile += kSkGroups) {
+        const int t0 = tile * tl;
+        const int n = min(tl, t_r - t0);
+        if (parked) {                                     // my previous tile's bulk store has read the buffer
+          if (cx.gt == 0) sk_bulk_store_wait();
+          cx.sync();
         }
-        sk_resample_tile<UP, DOWN, D, PS>(sig, sm.xs, xr, t_in_r, P.off, t0, n);
-        if (!single && tid == 0)                          // park the tile in the row buffer: one bulk copy
-          sk_bulk_store(rowbuf + t0, sig, (uint32_t)((n + 3) >> 2) * 16u);
+        sk_resample_tile<UP, DOWN, D, PS>(cx, xr, t_in_r, P.off, t0, n);
+        if (!single && cx.gt == 0)                        // park the tile in the row buffer: one bulk copy
+          sk_bulk_store(rowbuf + t0, cx.sig, (uint32_t)((n + 3) >> 2) * 16u);
+        parked = !single;
         // frame maxima in two steps: every aligned 128-sample span of the tile (branch-free sweep), then one warp
         // per frame folds its whole spans and rescans only the ragged ends
         {
-          const int ra = warp * (kSkTile / kSkWarps);
+          const int ra = cx.gw * (kSkTile / kSkGW);
 #pragma unroll
-          for (int it = 0; it < kSkTile / kSkWarps / 128; ++it) {
-            const float4 v = *reinterpret_cast<const float4*>(sig + ra + it * 128 + 4 * lane);
+          for (int it = 0; it < kSkTile / kSkGW / 128; ++it) {
+            const float4 v = *reinterpret_cast<const float4*>(cx.sig + ra + it * 128 + 4 * lane);
             const float m4 = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
             const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(m4, 0.f)));   // fmaxf drops NaN
-            if (lane == 0) sm.spanmax[(ra >> 7) + it] = __uint_as_float(m);
+            if (lane == 0) cx.gs->spanmax[(ra >> 7) + it] = __uint_as_float(m);
           }
         }
-        __syncthreads();
+        cx.sync();
         {
           const int f_first = t0 / win_d;
           int f_last = (t0 + n - 1) / win_d;
           if (f_last > nframes - 1) f_last = nframes - 1;
-          for (int f = f_first + warp; f <= f_last; f += kSkWarps) {
+          for (int f = f_first + cx.gw; f <= f_last; f += kSkGW) {
             const int lo = max(f * win_d - t0, 0), hi = min((f + 1) * win_d - t0, n);
             const int s_lo = (lo + 127) >> 7, s_hi = hi >> 7;
             float m = 0.f;
             if (s_lo < s_hi) {
-              for (int q = s_lo + lane; q < s_hi; q += 32) m = fmaxf(m, sm.spanmax[q]);
-              for (int j = lo + lane; j < (s_lo << 7); j += 32) m = fmaxf(m, fabsf(sig[j]));
-              for (int j = (s_hi << 7) + lane; j < hi; j += 32) m = fmaxf(m, fabsf(sig[j]));
+              for (int q = s_lo + lane; q < s_hi; q += 32) m = fmaxf(m, cx.gs->spanmax[q]);
+              for (int j = lo + lane; j < (s_lo << 7); j += 32) m = fmaxf(m, fabsf(cx.sig[j]));
+              for (int j = (s_hi << 7) + lane; j < hi; j += 32) m = fmaxf(m, fabsf(cx.sig[j]));
             } else {
-              for (int j = lo + lane; j < hi; j += 32) m = fmaxf(m, fabsf(sig[j]));
+              for (int j = lo + lane; j < hi; j += 32) m = fmaxf(m, fabsf(cx.sig[j]));
             }
             const unsigned mu = __reduce_max_sync(kFull, __float_as_uint(m));
-            if (lane == 0) sm.tops[f] = fmaxf(sm.tops[f], __uint_as_float(mu));
+            // a frame that straddles two tiles is updated by both groups: integer max of the non-negative float bits
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(&sm.tops[f]), mu);
           }
         }
-        __syncthreads();
+        cx.sync();
       }
-      if (!single) {                                      // the parked row is complete and visible
-        if (tid == 0) sk_bulk_store_wait();
-        __syncthreads();
-      }
+      if (parked && cx.gt == 0) sk_bulk_store_wait();     // the parked row is complete and visible
+      __syncthreads();
       SK_STAMP(1);
       const int nblk = (win_d + 31) >> 5;
       const int slot_stride = (win_d + 7) & ~3;           // room for the 16-byte phase match
-      int nslots = kSkTile / slot_stride;
+      int nslots = (kSkGroups * kSkBuf) / slot_stride;
       if (nslots > kSkSlots) nslots = kSkSlots;
       if (nslots * nblk > kSkBmWords) nslots = kSkBmWords / nblk;
+      float* sig0 = pool + kSkGuard;                      // (single rows live in group 0's tile)
       bool serial = single || P.trace != nullptr || P.serial_despike || nframes > kSkFastFrames || win_d < 2 ||
                     win_d > 65535;
       // ---------------------------------------------------------- parallel rounds
@@ -754,35 +791,35 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
             const bool a0 = open && lane < nf && cut.exceeds(v0), a1 = open && lane + 32 < nf && cut.exceeds(v1);
             const unsigned m0 = __ballot_sync(kFull, a0), m1 = __ballot_sync(kFull, a1);
             const unsigned below = (1u << lane) - 1u;
-            if (a0) sm.d.act[__popc(m0 & below)] = (unsigned char)lane;
-            if (a1) sm.d.act[__popc(m0) + __popc(m1 & below)] = (unsigned char)(lane + 32);
+            if (a0) dsp.act[__popc(m0 & below)] = (unsigned char)lane;
+            if (a1) dsp.act[__popc(m0) + __popc(m1 & below)] = (unsigned char)(lane + 32);
             if (lane == 0) {
-              sm.d.nact = __popc(m0) + __popc(m1); sm.d.cutf = cut.cutf; sm.d.cutd = cut.cutd;
-              sm.d.lo_mid = lo_mid; sm.d.hi_mid = hi_mid;
+              dsp.nact = __popc(m0) + __popc(m1); dsp.cutf = cut.cutf; dsp.cutd = cut.cutd;
+              dsp.lo_mid = lo_mid; dsp.hi_mid = hi_mid;
             }
           }
           __syncthreads();
-          const int nact = sm.d.nact;
+          const int nact = dsp.nact;
           if (nact == 0) break;
           {                                                 // the listed frames, nslots at a time, one warp each
             SkCut cut;
-            cut.mode = P.median_mode; cut.cutf = sm.d.cutf; cut.cutd = sm.d.cutd;
+            cut.mode = P.median_mode; cut.cutf = dsp.cutf; cut.cutd = dsp.cutd;
             if (warp < nslots)
               for (int slot = warp; slot < nact; slot += nslots) {
-                const int f = sm.d.act[slot];
-                sk_fast_frame(sm, sig + warp * slot_stride, sm.d.bm + warp * nblk, rowbuf + (long long)f * win_d, win_d,
+                const int f = dsp.act[slot];
+                sk_fast_frame(dsp, pool + warp * slot_stride, dsp.bm + warp * nblk, rowbuf + (long long)f * win_d, win_d,
                               sm.tops[f], slot, cut);
               }
           }
           __syncthreads();
           if (warp == 0) {                                  // the round's outcome
             const bool h0 = lane < nact, h1 = lane + 32 < nact;
-            const int me0 = h0 ? sm.d.xmeta[lane] : 0, me1 = h1 ? sm.d.xmeta[lane + 32] : 0;
+            const int me0 = h0 ? dsp.xmeta[lane] : 0, me1 = h1 ? dsp.xmeta[lane + 32] : 0;
             const bool over = __any_sync(kFull, ((me0 | me1) >> 9) & 1);
             unsigned long long ks = 0ull;
-            if ((me0 >> 8) & 1) ks = spike_key(sm.d.xtop[lane], sm.d.act[lane]);
+            if ((me0 >> 8) & 1) ks = spike_key(dsp.xtop[lane], dsp.act[lane]);
             if ((me1 >> 8) & 1) {
-              const unsigned long long k1 = spike_key(sm.d.xtop[lane + 32], sm.d.act[lane + 32]);
+              const unsigned long long k1 = spike_key(dsp.xtop[lane + 32], dsp.act[lane + 32]);
               ks = k1 > ks ? k1 : ks;
             }
             const unsigned long long kstar = sk_warp_max_u64(ks);
@@ -793,35 +830,35 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
             const bool hand_over = over || (long long)passes + total + (kstar != 0ull ? 1 : 0) > (long long)P.max_iter;
             // If no flattened frame fell below the old middle value(s), the median and with it the threshold are what
             // they were: nothing else can exceed it and the row is finished without another round.
-            const float floor_v = P.median_mode == MPCG_MEDIAN_LOWER ? sm.d.lo_mid : sm.d.hi_mid;
-            const bool same_median = __all_sync(kFull, (!h0 || sm.d.xtop[lane] >= floor_v) &&
-                                                           (!h1 || sm.d.xtop[lane + 32] >= floor_v));
+            const float floor_v = P.median_mode == MPCG_MEDIAN_LOWER ? dsp.lo_mid : dsp.hi_mid;
+            const bool same_median = __all_sync(kFull, (!h0 || dsp.xtop[lane] >= floor_v) &&
+                                                           (!h1 || dsp.xtop[lane + 32] >= floor_v));
             if (!hand_over && kstar == 0ull) {
-              if (h0) sm.tops[sm.d.act[lane]] = sm.d.xtop[lane];
-              if (h1) sm.tops[sm.d.act[lane + 32]] = sm.d.xtop[lane + 32];
+              if (h0) sm.tops[dsp.act[lane]] = dsp.xtop[lane];
+              if (h1) sm.tops[dsp.act[lane + 32]] = dsp.xtop[lane + 32];
             }
             if (lane == 0) {
-              sm.d.verdict = hand_over ? 2 : (kstar != 0ull ? 1 : (same_median ? 3 : 0));
-              sm.d.total = total;
-              sm.d.kstar = kstar;
+              dsp.verdict = hand_over ? 2 : (kstar != 0ull ? 1 : (same_median ? 3 : 0));
+              dsp.total = total;
+              dsp.kstar = kstar;
             }
           }
           __syncthreads();
-          const int verdict = sm.d.verdict;
-          const unsigned long long kstar = sm.d.kstar;
+          const int verdict = dsp.verdict;
+          const unsigned long long kstar = dsp.kstar;
           if (verdict != 2) {
             for (int slot = warp; slot < nact; slot += kSkWarps) {   // fill the spans of the passes that happen
-              const int f = sm.d.act[slot];
-              const int k = sm.d.xmeta[slot] & 0xff;
+              const int f = dsp.act[slot];
+              const int k = dsp.xmeta[slot] & 0xff;
               int jc = k;
               if (verdict == 1) {                             // only passes that started above K* (all of the stuck frame's)
-                if (spike_key(sm.d.seq[slot][k], f) != kstar)
-                  jc = __popc(__ballot_sync(kFull, lane < k && spike_key(sm.d.seq[slot][lane < k ? lane : 0], f) > kstar));
-                if (lane == 0) sm.d.xj[slot] = jc;
+                if (spike_key(dsp.seq[slot][k], f) != kstar)
+                  jc = __popc(__ballot_sync(kFull, lane < k && spike_key(dsp.seq[slot][lane < k ? lane : 0], f) > kstar));
+                if (lane == 0) dsp.xj[slot] = jc;
               }
               float* g = rowbuf + (long long)f * win_d;
               for (int j = 0; j < jc; ++j) {
-                const int lo = sm.d.span[slot][j][0], hi = sm.d.span[slot][j][1];
+                const int lo = dsp.span[slot][j][0], hi = dsp.span[slot][j][1];
                 for (int i = lo + lane; i < hi; i += 32) g[i] = kSpikeFill;
               }
             }
@@ -830,16 +867,16 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
           if (verdict == 1) {                                 // exact pass count: what really counted + the pass that moves nothing
             __syncthreads();
             if (warp == 0) {
-              int t = (lane < nact ? sm.d.xj[lane] : 0) + (lane + 32 < nact ? sm.d.xj[lane + 32] : 0);
+              int t = (lane < nact ? dsp.xj[lane] : 0) + (lane + 32 < nact ? dsp.xj[lane + 32] : 0);
 #pragma unroll
               for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
-              if (lane == 0) sm.d.total = t + 1;
+              if (lane == 0) dsp.total = t + 1;
             }
             __syncthreads();
-            passes += sm.d.total;
+            passes += dsp.total;
             break;
           }
-          passes += sm.d.total;
+          passes += dsp.total;
           if (verdict == 3) break;
           __syncthreads();
         }
@@ -855,32 +892,32 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
           for (int q = warp; q < nframes * nblk; q += kSkWarps) {
             const int f = q / nblk, b = q - f * nblk;
             const int i = b * 32 + lane;
-            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(sig[f * win_d + i]) : 0.f, 0.f)));
-            if (lane == 0) sm.d.bm[q] = __uint_as_float(m);
+            const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(sig0[f * win_d + i]) : 0.f, 0.f)));
+            if (lane == 0) dsp.bm[q] = __uint_as_float(m);
           }
         }
         __syncthreads();
         const bool sorted_mode = nframes <= 64;
-        if (warp == 0 && sorted_mode) spike_sort_init(sm.d.sorted, sm.tops, nframes);
+        if (warp == 0 && sorted_mode) spike_sort_init(dsp.sorted, sm.tops, nframes);
         for (;;) {
           if (warp == 0) {
             int req = -2;                                 // -2: the row is finished
             while (passes < P.max_iter) {
-              const SpikeDecision dec = sorted_mode ? spike_sort_decide(sm.d.sorted, nframes, P.threshold, P.median_mode)
+              const SpikeDecision dec = sorted_mode ? spike_sort_decide(dsp.sorted, nframes, P.threshold, P.median_mode)
                                                     : spike_decide_warp(sm.tops, nframes, P.threshold, P.median_mode);
               if (!dec.active) break;
               float* fr;
               float* bmf;
               if (single) {
-                fr = sig + dec.worst * win_d;
-                bmf = sm.d.bm + dec.worst * nblk;
+                fr = sig0 + dec.worst * win_d;
+                bmf = dsp.bm + dec.worst * nblk;
               } else {
                 int slot = -1;
-                for (int s = 0; s < nslots; ++s)
-                  if (sm.slot_frame[s] == dec.worst) slot = s;
+                for (int s2 = 0; s2 < nslots; ++s2)
+                  if (sm.slot_frame[s2] == dec.worst) slot = s2;
                 if (slot < 0) { req = dec.worst; break; }
-                fr = sig + slot * slot_stride + phase_of(rowbuf + (long long)dec.worst * win_d);
-                bmf = sm.d.bm + slot * nblk;
+                fr = pool + slot * slot_stride + phase_of(rowbuf + (long long)dec.worst * win_d);
+                bmf = dsp.bm + slot * nblk;
               }
               const float old_top = sm.tops[dec.worst];
               int peak, lo, hi;
@@ -902,8 +939,8 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
               ++passes;
               if (!changed) break;
               if (sorted_mode) {
-                if (new_top <= old_top) spike_sort_update(sm.d.sorted, dec.worst, old_top, new_top);
-                else spike_sort_init(sm.d.sorted, sm.tops, nframes);    // the fill raised a tiny frame: sort afresh
+                if (new_top <= old_top) spike_sort_update(dsp.sorted, dec.worst, old_top, new_top);
+                else spike_sort_init(dsp.sorted, sm.tops, nframes);     // the fill raised a tiny frame: sort afresh
               }
             }
             if (lane == 0) sm.req = req;
@@ -914,7 +951,7 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
           {                                               // fetch frame `req` into the next cache slot
             const int slot = sm.victim;
             const float* g = rowbuf + (long long)req * win_d;
-            float* fr = sig + slot * slot_stride + phase_of(g);
+            float* fr = pool + slot * slot_stride + phase_of(g);
             {
               int head = (int)(((16u - ((uintptr_t)g & 15u)) & 15u) >> 2);
               if (head > win_d) head = win_d;
@@ -930,7 +967,7 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
             for (int b = warp; b < nblk; b += kSkWarps) {
               const int i = b * 32 + lane;
               const unsigned m = __reduce_max_sync(kFull, __float_as_uint(fmaxf(i < win_d ? fabsf(fr[i]) : 0.f, 0.f)));
-              if (lane == 0) sm.d.bm[slot * nblk + b] = __uint_as_float(m);
+              if (lane == 0) dsp.bm[slot * nblk + b] = __uint_as_float(m);
             }
             if (tid == 0) {
               sm.slot_frame[slot] = req;
@@ -948,34 +985,45 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     }
 
     // ------------------------------------------------------------ B. band filter + statistics, tile by tile
+    // The filtered tile goes back to the row buffer un-normalised (one bulk store per tile, in place).
     double lsum = 0.0;
     float lmin = INFINITY, lmax = -INFINITY;
     if (tid < 4) sm.carry[tid] = 0.0;
-    int kf = 0;                                           // first window that may still intersect the coming tiles
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int t0 = tile * kSkTile;
-      const int n = min(kSkTile, t_r - t0);
-      if (nframes > 0) {
-        if (!single) {                                    // the despiked tile comes back from the row buffer: one bulk copy
-          sk_fence_async_smem();
-          __syncthreads();                                // (the previous tile's window stores have left shared memory)
-          if (tid == 0) sk_bulk_load(sig, rowbuf + t0, (uint32_t)((n + 3) >> 2) * 16u, bar);
-          sk_bar_wait(bar, bulk_phase);
-          bulk_phase ^= 1u;
+    sk_fence_async_smem();                                // (the tile buffers held despike slots: bulk loads overwrite them)
+    __syncthreads();
+    {
+      bool stored = false;
+      for (int tile = cx.g; tile < ntiles; tile += kSkGroups) {
+        const int t0 = tile * tl;
+        const int n = min(tl, t_r - t0);
+        if (stored) {                                     // my previous tile's bulk store has read the buffer
+          if (cx.gt == 0) sk_bulk_store_wait();
+          cx.sync();
         }
-      } else {
-        __syncthreads();
-        sk_resample_tile<UP, DOWN, D, PS>(sig, sm.xs, xr, t_in_r, P.off, t0, n);
+        if (nframes > 0) {
+          if (!single) {                                  // the despiked tile comes back from the row buffer: one bulk copy
+            if (cx.gt == 0) sk_bulk_load(cx.sig, rowbuf + t0, (uint32_t)((n + 3) >> 2) * 16u, bar);
+            sk_bar_wait(bar, bulk_phase);
+            bulk_phase ^= 1u;
+          }
+        } else {
+          sk_resample_tile<UP, DOWN, D, PS>(cx, xr, t_in_r, P.off, t0, n);
+        }
+        for (int i = n + cx.gt; i < kSkTile + kSkGuard; i += kSkGT) cx.sig[i] = 0.f;    // chunk grid beyond the row
+        cx.sync();
+        SK_STAMP(3);
+        if (kind == 0) sk_filter_tile<0>(P, sm, cx, tile, ntiles, tile_warps, n, fix_nan, lsum, lmin, lmax);
+        else sk_filter_tile<1>(P, sm, cx, tile, ntiles, tile_warps, n, fix_nan, lsum, lmin, lmax);
+        SK_STAMP(4);
+        if (!single) {
+          sk_fence_async_smem();
+          cx.sync();
+          if (cx.gt == 0) sk_bulk_store(rowbuf + t0, cx.sig, (uint32_t)((n + 3) >> 2) * 16u);
+          stored = true;
+        }
+        SK_STAMP(5);
       }
-      for (int i = n + tid; i < kSkTile + kSkGuard; i += kSkThreads) sig[i] = 0.f;    // chunk grid beyond the row
-      __syncthreads();
-      SK_STAMP(3);
-      if (kind == 0) sk_filter_tile<0>(P, sm, sig, n, fix_nan, lsum, lmin, lmax);
-      else sk_filter_tile<1>(P, sm, sig, n, fix_nan, lsum, lmin, lmax);
-      __syncthreads();
-      SK_STAMP(4);
-      if (!single) sk_store_windows(sig, obase, t0, n, P.start, P.win, P.hop, nwin, so_k, so_j, kf, pol_keep);
-      SK_STAMP(5);
+      if (stored && cx.gt == 0) sk_bulk_store_wait();     // my tiles have reached the row buffer
     }
 
     // ------------------------------------------------------------ row statistics -> the normalising map
@@ -1001,57 +1049,38 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     }
     __syncthreads();
     const float inv_f = sm.fscr[0], shift_f = sm.fscr[1];
-    auto scaled = [&](float s) { return fminf(fmaxf(fmaf(s, inv_f, shift_f), -1.f), 1.f); };
-    auto scaled4 = [&](float4 a) {
-      a.x = scaled(a.x); a.y = scaled(a.y); a.z = scaled(a.z); a.w = scaled(a.w);
-      return a;
-    };
+    auto scaled = [inv_f, shift_f](float v) { return fminf(fmaxf(fmaf(v, inv_f, shift_f), -1.f), 1.f); };
 
-    // ------------------------------------------------------------ C. normalise the row's windows
-    // samples of the row that the windows hold: all of every window, except a short row's single zero-padded window
-    const long long span = (long long)nwin * P.win;
-    long long valid = span;
-    if (P.start + (long long)(nwin - 1) * P.hop + P.win > t_r) {        // (only when nwin == 1)
-      valid = t_r - P.start;
-      if (valid < 0) valid = 0;
-    }
-    if (single) {                                         // the filtered row is still in shared memory
-      for (int k = 0; k < nwin; ++k) {
-        const int w0 = P.start + k * P.hop;
-        const int len = (int)min((long long)P.win, (long long)t_r - w0);
-        float* dp = obase + k * so_k;
-        for (int i = tid; i < len; i += kSkThreads) st_stream(dp + (long long)i * so_j, scaled(sig[w0 + i]));
-      }
-    } else if (so_j == 1) {
-      float* p = obase;                                   // [nwin * win] contiguous
-      int head = (int)(((16u - ((uintptr_t)p & 15u)) & 15u) >> 2);
-      if ((long long)head > valid) head = (int)valid;
-      if (tid < head) st_stream(p + tid, scaled(ld_cg(p + tid)));
-      const long long nvec = (valid - head) >> 2;
-      float4* p4 = reinterpret_cast<float4*>(p + head);
-      long long i = tid;
-      for (; i + 7 * kSkThreads < nvec; i += 8 * kSkThreads) {          // eight 128-bit loads in flight per thread
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ld_cg4(p4 + i + u * kSkThreads);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) st_stream4(p4 + i + u * kSkThreads, scaled4(v[u]));
-      }
-      for (; i < nvec; i += kSkThreads) st_stream4(p4 + i, scaled4(ld_cg4(p4 + i)));
-      const long long done = head + (nvec << 2);
-      if (tid < valid - done) st_stream(p + done + tid, scaled(ld_cg(p + done + tid)));
-    } else {
-      for (long long i = tid; i < valid; i += kSkThreads) {
-        float* q = obase + i * so_j;
-        *q = scaled(ld_cg(q));
+    // ------------------------------------------------------------ C. normalise + write the row's windows
+    if (single) {                                         // the filtered row is still in group 0's tile
+      int kf = 0;
+      sk_store_windows(pool + kSkGuard, obase, 0, t_r, P.start, P.win, P.hop, nwin, so_k, so_j, kf, tid, kSkThreads, scaled);
+    } else {                                              // tiles come back from the row buffer, one bulk copy each
+      int kf = 0;
+      for (int tile = cx.g; tile < ntiles; tile += kSkGroups) {
+        const int t0 = tile * tl;
+        const int n = min(tl, t_r - t0);
+        sk_fence_async_smem();
+        cx.sync();                                        // the group is done with the buffer's previous content
+        if (cx.gt == 0) sk_bulk_load(cx.sig, rowbuf + t0, (uint32_t)((n + 3) >> 2) * 16u, bar);
+        sk_bar_wait(bar, bulk_phase);
+        bulk_phase ^= 1u;
+        sk_store_windows(cx.sig, obase, t0, n, P.start, P.win, P.hop, nwin, so_k, so_j, kf, cx.gt, kSkGT, scaled);
       }
     }
-    for (long long i = valid + tid; i < span; i += kSkThreads) obase[i * so_j] = 0.f;   // short row: zero padding
+    {                                                     // a short row's single window: zero padding past the row's end
+      const long long span = (long long)nwin * P.win;
+      if (P.start + (long long)(nwin - 1) * P.hop + P.win > t_r) {        // (only when nwin == 1)
+        long long valid = t_r - P.start;
+        if (valid < 0) valid = 0;
+        for (long long i = valid + tid; i < span; i += kSkThreads) obase[i * so_j] = 0.f;
+      }
+    }
     SK_STAMP(6);
   }
 #if defined(MPCG_FZ_PHASE_CLOCKS) && MPCG_FZ_PHASE_CLOCKS
-  if (P.dbg && tid == 0)
-    for (int k = 0; k < 8; ++k) P.dbg[(long long)blockIdx.x * 16 + k] = ph_acc[k];
+  if (P.dbg && cx.gt == 0)
+    for (int k = 0; k < 8; ++k) P.dbg[((long long)blockIdx.x * kSkGroups + cx.g) * 16 + k] = ph_acc[k];
 #endif
 #undef SK_STAMP
 }
