@@ -116,8 +116,8 @@ struct SkGroupShared {                            // private to one tile group
   double wagg[kSkGW][4];                          // warp aggregates
   double wcar[kSkGW][4];                          // state at the start of each warp's first chunk
   float spanmax[kSkTile / 128];                   // maxima of the tile's aligned 128-sample spans
-  unsigned long long bulk_bar;                    // mbarrier of this group's bulk (TMA) tile loads
-  unsigned long long pad_;
+  unsigned long long bulk_bar;                    // mbarriers of this group's bulk (TMA) loads: whole tiles / first halves,
+  unsigned long long bulk_bar2;                   //   second halves
 };
 struct SkShared {
   SkGroupShared grp[kSkGroups];
@@ -177,6 +177,19 @@ __device__ __forceinline__ void sk_bulk_store(void* g, const void* smem_src, uin
 __device__ __forceinline__ void sk_bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sk_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sk_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Ask L2 for the raw samples that the resampler will read for output samples [t0, t0 + n) of a row (one bulk
+// prefetch by one thread, issued a tile ahead: the staged loads then find their lines in L2 instead of waiting for HBM).
+template <int UP, int DOWN, int D>
+__device__ __forceinline__ void sk_prefetch_inputs(const float* xr, int t_in, int off, int t0, int n) {
+  if (n <= 0) return;
+  long long lo = (long long)(t0 / UP) * DOWN + off, hi = (long long)((t0 + n - 1) / UP) * DOWN + off + D;
+  if (lo < 0) lo = 0;
+  if (hi > t_in) hi = t_in;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(xr + lo) & ~(uintptr_t)15;
+  const uintptr_t b = reinterpret_cast<uintptr_t>(xr + hi) & ~(uintptr_t)15;      // (rounded down: stays inside the row)
+  if (b > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)(b - a)) : "memory");
+}
 
 __device__ __forceinline__ void sk_team_sync(int bar_id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(count) : "memory");
@@ -615,10 +628,11 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
   const unsigned long long total_rows = (unsigned long long)P.recordings * (unsigned)P.channels;
   const bool fix_nan = (P.norm_flags & MPCG_NORM_NAN_TO_NUM) != 0;
   const uint32_t bar = sk_smem(&cx.gs->bulk_bar);
-  uint32_t bulk_phase = 0;
+  uint32_t bulk_phase = 0, bulk_phase2 = 0;
   int cur_kind = -1;
   if (cx.gt == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sk_smem(&cx.gs->bulk_bar2)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #if defined(MPCG_FZ_PHASE_CLOCKS) && MPCG_FZ_PHASE_CLOCKS
@@ -682,6 +696,8 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     const int tile_warps = tl / (32 * kSkL);              // warps whose chunks lie inside a full tile
     const bool single = ntiles <= 1;                      // the whole row fits group 0's tile: it never leaves shared memory
     int passes = 0;
+    if (UP != DOWN && cx.gt == 32)                        // the raw samples of my first tile
+      sk_prefetch_inputs<UP, DOWN, D>(xr, t_in_r, P.off, cx.g * tl, min(tl, t_r - cx.g * tl));
     SK_STAMP(0);
 
     // ------------------------------------------------------------ A. resample, frame maxima, Schmidt despike
@@ -696,6 +712,8 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
           if (cx.gt == 0) sk_bulk_store_wait();
           cx.sync();
         }
+        if (cx.gt == 32 && tile + kSkGroups < ntiles)     // the raw samples of my next tile: on their way to L2
+          sk_prefetch_inputs<UP, DOWN, D>(xr, t_in_r, P.off, t0 + kSkGroups * tl, min(tl, t_r - t0 - kSkGroups * tl));
         sk_resample_tile<UP, DOWN, D, PS>(cx, xr, t_in_r, P.off, t0, n);
         if (!single && cx.gt == 0)                        // park the tile in the row buffer: one bulk copy
           sk_bulk_store(rowbuf + t0, cx.sig, (uint32_t)((n + 3) >> 2) * 16u);
@@ -1007,6 +1025,8 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
             bulk_phase ^= 1u;
           }
         } else {
+          if (cx.gt == 32 && tile + kSkGroups < ntiles)   // the raw samples of my next tile: on their way to L2
+            sk_prefetch_inputs<UP, DOWN, D>(xr, t_in_r, P.off, t0 + kSkGroups * tl, min(tl, t_r - t0 - kSkGroups * tl));
           sk_resample_tile<UP, DOWN, D, PS>(cx, xr, t_in_r, P.off, t0, n);
         }
         for (int i = n + cx.gt; i < kSkTile + kSkGuard; i += kSkGT) cx.sig[i] = 0.f;    // chunk grid beyond the row
@@ -1055,18 +1075,43 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     if (single) {                                         // the filtered row is still in group 0's tile
       int kf = 0;
       sk_store_windows(pool + kSkGuard, obase, 0, t_r, P.start, P.win, P.hop, nwin, so_k, so_j, kf, tid, kSkThreads, scaled);
-    } else {                                              // tiles come back from the row buffer, one bulk copy each
+    } else {                                              // tiles come back from the row buffer in halves, two bulk copies in flight
       int kf = 0;
-      for (int tile = cx.g; tile < ntiles; tile += kSkGroups) {
-        const int t0 = tile * tl;
-        const int n = min(tl, t_r - t0);
-        sk_fence_async_smem();
-        cx.sync();                                        // the group is done with the buffer's previous content
-        if (cx.gt == 0) sk_bulk_load(cx.sig, rowbuf + t0, (uint32_t)((n + 3) >> 2) * 16u, bar);
-        sk_bar_wait(bar, bulk_phase);
-        bulk_phase ^= 1u;
-        sk_store_windows(cx.sig, obase, t0, n, P.start, P.win, P.hop, nwin, so_k, so_j, kf, cx.gt, kSkGT, scaled);
+      const uint32_t bar2 = sk_smem(&cx.gs->bulk_bar2);
+      constexpr int HALF = kSkTile / 2;
+      // piece q = half (q & 1) of my (q >> 1)-th tile; piece q lands in half (q & 1) of the tile buffer
+      int npieces = 0;
+      for (int tile = cx.g; tile < ntiles; tile += kSkGroups) npieces += (min(tl, t_r - tile * tl) > HALF) ? 2 : 1;
+      auto piece = [&](int q, int& s0, int& len, int& half) {
+        // tiles are full (two pieces each) except possibly the last one
+        const int tile = cx.g + (q >> 1) * kSkGroups;
+        const int n = min(tl, t_r - tile * tl);
+        half = q & 1;
+        s0 = tile * tl + half * HALF;
+        len = half ? n - HALF : min(n, HALF);
+      };
+      sk_fence_async_smem();
+      cx.sync();                                          // the group is done with the buffer's previous content
+      uint32_t ph0 = bulk_phase, ph1 = bulk_phase2;
+      if (cx.gt == 0 && npieces > 0) {
+        int s0, len, half;
+        piece(0, s0, len, half);
+        sk_bulk_load(cx.sig, rowbuf + s0, (uint32_t)((len + 3) >> 2) * 16u, bar);
       }
+      for (int q = 0; q < npieces; ++q) {
+        int s0, len, half;
+        piece(q, s0, len, half);
+        if (cx.gt == 0 && q + 1 < npieces) {              // the next piece flies while this one is written out
+          int s1, len1, half1;
+          piece(q + 1, s1, len1, half1);
+          sk_bulk_load(cx.sig + half1 * HALF, rowbuf + s1, (uint32_t)((len1 + 3) >> 2) * 16u, half1 ? bar2 : bar);
+        }
+        if (half) { sk_bar_wait(bar2, ph1); ph1 ^= 1u; } else { sk_bar_wait(bar, ph0); ph0 ^= 1u; }
+        sk_store_windows(cx.sig + half * HALF, obase, s0, len, P.start, P.win, P.hop, nwin, so_k, so_j, kf, cx.gt, kSkGT, scaled);
+        sk_fence_async_smem();
+        cx.sync();                                        // this half may be overwritten by the piece after next
+      }
+      bulk_phase = ph0; bulk_phase2 = ph1;
     }
     {                                                     // a short row's single window: zero padding past the row's end
       const long long span = (long long)nwin * P.win;
