@@ -84,6 +84,12 @@ int mpcg_despike_f32(float* x, int64_t rows, int64_t t, int64_t win, double thre
  * NaN interpolation).  flags: MPCG_NORM_*. */
 int mpcg_absmax_norm_f32(const float* x, float* y, int64_t rows, int64_t t, int flags, void* stream);
 
+/* Bridge NaN runs by linear interpolation between the nearest valid samples of the row; edges hold the first / last valid
+ * value; a row without a valid sample stays as it is.  Replaces normalize.interpolate_nans (signalproc/normalize.py:11-17),
+ * the first step of the NumPy chains (signalproc/preprocess.py:25,34).  In place on x[recordings, channels, t]; row_len
+ * (optional, device, [recordings] int32): valid samples of each recording's rows (the rest of the pitch is ignored). */
+int mpcg_fill_nans_f32(float* x, int64_t recordings, int channels, int64_t t, const int32_t* row_len, void* stream);
+
 /* Overlapping-window gather.  x is [rows, channels, t]; window k of a row starts at start + k*hop and is
  * zero-filled past t.  channels_last = 0: out[rows, channels, n, win] (torchproc.segment on [B,C,T],
  * signalproc/torchproc.py:119-129, returned there as a view);  channels_last = 1: out[rows, n, win, channels]

@@ -95,6 +95,64 @@ def test_long_ecg_rows_and_row_independence(pkg):
     assert torch.equal(a[690:], b)
 
 
+def test_ragged_batch_equals_per_record_calls(pkg):
+    """lengths=: recordings of different lengths in ONE launch (per-row tables in the descriptor).  Every recording's
+    windows must equal, bit for bit, the call on that recording alone; counts follow mpcg_window_count."""
+    rng = np.random.default_rng(71)
+    lens = [60000, 9000, 31001, 2400, 17, 45678, 20000]
+    pitch = (max(lens) + 3) & ~3
+    x = np.zeros((len(lens), 2, pitch), np.float32)
+    for b, n in enumerate(lens):
+        x[b, 0, :n] = _spiky(1, n, seed=80 + b, spikes=2 if n > 100 else 0)[0] if n > 50 else 1.0
+        x[b, 1, :n] = np.sin(np.arange(n) / 250.0) + 0.05 * rng.standard_normal(n)
+        x[b, :, n:] = 7.0                                    # garbage past the valid part must not matter
+    spec = pkg.WindowSpec(4.0)
+    for layout in ("channels_last", "channel_major"):
+        got, counts = pkg.preprocess_segment(_dev(x), 2000, 4125, spec, kinds=("pcg", "ecg"), lengths=lens, **{layout: True})
+        at = 0
+        for b, n in enumerate(lens):
+            one = pkg.preprocess_segment(_dev(x[b:b + 1, :, :n]), 2000, 4125, spec, kinds=("pcg", "ecg"), fused=True,
+                                         **{layout: True})
+            k = int(counts[b])
+            assert k == one.shape[1 if layout == "channels_last" else 2]
+            mine = got[at:at + k] if layout == "channels_last" else got[:, at:at + k]
+            want = one[0] if layout == "channels_last" else one[:, 0]
+            assert torch.equal(mine, want), (layout, b)
+            at += k
+        assert at == got.shape[0 if layout == "channels_last" else 1]
+    mono, counts = pkg.preprocess_segment(_dev(x[:, 0]), 2000, 16000, pkg.WindowSpec(1.0), lengths=lens, mode="numpy")
+    at = 0
+    for b, n in enumerate(lens):
+        one = pkg.preprocess_segment(_dev(x[b:b + 1, 0, :n]), 2000, 16000, pkg.WindowSpec(1.0), mode="numpy", fused=True)
+        k = int(counts[b])
+        assert torch.equal(mono[at:at + k], one[0])
+        at += k
+
+
+def test_numpy_mode_bridges_nans_like_the_reference(pkg):
+    """wfdb marks invalid samples with NaN; the NumPy chains interpolate them away first (signalproc/preprocess.py:25,34,
+    normalize.py:11-17).  Leading / trailing / interior runs and runs across thread chunks, against the float64 oracle."""
+    x = _spiky(4, 20000, seed=91, spikes=2)
+    x[0, :37] = np.nan; x[0, 5000:5003] = np.nan; x[0, -11:] = np.nan
+    x[1, 77] = np.nan; x[1, 9990:10400] = np.nan
+    x[2, 1::2] = np.nan                                     # every other sample
+    spec = onp.WindowSpec(1.0)
+    got = pkg.preprocess_segment(_dev(x), 2000, 4125, pkg.WindowSpec(1.0), mode="numpy", fused=True).cpu().numpy()
+    for r in range(4):
+        want = onp.segment(onp.preprocess_pcg(x[r], 2000, 4125), 4125, spec)
+        assert np.isfinite(got[r]).all()
+        assert rel_err(got[r], want) < TOL, r
+    from wav2vec_heart_sounds_b200 import torchproc
+    filled = torchproc.fill_nans(_dev(x)).cpu().numpy()
+    for r in range(4):
+        assert rel_err(filled[r], onp.fill_nans(x[r])) < 1e-6
+    e = torchproc.preprocess_ecg(_dev(x[:2]), 2000, 4125, mode="numpy").cpu().numpy()
+    for r in range(2):
+        assert rel_err(e[r], onp.preprocess_ecg(x[r], 2000, 4125)) < TOL
+    clean = _dev(x[3:4])
+    assert torchproc.fill_nans(clean) is clean               # nothing to repair: no copy
+
+
 def test_fused_equals_chained_kernels(pkg):
     x = _dev(_spiky(5, 60000, seed=22))
     spec = pkg.WindowSpec(4.0)

@@ -31,6 +31,7 @@ _SIGNATURES = {
                                   ctypes.c_void_p]),
     "mpcg_despike_f32": (c_int, [c_f32p, c_i64, c_i64, c_i64, ctypes.c_double, c_int, c_int, ctypes.c_void_p,
                                  ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_fill_nans_f32": (c_int, [c_f32p, c_i64, c_int, c_i64, ctypes.c_void_p, ctypes.c_void_p]),
     "mpcg_absmax_norm_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_segment_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
                                  ctypes.c_void_p]),

@@ -3,8 +3,8 @@
 The reference builds its in-memory fragment lists one record at a time on the CPU --
 ``datasets/cinc.py:54-125`` (``build_fragments``: read record -> ``preprocess_pcg`` [-> ``preprocess_ecg``] ->
 ``segment`` -> one ``Fragment`` per window) and ``datasets/vest.py:54-113`` (six PCG channels) -- and hands them to
-``datasets/fragments.py:30-83`` (``FragmentDataset``).  Here the records of one call are grouped by length and rate,
-each group goes through ONE fused preprocess + segment launch (``pipeline.preprocess_segment``, NumPy-path arithmetic
+``datasets/fragments.py:30-83`` (``FragmentDataset``).  Here the records of one call are grouped by input rate only
+(records of any lengths ride in one ragged batch), each group goes through ONE fused preprocess + segment launch (``pipeline.preprocess_segment``, NumPy-path arithmetic
 by default because that is what the loaders call), and the windows land in one tensor in the reference's order with
 label / record index tensors beside it.  File reading (wfdb / WAV) stays with the caller: records arrive as arrays.
 
@@ -68,21 +68,29 @@ def build_fragments_batched(records: Iterable, *, fs_out: int, window, ecg: bool
         sig2 = sig[:, None] if sig.ndim == 1 else sig
         if sig2.shape[1] < c:
             raise ValueError(f"record {i} has {sig2.shape[1]} channels, {c} are needed")
-        groups.setdefault((sig2.shape[0], fs), []).append(i)
+        groups.setdefault(fs, []).append(i)                  # one launch per input rate, whatever the record lengths
     counts = [0] * len(recs)
     pieces: dict = {}
-    for (t_in, fs), idx in groups.items():
-        host = np.stack([(recs[i][0][:, None] if recs[i][0].ndim == 1 else recs[i][0])[:, :c].T for i in idx]).astype(np.float32)
-        x = torch.from_numpy(np.ascontiguousarray(host)).to(dev)                      # [B, C, T]
-        if mode == "numpy":
-            t_out = _numpy_out_len(t_in, fs, fs_out)
-            if t_out <= start_index(fs_out, window):
-                continue                                                              # segment() returns no window
-        w = preprocess_segment(x, fs, fs_out, window, kinds=kinds, mode=mode, channels_last=not mono)
-        w = w[:, 0] if mono else w                                                    # [B, N, win] or [B, N, win, C]
+    for fs, idx in groups.items():
+        if mode == "numpy":                                  # segment() returns no window for these (signalproc/segment.py:34-35)
+            idx = [i for i in idx if _numpy_out_len(recs[i][0].shape[0], fs, fs_out) > start_index(fs_out, window)]
+        if not idx:
+            continue
+        lens = np.array([recs[i][0].shape[0] for i in idx], dtype=np.int64)
+        pitch = (int(lens.max()) + 3) & ~3                   # rows start on 16-byte boundaries: the vector resampler path
+        host = np.zeros((len(idx), c, pitch), dtype=np.float32)
         for k, i in enumerate(idx):
-            pieces[i] = w[k]
-            counts[i] = int(w.shape[1])
+            sig = recs[i][0]
+            host[k, :, :sig.shape[0]] = (sig[:, None] if sig.ndim == 1 else sig)[:, :c].T
+        x = torch.from_numpy(host).to(dev)                                            # [B, C, Tmax]
+        w, n_each = preprocess_segment(x[:, 0] if mono else x, fs, fs_out, window, kinds=kinds, mode=mode,
+                                       channels_last=not mono, lengths=lens)
+        at = 0
+        for k, i in enumerate(idx):
+            n = int(n_each[k])
+            pieces[i] = w[at:at + n]
+            counts[i] = n
+            at += n
     total = sum(counts)
     shape = (total, win) if mono else (total, win, c)
     windows = torch.empty(shape, device=dev, dtype=torch.float32)

@@ -2,10 +2,10 @@
 (``datasets/cinc.py:86-94,115``, ``datasets/vest.py:50-51,84``:  ``preprocess_pcg`` / ``preprocess_ecg``
 then ``segment``), batched on the device.
 
-``preprocess_segment`` drives the fused cluster kernel (``mpcg_preprocess_segment_f32``): samples are read
-from HBM once and windows written once.  When the geometry does not fit the fused kernel (row too long for
-an 8-CTA cluster, a resampling ratio without a baked instance, ...) the same result is produced by chaining
-the stand-alone CUDA entry points; there is no CPU path either way.
+``preprocess_segment`` drives the fused row-streaming kernel (``mpcg_preprocess_segment_f32``): one launch, rows of
+any length (and, with ``lengths``, a different length per recording).  When the geometry does not fit the fused kernel
+(a resampling ratio without a baked tap set, ...) the same result is produced by chaining the stand-alone CUDA entry
+points; there is no CPU path either way.
 """
 from __future__ import annotations
 
@@ -32,10 +32,88 @@ def _kind_struct(kind: str, fs_out: float, despike: bool) -> _lib.ChainKind:
     return k
 
 
+def _out_lengths(lengths: np.ndarray, fs_in: float, fs_out: float, mode: str) -> np.ndarray:
+    """Resampled length of every recording, with the oracle's own rounding."""
+    if fs_in == fs_out:
+        return lengths.copy()
+    up, down = design.reduce_ratio(fs_in, fs_out)
+    if up == down:
+        return lengths.copy()
+    f = design.sinc_out_len if mode == "torch" else design.kaiser_out_len
+    return np.array([f(int(t), up, down) for t in lengths], dtype=np.int64)
+
+
+def _preprocess_segment_ragged(v: torch.Tensor, lengths, fs_in, fs_out, spec, kinds, despike, mode, channels_last,
+                               channel_major, planar_in, return_edits):
+    """One launch over recordings of different lengths: ``v`` is ``[B, C, Tmax]`` (rows padded to a common pitch) and
+    ``lengths[b]`` the valid samples of recording ``b``.  Returns the windows of all recordings back to back --
+    ``[sum N, win]`` (mono), ``[sum N, win, C]`` (``channels_last``) or ``[C, sum N, win]`` (``channel_major``) -- and
+    the window count of each recording (host int64 array)."""
+    b, c, pitch = v.shape
+    lengths = np.asarray(lengths.cpu() if torch.is_tensor(lengths) else lengths, dtype=np.int64).reshape(-1)
+    if lengths.shape[0] != b or (lengths < 0).any() or (lengths > pitch).any():
+        raise ValueError("lengths must hold one value in [0, T] per recording")
+    if not (planar_in or channels_last or channel_major):
+        raise ValueError("a ragged batch of multichannel recordings needs channels_last or channel_major")
+    win, hop, start = spec.window_len(fs_out), spec.hop_len(fs_out), start_index(fs_out, spec)
+    t_max = int(lengths.max()) if b else 0
+    same_rate = fs_in == fs_out
+    if same_rate:
+        up = down = 1
+        taps, off, depth = None, 0, 1
+    else:
+        up, down, taps, off, depth, _ = torchproc._resample_plan(fs_in, fs_out, max(t_max, 1), mode)
+        same_rate = up == down
+    t_out = _out_lengths(lengths, fs_in, fs_out, mode)
+    counts = np.array([int(_lib.lib().mpcg_window_count(int(t), start, win, hop)) for t in t_out], dtype=np.int64)
+    total = int(counts.sum())
+    first = np.concatenate([[0], np.cumsum(counts)[:-1]]) if b else np.zeros(0, np.int64)
+    if planar_in:
+        shape, unit = (total, win), win
+    elif channels_last:
+        shape, unit = (total, win, c), win * c
+    else:
+        shape, unit = (c, total, win), win
+    out = torch.empty(shape, device=v.device, dtype=torch.float32)
+    edits = torch.zeros(b * c, dtype=torch.int32, device=v.device) if return_edits else None
+    if b == 0 or total == 0:
+        return (out, counts, edits) if return_edits else (out, counts)
+    uniq = sorted(set(kinds))
+    if len(uniq) > 2 or c > 8:
+        raise ValueError("at most two channel kinds and eight channels per launch")
+    d = _lib.ChainDesc()
+    d.t_in, d.t_out = pitch, max(int(t_out.max()), 1)
+    d.up, d.down, d.taps_per_phase, d.offset = up, down, depth, off
+    d.taps = None if same_rate else taps.ctypes.data
+    d.despike_win = int(round(float(fs_out) / 2.0))
+    d.despike_threshold, d.despike_max_iterations = 3.0, 1000
+    d.median_mode = _lib.MEDIAN_LOWER if mode == "torch" else _lib.MEDIAN_MEAN
+    d.norm_flags = _lib.NORM_NAN_TO_NUM if mode == "torch" else _lib.NORM_PEAK_GT0
+    d.seg_start, d.seg_win, d.seg_hop, d.seg_n = start, win, hop, 0
+    d.channels_last = 2 if channel_major else (1 if channels_last else 0)
+    d.n_kinds = len(uniq)
+    for i, k in enumerate(uniq):
+        d.kinds[i] = _kind_struct(k, fs_out, despike)
+    for ch in range(c):
+        d.kind_of_channel[ch] = uniq.index(kinds[ch])
+    tabs = torch.from_numpy(np.stack([lengths, t_out]).astype(np.int32)).to(v.device)              # one small upload
+    offs = torch.from_numpy((first * unit).astype(np.int64)).to(v.device)
+    d.row_t_in, d.row_t_out, d.row_out_offset = tabs[0].data_ptr(), tabs[1].data_ptr(), offs.data_ptr()
+    d.plane_elems = total * win
+    nbytes = int(_lib.lib().mpcg_preprocess_segment_work_bytes(int(d.t_out)))
+    work = _lib.workspace(v, nbytes)
+    rc = _lib.lib().mpcg_preprocess_segment_f32(v.data_ptr(), out.data_ptr(), b, c, ctypes.byref(d), work.data_ptr(), work.numel(),
+                                                _lib.ptr(edits), None, 0, _lib.stream_ptr(v))
+    if rc == _lib.EUNSUPPORTED:
+        raise ValueError("this geometry does not fit the fused kernel")
+    _lib.check(rc, "fused preprocess+segment (ragged)")
+    return (out, counts, edits) if return_edits else (out, counts)
+
+
 def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, kinds=None, despike: bool = True,
                        mode: str = "torch", channels_last: bool = False, return_trace: bool = False,
                        trace_cap: int = 64, fused: bool | None = None, out: torch.Tensor | None = None,
-                       return_edits: bool = False, channel_major: bool = False):
+                       return_edits: bool = False, channel_major: bool = False, lengths=None):
     """``[B, T]`` -> ``[B, N, win]``  or  ``[B, C, T]`` -> ``[B, C, N, win]`` (``[B, N, win, C]`` with
     ``channels_last``): resample, (PCG only) Schmidt despike, band-limit, abs-max normalise, segment.
 
@@ -44,8 +122,12 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
     ``False`` = always chain the stand-alone kernels.  ``out``: optional preallocated result tensor.
     ``return_trace``: also return ``(edits[B*C], trace[B*C, cap, 4])``, the despike passes in the reference's order
     (this takes the fused kernel's serial despike path); ``return_edits``: also return the pass counts alone
-    (fused kernel only; the fast despike path stays on).  ``channel_major``: ``[B, C, T]`` -> ``[C, B, N, win]`` (every
+    (fused kernel only; the parallel despike rounds stay on).  ``channel_major``: ``[B, C, T]`` -> ``[C, B, N, win]`` (every
     channel's windows form one contiguous ``[B * N, win]`` batch, ready for ``augment_pcg_batch``; fused kernel only).
+    ``lengths``: valid samples of each recording of a padded ``[B, (C,) Tmax]`` batch (a ragged batch, still ONE launch);
+    the result is then ``(windows, counts)`` with all recordings' windows back to back (``[sum N, win]``,
+    ``[sum N, win, C]`` with ``channels_last``, ``[C, sum N, win]`` with ``channel_major``) and ``counts[b]`` windows of
+    recording ``b`` (the tensor rule: a recording shorter than the start pad still yields one zero window).
     """
     torchproc._check_mode(mode)
     x = _lib.require_cuda_f32(x)
@@ -57,6 +139,16 @@ def preprocess_segment(x: torch.Tensor, fs_in: float, fs_out: float, spec, *, ki
     kinds = tuple(kinds) if kinds is not None else ("pcg",) * c
     if len(kinds) != c or any(k not in _BANDS for k in kinds):
         raise ValueError(f"kinds must name 'pcg' or 'ecg' for each of the {c} channels")
+    if mode == "numpy":                                      # the NumPy chains bridge NaNs first (signalproc/preprocess.py:25,34)
+        lens_dev = None
+        if lengths is not None:
+            lens_dev = torch.as_tensor(np.asarray(lengths.cpu() if torch.is_tensor(lengths) else lengths), dtype=torch.int32).to(v.device)
+        v = torchproc.fill_nans(v.contiguous(), lens_dev)
+    if lengths is not None:
+        if return_trace or fused is False or out is not None:
+            raise ValueError("lengths= (a ragged batch) is a fused-kernel call without trace / out")
+        return _preprocess_segment_ragged(v.contiguous(), lengths, fs_in, fs_out, spec, kinds, despike, mode, channels_last,
+                                          channel_major, planar_in, return_edits)
     if channels_last and planar_in:
         raise ValueError("channels_last needs a [B, C, T] input")
     if channel_major and (planar_in or channels_last or fused is False):

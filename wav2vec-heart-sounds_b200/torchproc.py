@@ -38,6 +38,22 @@ def _as_rows(x: torch.Tensor):
     return x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x, lead
 
 
+def fill_nans(x: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
+    """NaN runs bridged by linear interpolation between the nearest valid samples, edges held (reference
+    ``signalproc/normalize.py:11-17``, the first step of the NumPy chains).  Returns ``x`` itself when it holds no NaN
+    (one device reduction), else a repaired copy.  ``lengths``: int32 ``[B]`` valid samples per recording of ``[B, C, T]``."""
+    x = _lib.require_cuda_f32(x)
+    if x.numel() == 0 or not bool(torch.isnan(x).any()):
+        return x
+    y = x.clone()
+    rows = y.reshape(-1, y.shape[-1])
+    c = 1 if lengths is None else int(rows.shape[0] // max(int(lengths.numel()), 1))
+    b = rows.shape[0] // c
+    _lib.check(_lib.lib().mpcg_fill_nans_f32(rows.data_ptr(), b, c, rows.shape[1], _lib.ptr(lengths), _lib.stream_ptr(rows)),
+               "fill NaNs")
+    return y
+
+
 def _host_f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -99,6 +115,8 @@ def resample(x: torch.Tensor, fs_in: float, fs_out: float, *, mode: str = "torch
 def abs_max_normalise(x: torch.Tensor, *, mode: str = "torch") -> torch.Tensor:
     """Zero-mean, divide by the peak magnitude, clamp to [-1, 1] per row (reference torchproc.py:62-66)."""
     _check_mode(mode)
+    if mode == "numpy":
+        x = fill_nans(x)                                     # normalize.abs_max_normalise interpolates NaNs first (:25)
     rows, lead = _as_rows(x)
     out = torch.empty_like(rows)
     flags = _lib.NORM_NAN_TO_NUM if mode == "torch" else _lib.NORM_PEAK_GT0
@@ -177,6 +195,8 @@ def preprocess_pcg(x: torch.Tensor, fs_in: float, fs_out: float, *, despike: boo
     (reference torchproc.py:101-108).  ``fused``: ``None`` = one fused cluster-kernel launch when the row fits it,
     ``False`` = always the four stand-alone kernels, ``True`` = require the fused launch."""
     x = _lib.require_cuda_f32(x)
+    if mode == "numpy":
+        x = fill_nans(x)                                     # signalproc/preprocess.py:25
     if fused is not False:
         out = _fused_rows(x, fs_in, fs_out, "pcg", despike, mode)
         if out is not None:
@@ -196,6 +216,8 @@ def preprocess_ecg(x: torch.Tensor, fs_in: float, fs_out: float, *, mode: str = 
     """resample -> 2-40 Hz band (fs-normalised) -> abs-max normalise (reference torchproc.py:111-116).
     ``fused`` as in :func:`preprocess_pcg`."""
     x = _lib.require_cuda_f32(x)
+    if mode == "numpy":
+        x = fill_nans(x)                                     # signalproc/preprocess.py:34
     if fused is not False:
         out = _fused_rows(x, fs_in, fs_out, "ecg", False, mode)
         if out is not None:
