@@ -373,12 +373,14 @@ def other_paths(dev, peak):
     rowp4, _ = ta._draw_noise(x, None, None, "philox"); m4 = ta._mask(b, cfg.prob_noise / 4, dev).reshape(b)
     sos = np.ascontiguousarray(design.eq_band_sos(fs, bands), dtype=np.float64)
     y = torch.empty_like(x)
+    work = _lib.aug_workspace(x)
 
     def chain():
         _lib.check(_lib.lib().mpcg_aug_chain_f32(x.data_ptr(), y.data_ptr(), b, t, float(fs), rowp1.data_ptr(), None,
                                                  m1.data_ptr(), 1, 2, rowp2.data_ptr(), m2.data_ptr(), sos.ctypes.data,
                                                  sos.shape[0], m3.data_ptr(), rowp4.data_ptr(), None, m4.data_ptr(), 3, 4,
-                                                 1, torch.cuda.current_stream().cuda_stream), "aug chain")
+                                                 1, work.data_ptr(), work.numel(), torch.cuda.current_stream().cuda_stream),
+                   "aug chain")
     ms = best_ms(chain)
     nbytes = 2 * b * t * 4
     res["augment_chain"] = {"workload": "configs[2]: augment_pcg_batch, 4096 windows x 64000 samples @16 kHz, one fused "

@@ -209,7 +209,10 @@ int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float 
                        const float* noise1, const float* mask1, uint64_t seed1, uint64_t sid1, const float* rowp2,
                        const float* mask2, const double* eq_sos, int eq_sections, const float* mask3,
                        const float* rowp4, const float* noise4, const float* mask4, uint64_t seed4, uint64_t sid4,
-                       int flags, void* stream);
+                       int flags, void* work, int64_t work_bytes, void* stream);
+/* work: 16-byte aligned device scratch of mpcg_aug_chain_work_bytes() bytes that receives the EQ recipe of this call (only
+ * read when eq_sections > 0), private to the call until it has finished: the library keeps no device state between calls. */
+int64_t mpcg_aug_chain_work_bytes(void);
 #define MPCG_AUG_CHAIN_COLLAPSE 1
 
 /* Zero-phase IIR filtering, scipy.signal.sosfiltfilt arithmetic (reference signalproc/filters.py:44-90): odd extension by

@@ -172,6 +172,9 @@ def test_mix_noise_arithmetic(ta):
         assert rel_err(got[r].cpu().numpy(), want) < 1e-5
     out = ta.mix_noise(torch.from_numpy(x).cuda(), torch.from_numpy(bank).cuda())          # random draws
     assert out.shape == (3, 4000) and float(out.abs().max()) <= 1.0
+    for bad in (dict(rows=[2, 0, 1], starts=starts), dict(rows=rows, starts=[0, 5001, 0]), dict(rows=[-1, 0, 0], starts=starts)):
+        with pytest.raises(ValueError):                      # injected tables are checked before the kernel trusts them
+            ta.mix_noise(torch.from_numpy(x).cuda(), torch.from_numpy(bank).cuda(), scale=scale, **bad)
 
 
 @pytest.mark.parametrize("t,rows", [(64000, 24), (8250, 40), (12347, 16), (133000, 5), (600, 9)])

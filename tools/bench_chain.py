@@ -14,11 +14,13 @@ bands = ta._draw_bands(2, 500, 5); m3 = ta._mask(B, cfg.prob_banding, "cuda").re
 rowp4, _ = ta._draw_noise(x, None, None, "philox"); m4 = ta._mask(B, cfg.prob_noise / 4, "cuda").reshape(B)
 sos = np.ascontiguousarray(design.eq_band_sos(FS, bands), dtype=np.float64)
 out = torch.empty_like(x)
+work = _lib.aug_workspace(x)
 def run(masks=(m1, m2, m3, m4)):
     rc = _lib.lib().mpcg_aug_chain_f32(x.data_ptr(), out.data_ptr(), B, T, float(FS), rowp1.data_ptr(), None, masks[0].data_ptr(),
                                        1, 2, rowp2.data_ptr(), masks[1].data_ptr(), sos.ctypes.data, sos.shape[0],
                                        masks[2].data_ptr(), rowp4.data_ptr(), None, masks[3].data_ptr(), 3, 4,
-                                       int(os.environ.get("COLLAPSE", 1)), torch.cuda.current_stream().cuda_stream)
+                                       int(os.environ.get("COLLAPSE", 1)), work.data_ptr(), work.numel(),
+                                       torch.cuda.current_stream().cuda_stream)
     assert rc == 0, rc
 def timeit(name, fn, reps=10):
     fn(); fn(); torch.cuda.synchronize()

@@ -44,7 +44,8 @@ _SIGNATURES = {
                              c_int, c_f32p, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_aug_chain_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, ctypes.c_float, c_f32p, c_f32p, c_f32p, ctypes.c_uint64,
                                    ctypes.c_uint64, c_f32p, c_f32p, ctypes.c_void_p, c_int, c_f32p, c_f32p, c_f32p, c_f32p,
-                                   ctypes.c_uint64, ctypes.c_uint64, c_int, ctypes.c_void_p]),
+                                   ctypes.c_uint64, ctypes.c_uint64, c_int, ctypes.c_void_p, c_i64, ctypes.c_void_p]),
+    "mpcg_aug_chain_work_bytes": (c_i64, []),
     "mpcg_sosfiltfilt_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p, c_i64,
                                      ctypes.c_void_p]),
     "mpcg_sosfiltfilt_epi_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p, c_i64,
@@ -171,10 +172,15 @@ def ptr(x) -> int:
 _workspaces: dict = {}
 
 
-def workspace(x: torch.Tensor, nbytes: int) -> torch.Tensor:
+def aug_workspace(x: torch.Tensor) -> torch.Tensor:
+    """Scratch of the fused augmentation chain (its EQ recipe), per (device, stream) like every workspace here."""
+    return workspace(x, int(lib().mpcg_aug_chain_work_bytes()), tag="aug")
+
+
+def workspace(x: torch.Tensor, nbytes: int, tag: str = "pre") -> torch.Tensor:
     """Device scratch for entry points that take a caller-provided workspace (the C ABI never allocates).  One grow-only
     buffer per (device, current stream): launches that may overlap on different streams never share scratch."""
-    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    key = (tag, x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=x.device)

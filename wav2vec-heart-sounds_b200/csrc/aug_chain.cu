@@ -500,19 +500,16 @@ aug_chain_kernel(const __grid_constant__ AcParams P) {
 
 }  // namespace mpcg
 
-// EQ recipes: a small ring of device-global slots, rewritten on the caller's stream only when a call brings a recipe
-// that is not resident (the ABI never allocates).
-constexpr int kAcPlanSlots = 4;
-__device__ mpcg::AcGroup g_ac_plan_dev[kAcPlanSlots][mpcg::kAcMaxGroups];
-static mpcg::AcGroup g_ac_plan_host[kAcPlanSlots][mpcg::kAcMaxGroups];
-static bool g_ac_plan_valid[kAcPlanSlots];
-static int g_ac_plan_next = 0, g_ac_plan_device = -1;
+// EQ recipes travel through the caller's workspace (the ABI never allocates and keeps no device state between calls):
+// uploaded on the caller's stream right before the launch, so calls on different streams or from different host
+// threads cannot disturb each other as long as each brings its own workspace.
+extern "C" int64_t mpcg_aug_chain_work_bytes(void) { return (int64_t)sizeof(mpcg::AcGroup) * mpcg::kAcMaxGroups; }
 
 extern "C" int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float fs, const float* rowp1,
                                   const float* noise1, const float* mask1, uint64_t seed1, uint64_t sid1,
                                   const float* rowp2, const float* mask2, const double* eq_sos, int eq_sections,
                                   const float* mask3, const float* rowp4, const float* noise4, const float* mask4,
-                                  uint64_t seed4, uint64_t sid4, int flags, void* stream_) {
+                                  uint64_t seed4, uint64_t sid4, int flags, void* work, int64_t work_bytes, void* stream_) {
   using namespace mpcg;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows < 0 || t < 0 || !(fs > 0.f) || eq_sections < 0) return MPCG_EINVAL;
@@ -562,29 +559,11 @@ extern "C" int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_
   }
   const AcGroup* dev_groups = nullptr;
   if (ngroups > 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    if (!work || ((uintptr_t)work & 15u) || work_bytes < (int64_t)sizeof(groups)) return MPCG_EINVAL;
+    // (pageable source: the runtime stages the bytes before returning, so `groups` may leave scope)
+    cudaError_t e = cudaMemcpyAsync(work, groups, sizeof(AcGroup) * ngroups, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return (int)e;
-    if (dev != g_ac_plan_device) {
-      for (int i = 0; i < kAcPlanSlots; ++i) g_ac_plan_valid[i] = false;
-      g_ac_plan_device = dev;
-    }
-    AcGroup* base = nullptr;
-    e = cudaGetSymbolAddress((void**)&base, g_ac_plan_dev);
-    if (e != cudaSuccess) return (int)e;
-    int slot = -1;
-    for (int i = 0; i < kAcPlanSlots; ++i)
-      if (g_ac_plan_valid[i] && memcmp(g_ac_plan_host[i], groups, sizeof(groups)) == 0) slot = i;
-    if (slot < 0) {
-      slot = g_ac_plan_next;
-      g_ac_plan_next = (g_ac_plan_next + 1) % kAcPlanSlots;
-      memcpy(g_ac_plan_host[slot], groups, sizeof(groups));
-      g_ac_plan_valid[slot] = true;
-      e = cudaMemcpyAsync(base + (size_t)slot * kAcMaxGroups, g_ac_plan_host[slot], sizeof(groups), cudaMemcpyHostToDevice,
-                          stream);
-      if (e != cudaSuccess) { g_ac_plan_valid[slot] = false; return (int)e; }
-    }
-    dev_groups = base + (size_t)slot * kAcMaxGroups;
+    dev_groups = reinterpret_cast<const AcGroup*>(work);
   }
 
   AcParams P;

@@ -590,6 +590,9 @@ __device__ __forceinline__ void sk_fast_frame(D& d, float* slot_buf, float* bm, 
     float new_top;
     spike_fill_span(fr, win, bm, nblk, lo, hi, changed, new_top);
     if (!changed) { stuck = 1; break; }      // a pass that moves nothing: the reference repeats it until max_iterations
+    // the fill value RAISED the maximum (a frame quieter than 1e-4): the rounds' "maxima only fall" argument does not
+    // hold for this row; nothing of this round is committed and the serial order takes over
+    if (new_top > top) { over = 1; break; }
     ++k;
     top = new_top;
     if (lane == 0) {

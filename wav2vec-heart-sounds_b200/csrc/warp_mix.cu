@@ -61,13 +61,15 @@ __device__ __forceinline__ float mx_norm(float v, double mean, double inv) {
 
 __global__ void __launch_bounds__(kMxThreads)
 mix_noise_kernel(const float* __restrict__ x, const float* __restrict__ bank, float* __restrict__ y, long long t,
-                 long long bank_len, const long long* __restrict__ src_row, const long long* __restrict__ src_start,
-                 const float* __restrict__ scale) {
+                 long long bank_rows, long long bank_len, const long long* __restrict__ src_row,
+                 const long long* __restrict__ src_start, const float* __restrict__ scale) {
   __shared__ double dscr[32];
   __shared__ float fscr[32];
   const long long row = blockIdx.x;
   const float* xr = x + row * t;
-  const float* nr = bank + src_row[row] * bank_len + src_start[row];
+  // the tables come from the caller: keep the crop inside the bank whatever they hold
+  const long long br = min(max(src_row[row], 0LL), bank_rows - 1), bs = min(max(src_start[row], 0LL), bank_len - t);
+  const float* nr = bank + br * bank_len + bs;
   const float s = scale[row];
   const int tid = threadIdx.x;
   MxStat sn{0.0, INFINITY, -INFINITY};
@@ -111,7 +113,8 @@ extern "C" int mpcg_mix_noise_f32(const float* x, const float* bank, float* y, i
   if (!x || !bank || !y || !src_row || !src_start || !scale) return MPCG_EINVAL;
   if (rows > 0x7fffffffLL) return MPCG_ERANGE;
   mix_noise_kernel<<<(unsigned)rows, kMxThreads, 0, (cudaStream_t)stream>>>(
-      x, bank, y, (long long)t, (long long)bank_len, (const long long*)src_row, (const long long*)src_start, scale);
+      x, bank, y, (long long)t, (long long)bank_rows, (long long)bank_len, (const long long*)src_row, (const long long*)src_start,
+      scale);
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }

@@ -326,4 +326,7 @@ class HostPipeline:
                 drained[b].record(self.s_out)
         for s in (self.s_in, self.s_run, self.s_out):
             entry.wait_stream(s)
+        done = torch.cuda.Event()
+        done.record(self.s_out)
+        done.synchronize()                                   # host buffers out: the last device->host copy has landed
         return out_host

@@ -73,7 +73,7 @@ def _normalise(x: torch.Tensor) -> torch.Tensor:
         out = torch.empty_like(x)
         rc = _lib.lib().mpcg_aug_chain_f32(x.data_ptr(), out.data_ptr(), b, t, 1.0, rowp.data_ptr(), None, off.data_ptr(), 0, 0,
                                            rowp.data_ptr(), off.data_ptr(), None, 0, off.data_ptr(), rowp.data_ptr(), None,
-                                           off.data_ptr(), 0, 0, 1, _lib.stream_ptr(x))
+                                           off.data_ptr(), 0, 0, 1, None, 0, _lib.stream_ptr(x))
         if rc != _lib.EUNSUPPORTED:
             _lib.check(rc, "normalise")
             return out
@@ -291,10 +291,12 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
         elif out.shape != x.shape or not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or \
                 out.data_ptr() == x.data_ptr():
             raise ValueError("out must be a contiguous CUDA float32 tensor of x's shape that does not alias x")
+        work = _lib.aug_workspace(x)
         rc = _lib.lib().mpcg_aug_chain_f32(x.data_ptr(), out.data_ptr(), b, x.shape[1], float(fs), rowp1.data_ptr(),
                                            _lib.ptr(nz1), m1.data_ptr(), seed1, sid1, rowp2.data_ptr(), m2.data_ptr(),
                                            sos.ctypes.data, sos.shape[0], m3.data_ptr(), rowp4.data_ptr(), _lib.ptr(nz4),
-                                           m4.data_ptr(), seed4, sid4, 1 if collapse else 0, _lib.stream_ptr(x))
+                                           m4.data_ptr(), seed4, sid4, 1 if collapse else 0, work.data_ptr(), work.numel(),
+                                           _lib.stream_ptr(x))
         if rc != _lib.EUNSUPPORTED:
             _lib.check(rc, "fused augmentation chain")
             return out
@@ -354,8 +356,14 @@ def mix_noise(x: torch.Tensor, bank: torch.Tensor, *, rows=None, starts=None, sc
     if tn < t:
         raise ValueError("noise records must be at least as long as the signals")
     dev = x.device
+    injected = rows is not None or starts is not None
     rows = torch.randint(0, k, (b,), device=dev) if rows is None else torch.as_tensor(rows, device=dev)
     starts = (torch.rand(b, device=dev) * (tn - t + 1)).long().clamp_(0, tn - t) if starts is None else torch.as_tensor(starts, device=dev)
+    if injected:                                             # the kernel trusts its tables: check what the caller brought
+        if rows.numel() != b or starts.numel() != b:
+            raise ValueError("rows and starts need one entry per signal")
+        if bool(((rows < 0) | (rows >= k) | (starts < 0) | (starts > tn - t)).any()):
+            raise ValueError("rows must lie in [0, K) and starts in [0, Tn - T]")
     if scale is None:
         scale = torch.where(torch.rand(b, device=dev) < 0.5, torch.zeros(b, device=dev), torch.rand(b, device=dev) * hi)
     rows, starts = rows.long().contiguous(), starts.long().contiguous()
