@@ -17,10 +17,13 @@ this repo's kernels (fused preprocess+segment, fused augmentation chain).
   roofline   the dominant kernel (fused preprocess+segment, ~70 % of a step): its algorithmic bytes (input read once +
              windows written once) / its own duration (CUDA events around each of its launches inside the timed
              region), against the measured HBM peak in MEASURED_PEAKS.json.  `stages` holds both kernels' times.
-  other_paths   (N=1) kernel times of the fused augmentation chain (configs[2]) and the tensor-core log-mel
-             (configs[3]) at their BASELINE.json shapes, measured outside the timed region.
+  other_paths   (N=1, outside the timed region) the fused preprocess kernel on configs[0]-shaped rows (480 000 samples at
+             16 kHz, the 64 recordings replicated 16x), the fused augmentation chain (configs[2]) with and without
+             `collapse`, the tensor-core log-mel (configs[3]), and `reference_gpu`: the reference's own tensor path
+             (torchaudio resample / lfilter = iir_cu_kernel, Python despike loop) on this GPU for a sub-batch.
   cpu_baseline  the NumPy oracle (the reference's CPU algorithm, restated in oracle/numpy_path.py) timed on the
-             box's host cores on a bounded sample of the same workload (rank 0, N=1 only).
+             box's host cores on a bounded sample of the same workload (rank 0, N=1 only): all cores, plus the
+             single-core figure with its per-stage split.
 
 --impl reference times that CPU implementation alone (all host threads) and prints the same line shape.
 Multi-GPU: recordings are sharded by index, no collective on the data path ("scaling": "weak").
@@ -125,6 +128,31 @@ def cpu_throughput(n_recordings: int, cores: int, seed: int = 1234, steps: int =
     return n_recordings * SECONDS * steps / dt, dt
 
 
+def cpu_single_core(n_recordings: int = 6, seed: int = 4321):
+    """One process, one thread: the configs[1] preprocessing of `n_recordings` recordings stage by stage."""
+    import numpy as np
+    from oracle import numpy_path as onp
+    from wav2vec_heart_sounds_b200.synth import synth_pair
+    x = synth_pair(n_recordings, T_IN, FS_IN, seed=seed).numpy().astype(np.float64)
+    spec = onp.WindowSpec(WINDOW_S)
+    st = {"resample": 0.0, "despike": 0.0, "band": 0.0, "normalise": 0.0, "segment": 0.0}
+    t_all = time.perf_counter()
+    for i in range(n_recordings):
+        cols = []
+        for ch, band in ((0, onp.PCG_BAND), (1, onp.ECG_BAND)):
+            t0 = time.perf_counter(); v = onp.resample(onp.fill_nans(x[i, ch]), FS_IN, FS_OUT); st["resample"] += time.perf_counter() - t0
+            if ch == 0:
+                t0 = time.perf_counter(); v = onp.remove_spikes(v, FS_OUT); st["despike"] += time.perf_counter() - t0
+            t0 = time.perf_counter(); v = onp.bandpass_cascade(v, FS_OUT, *band); st["band"] += time.perf_counter() - t0
+            t0 = time.perf_counter(); v = onp.abs_max_normalise(v); st["normalise"] += time.perf_counter() - t0
+            cols.append(v)
+        t0 = time.perf_counter(); onp.segment(np.stack(cols, axis=1), FS_OUT, spec); st["segment"] += time.perf_counter() - t0
+    dt = time.perf_counter() - t_all
+    return {"value": n_recordings * SECONDS / dt, "unit": UNIT, "cores": 1, "recordings": n_recordings,
+            "what": "NumPy/SciPy float64 preprocessing + windows of both channels (no augmentation), OMP_NUM_THREADS=1",
+            "ms_per_recording": {k: 1e3 * v / n_recordings for k, v in st.items()}}
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -149,7 +177,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": {"workload": WORKLOAD, "sample": sample, "recordings_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -298,6 +326,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * RECORDINGS * SECONDS * e2e_steps / float(t.item())
     same = bool(torch.equal(out_host[1, :8], out[1, :8].cpu()))               # the ECG windows (the PCG ones carry fresh random draws)
+    # the ceiling of that leg on this box: the same bytes as bare pinned copies (one cudaMemcpyAsync per chunk and
+    # direction, both directions at once, every rank at the same time), no kernel in between
+    copy_s = bare_copy_seconds(x_host, out_host, dev, barrier, chunk=64)
+    t = torch.tensor([copy_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_value = world * RECORDINGS * SECONDS / float(t.item())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -315,10 +350,11 @@ def run_ours(args):
                            "preprocess_only_audio_s_per_s": RECORDINGS * SECONDS / (pre_ms * 1e-3),
                            "augment_GB/s": aug_bytes / (aug_ms * 1e-3) / 1e9},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hp.h2d_bytes,
-                        "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "matches_device_run": same},
+                        "d2h_bytes_per_step": hp.d2h_bytes, "steps": e2e_steps, "matches_device_run": same,
+                        "bare_copy_ceiling": copy_value, "frac_of_copy_ceiling": e2e_value / copy_value},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": recorded_traffic(), "algorithmic_bytes_per_launch": algo_bytes,
-                             "kernel": "fused_preprocess_kernel<33,16,30,4>", "share_of_step": pre_ms / step_ms,
+                             "kernel": "fused_stream_kernel<33,16,30,4>", "share_of_step": pre_ms / step_ms,
                              "peak_source": peak_src},
                 "clocks": clocks.summary()}
         if world == 1 and not args.no_extras:
@@ -333,7 +369,7 @@ def run_ours(args):
                 proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", str(n)], capture_output=True,
                                       text=True, timeout=240, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
                 leg = json.loads(proc.stdout.strip().splitlines()[-1])
-                line["cpu_baseline"] = {"value": leg["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                line["cpu_baseline"] = {"value": leg["value"], "unit": UNIT, "cores": cores, "kind": "port", "single_core": leg.get("single_core"),
                                         "sample": f"{n} of the {RECORDINGS} recordings, NumPy/SciPy float64 oracle "
                                                   f"(oracle/numpy_path.py) + float64 torchaug chain (oracle/torch_path.py), "
                                                   f"{cores} worker processes, {leg['seconds']:.1f} s"}
@@ -343,6 +379,30 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bare_copy_seconds(x_host, out_host, dev, barrier, chunk=64, reps=3):
+    """Seconds per step of the e2e leg's PCIe traffic alone: its H2D and D2H bytes as plain pinned cudaMemcpyAsync
+    calls in the same chunking, the two directions on two streams at once, nothing else on the device."""
+    n = x_host.shape[0]
+    d_in = torch.empty((chunk,) + tuple(x_host.shape[1:]), device=dev)
+    d_out = torch.empty((out_host.shape[0], chunk) + tuple(out_host.shape[2:]), device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = None
+    for _ in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        for lo in range(0, n, chunk):
+            hi = min(lo + chunk, n)
+            with torch.cuda.stream(s_in):
+                d_in[: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                for c in range(out_host.shape[0]):
+                    out_host[c, lo:hi].copy_(d_out[c, : hi - lo], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)       # (first pass is the warm-up)
+    return best
 
 
 def other_paths(dev, peak):
@@ -361,6 +421,50 @@ def other_paths(dev, peak):
         return best
 
     res = {}
+    import wav2vec_heart_sounds_b200 as pkg
+    from wav2vec_heart_sounds_b200.synth import synth_pcg, synth_pair
+    # configs[0]-shaped rows through the fused kernel: 64 recordings of 30 s at 2 kHz -> 16 kHz (480 000 samples per row,
+    # 26 tiles streamed by one CTA), despike, 25-450 Hz band, abs-max norm, 4 s windows; replicated 16x so that the
+    # launch fills the machine
+    x0 = synth_pcg(64, T_IN, float(FS_IN), seed=11, device=dev).repeat(16, 1)
+    spec4 = pkg.WindowSpec(4.0)
+    out0 = pkg.preprocess_segment(x0, FS_IN, 16000, spec4, fused=True)
+    ms = best_ms(lambda: pkg.preprocess_segment(x0, FS_IN, 16000, spec4, fused=True, out=out0))
+    nbytes = 4 * (x0.numel() + out0.numel())
+    res["config0"] = {"workload": "configs[0] x16: 1024 single-channel PCG rows, 30 s @2 kHz -> 16 kHz (480000 samples), despike, "
+                                  "25-450 Hz band, abs-max norm, 4 s / 0.25 s-overlap windows, one fused launch",
+                      "ms": ms, "audio_s_per_s": x0.shape[0] * SECONDS / (ms * 1e-3), "algorithmic_bytes": nbytes,
+                      "GB/s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
+                      "target_audio_s_per_s_at_0.6": 0.6 * peak * 1e9 / 67733.0}
+    del x0, out0
+    # the reference's own tensor path on this GPU (torchproc arithmetic: torchaudio resample + lfilter -> iir_cu_kernel,
+    # the Python despike loop with its host syncs), float32, on a sub-batch of the headline workload; ours on the same rows
+    try:
+        from oracle import torch_path as otp
+        from oracle import numpy_path as onp
+        nsub = 32
+        xs = synth_pair(nsub, T_IN, FS_IN, seed=1234, device=dev)
+
+        def ref_gpu():
+            p = otp.preprocess_pcg(xs[:, 0], FS_IN, FS_OUT)
+            e = otp.preprocess_ecg(xs[:, 1], FS_IN, FS_OUT)
+            return otp.segment(p, FS_OUT, onp.WindowSpec(WINDOW_S)), otp.segment(e, FS_OUT, onp.WindowSpec(WINDOW_S))
+        ref_gpu()                                             # warm-up (cuDNN / kernel selection); its despike loop takes seconds
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref_gpu()
+        torch.cuda.synchronize()
+        ref_ms = 1e3 * (time.perf_counter() - t0)
+        outs = pkg.preprocess_segment(xs, FS_IN, FS_OUT, spec4, kinds=KINDS, fused=True)
+        our_ms = best_ms(lambda: pkg.preprocess_segment(xs, FS_IN, FS_OUT, spec4, kinds=KINDS, fused=True, out=outs))
+        res["reference_gpu"] = {"workload": f"{nsub} recordings x (PCG, ECG) of the headline workload, preprocessing + windows, float32, "
+                                            "the reference's tensor-path arithmetic (torchaudio resample/lfilter kernels, Python "
+                                            "despike loop) on this GPU vs one fused launch of this repo",
+                                "reference_ms": ref_ms, "ours_ms": our_ms, "ours_over_theirs": ref_ms / our_ms,
+                                "reference_audio_s_per_s": nsub * SECONDS / (ref_ms * 1e-3)}
+        del xs, outs
+    except Exception as exc:                                  # never lose the line over a side measurement
+        res["reference_gpu"] = {"error": f"{type(exc).__name__}: {exc}"}
     # configs[2]: full torchaug chain on 4096 windows x 64000 samples @ 16 kHz, in-kernel Philox noise, default masks
     b, t, fs = 4096, 64000, 16000
     g = torch.Generator(device=dev).manual_seed(7)
@@ -389,6 +493,9 @@ def other_paths(dev, peak):
                             "algorithmic_bytes": nbytes, "GB/s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
     ms_api = best_ms(lambda: ta.augment_pcg_batch(x, fs, cfg, noise="philox"))
     res["augment_chain"]["ms_through_python_api"] = ms_api
+    # collapse=False re-normalises masked-off rows too, as the reference does (torchaug.py:240-243); same result within 1e-5
+    ms_nc = best_ms(lambda: ta.augment_pcg_batch(x, fs, cfg, noise="philox", collapse=False))
+    res["augment_chain"]["ms_through_python_api_collapse_off"] = ms_nc
     del x, y
     # configs[3]: log-mel conditioning of 8192 windows x 64000 samples @ 16 kHz on the tensor-core tier
     xm = torch.randn(8192, 64000, device=dev, generator=g)
@@ -417,7 +524,7 @@ def main():
     if args.cpu_leg > 0:
         torch.set_num_threads(1)
         v, dt = cpu_throughput(args.cpu_leg, host_cores())
-        print(json.dumps({"value": v, "seconds": dt}))
+        print(json.dumps({"value": v, "seconds": dt, "single_core": cpu_single_core()}))
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -53,8 +53,8 @@ def butter_ba(cutoff: float, fs: float, kind: str, order: int):
 
 
 def _lfilter(x, b, a):
-    bt = torch.as_tensor(b, dtype=x.dtype)
-    at = torch.as_tensor(a, dtype=x.dtype)
+    bt = torch.as_tensor(b, dtype=x.dtype, device=x.device)
+    at = torch.as_tensor(a, dtype=x.dtype, device=x.device)
     return AF.lfilter(x, at, bt, clamp=False, batching=True)
 
 
