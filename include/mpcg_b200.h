@@ -168,7 +168,9 @@ int mpcg_preprocess_segment_f32(const float* x, float* out, int64_t recordings, 
 
 /* One stage: w = transform(x) on rows whose mask is non-zero (mask NULL: every row), w = x elsewhere; then
  * y = w, or with normalise != 0  y = _normalise(w)  -- i.e. torchaug._apply (torchaug.py:34-36) with the
- * Bernoulli mask given.  rowp: device [rows, 8] floats = (a0, f0, p0, a1, f1, p1, -, -) for the sine ops,
+ * Bernoulli mask given.  normalise == 2 re-normalises only the rows whose mask is on and passes the others through
+ * untouched: the NumPy primitives normalise inside the transform (augment/primitives.py:44-70), so a stage that the
+ * pipeline skips leaves its signal as it was (augment/pipelines.py:47-60).  rowp: device [rows, 8] floats = (a0, f0, p0, a1, f1, p1, -, -) for the sine ops,
  * (scale*std, ...) for noise.  noise: device [rows, t] standard normals or NULL (Philox keyed by seed/stream_id). */
 int mpcg_aug_stage_f32(const float* x, float* y, int64_t rows, int64_t t, int op, float fs, const float* rowp,
                        const float* noise, const float* mask, int normalise, uint64_t seed, uint64_t stream_id,
@@ -323,6 +325,17 @@ int mpcg_time_warp_f32(const float* x, float* y, int64_t rows, int64_t t, int64_
 int mpcg_mix_noise_f32(const float* x, const float* bank, float* y, int64_t rows, int64_t t, int64_t bank_rows,
                        int64_t bank_len, const int64_t* src_row, const int64_t* src_start, const float* scale,
                        void* stream);
+
+/* Recorded clinical noise for a batch (reference augment/noise_sources.py:33-64 after its file reads): for row r
+ *   out[r] = sum_c scale[r, c] * N(bank[src_row[r, c], src_start[r, c] : src_start[r, c] + t]),   c < ncomp <= 4,
+ * N = NumPy abs_max_normalise of the cropped record; with normalise_sum != 0 the sum is normalised again when its peak is
+ * non-zero (pcg_noise, :48-50), otherwise it is returned as it is (ecg_noise, :61).  bank: device [bank_rows, bank_len]
+ * records already resampled to the signal rate (mpcg_resample_f32 with the SciPy taps = the reference's resample_poly);
+ * src_row / src_start: device int64 [rows, ncomp]; scale: device [rows, ncomp] (a zero scale skips the component's
+ * statistics, as the reference's choice([0, U]) does).  Entries are clamped into the bank. */
+int mpcg_noise_combine_f32(const float* bank, float* out, int64_t rows, int64_t t, int64_t bank_rows, int64_t bank_len,
+                           int ncomp, const int64_t* src_row, const int64_t* src_start, const float* scale,
+                           int normalise_sum, void* stream);
 
 /* Profiling aid (tools/ only): device buffer [ctas, 16] of int64 that the fused kernel fills with clock64 stamps at
  * its phase boundaries; NULL switches it off.  Not part of the data path. */

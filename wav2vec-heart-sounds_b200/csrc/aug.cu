@@ -27,7 +27,8 @@ aug_stage_kernel(const float* __restrict__ x, float* __restrict__ y, long long t
   const int tid = threadIdx.x;
   const long long nq = (t + 3) >> 2;                                 // groups of four samples
   double mean = 0.0, inv_peak = 1.0;
-  if (NORMALISE) {
+  const bool norm_row = NORMALISE && (!a.norm_masked_only || on);     // (block-uniform)
+  if (norm_row) {
     RowStats st;
     stats_init(st);
     for (long long q = tid; q < nq; q += kAgThreads) {
@@ -57,7 +58,7 @@ aug_stage_kernel(const float* __restrict__ x, float* __restrict__ y, long long t
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float w = on ? stage_value(a, p, nz, row, 4 * q + k, vv[k], zz[k]) : vv[k];
-        ww[k] = NORMALISE ? norm_apply(w, mean, inv_peak) : w;
+        ww[k] = norm_row ? norm_apply(w, mean, inv_peak) : w;
       }
       *reinterpret_cast<float4*>(yr + 4 * q) = make_float4(ww[0], ww[1], ww[2], ww[3]);
       continue;
@@ -68,7 +69,7 @@ aug_stage_kernel(const float* __restrict__ x, float* __restrict__ y, long long t
       if (i < t) {
         const float v = xr[i];
         const float w = on ? stage_value(a, p, nz, row, i, v, zz[k]) : v;
-        yr[i] = NORMALISE ? norm_apply(w, mean, inv_peak) : w;
+        yr[i] = norm_row ? norm_apply(w, mean, inv_peak) : w;
       }
     }
   }
@@ -191,6 +192,7 @@ extern "C" int mpcg_aug_stage_f32(const float* x, float* y, int64_t rows, int64_
   if (rows > 0x7fffffffLL) return MPCG_ERANGE;
   StageArgs a;
   a.op = op; a.fs = fs; a.rowp = rowp; a.noise = noise; a.mask = mask; a.seed = seed; a.stream = stream_id;
+  a.norm_masked_only = (normalise == 2) ? 1 : 0;
   if (normalise)
     aug_stage_kernel<true><<<(unsigned)rows, kAgThreads, 0, (cudaStream_t)stream>>>(x, y, (long long)t, a);
   else

@@ -68,6 +68,7 @@ struct StageArgs {
   const float* rowp;         // [rows, 8] per-row parameters (see include/mpcg_b200.h)
   const float* noise;        // [rows, t] injected standard normals, or NULL -> Philox
   const float* mask;         // [rows] 0/1, or NULL -> all rows transformed
+  int norm_masked_only;      // 1: only the rows whose mask is on are re-normalised (the NumPy primitives' rule)
   unsigned long long seed, stream;
 };
 

@@ -89,7 +89,73 @@ mix_noise_kernel(const float* __restrict__ x, const float* __restrict__ bank, fl
     y[row * t + i] = mx_norm(xr[i] + s * mx_norm(nr[i], mn, in_), ms, is_);
 }
 
+// out[r] = sum_c scale_c N(crop_c), optionally normalised again: the arithmetic of noise_sources.pcg_noise / ecg_noise.
+__global__ void __launch_bounds__(kMxThreads)
+noise_combine_kernel(const float* __restrict__ bank, float* __restrict__ out, long long t, long long bank_rows,
+                     long long bank_len, int ncomp, const long long* __restrict__ src_row,
+                     const long long* __restrict__ src_start, const float* __restrict__ scale, int normalise_sum) {
+  __shared__ double dscr[32];
+  __shared__ float fscr[32];
+  const long long row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* nr[4];
+  float sc[4];
+  double mn[4], in_[4];
+  for (int c = 0; c < ncomp; ++c) {
+    const long long br = min(max(src_row[row * ncomp + c], 0LL), bank_rows - 1);
+    const long long bs = min(max(src_start[row * ncomp + c], 0LL), bank_len - t);
+    nr[c] = bank + br * bank_len + bs;
+    sc[c] = scale[row * ncomp + c];
+    mn[c] = 0.0; in_[c] = 1.0;
+    if (sc[c] != 0.f) {                                      // (block-uniform) statistics of the crop
+      MxStat s{0.0, INFINITY, -INFINITY};
+      for (long long i = tid; i < t; i += kMxThreads) {
+        const float v = nr[c][i];
+        s.sum += (double)v; s.lo = fminf(s.lo, v); s.hi = fmaxf(s.hi, v);
+      }
+      mx_finish(s, t, mn[c], in_[c], dscr, fscr);
+    }
+  }
+  auto value = [&](long long i) {
+    float v = 0.f;
+    for (int c = 0; c < ncomp; ++c)
+      if (sc[c] != 0.f) v += sc[c] * mx_norm(nr[c][i], mn[c], in_[c]);
+    return v;
+  };
+  if (!normalise_sum) {
+    for (long long i = tid; i < t; i += kMxThreads) out[row * t + i] = value(i);
+    return;
+  }
+  MxStat ss{0.0, INFINITY, -INFINITY};
+  for (long long i = tid; i < t; i += kMxThreads) {
+    const float v = value(i);
+    ss.sum += (double)v; ss.lo = fminf(ss.lo, v); ss.hi = fmaxf(ss.hi, v);
+  }
+  const float amax = fmaxf(fabsf(block_min<kMxThreads>(ss.lo, fscr)), fabsf(block_max<kMxThreads>(ss.hi, fscr)));
+  double ms, is_;
+  mx_finish(ss, t, ms, is_, dscr, fscr);
+  for (long long i = tid; i < t; i += kMxThreads) {
+    const float v = value(i);
+    out[row * t + i] = amax > 0.f ? mx_norm(v, ms, is_) : v;   // "if np.max(np.abs(combined)) > 0" (noise_sources.py:48)
+  }
+}
+
 }  // namespace mpcg
+
+extern "C" int mpcg_noise_combine_f32(const float* bank, float* out, int64_t rows, int64_t t, int64_t bank_rows,
+                                      int64_t bank_len, int ncomp, const int64_t* src_row, const int64_t* src_start,
+                                      const float* scale, int normalise_sum, void* stream) {
+  using namespace mpcg;
+  if (rows < 0 || t < 0 || bank_rows < 1 || bank_len < t || ncomp < 1 || ncomp > 4) return MPCG_EINVAL;
+  if (rows == 0 || t == 0) return MPCG_OK;
+  if (!bank || !out || !src_row || !src_start || !scale) return MPCG_EINVAL;
+  if (rows > 0x7fffffffLL) return MPCG_ERANGE;
+  noise_combine_kernel<<<(unsigned)rows, kMxThreads, 0, (cudaStream_t)stream>>>(
+      bank, out, (long long)t, (long long)bank_rows, (long long)bank_len, ncomp, (const long long*)src_row,
+      (const long long*)src_start, scale, normalise_sum);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}
 
 extern "C" int mpcg_time_warp_f32(const float* x, float* y, int64_t rows, int64_t t, int64_t n_out, double rate,
                                   void* stream) {

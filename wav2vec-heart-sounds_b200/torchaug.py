@@ -52,7 +52,7 @@ def _dev_f32(v, device, shape=None) -> torch.Tensor:
 def _stage(x, op, *, fs=1.0, rowp=None, noise=None, mask=None, normalise=False, seed=0, stream_id=0):
     out = torch.empty_like(x)
     _lib.check(_lib.lib().mpcg_aug_stage_f32(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], op, float(fs),
-                                             _lib.ptr(rowp), _lib.ptr(noise), _lib.ptr(mask), 1 if normalise else 0,
+                                             _lib.ptr(rowp), _lib.ptr(noise), _lib.ptr(mask), int(normalise),
                                              int(seed), int(stream_id), _lib.stream_ptr(x)), "augmentation stage")
     return out
 
