@@ -496,6 +496,28 @@ def other_paths(dev, peak):
     # collapse=False re-normalises masked-off rows too, as the reference does (torchaug.py:240-243); same result within 1e-5
     ms_nc = best_ms(lambda: ta.augment_pcg_batch(x, fs, cfg, noise="philox", collapse=False))
     res["augment_chain"]["ms_through_python_api_collapse_off"] = ms_nc
+    # configs[2] in full: the composed pipeline of augment/pipelines.py:43-61 on the same 4096 windows -- min-max, HPSS
+    # recombination (p = 0.75; transform sizes fixed at a middle setting of the reference's ranges so that the figure is
+    # reproducible), noise, micro-stretch, wandering volume, noise, EQ, abs-max -- per-row masks, default probabilities
+    try:
+        import random as _random
+        from wav2vec_heart_sounds_b200 import pipelines as pl
+        _random.seed(7); np.random.seed(7)
+        hp = dict(n_fft1=1024, hop1=64, n_fft2=1024, hop2=64, margin1=(1.5, 1.5), margin2=(2.5, 2.5), kernel1=(17, 17),
+                  kernel2=(17, 17), w1=[1.0, 2.0, 3.0, 4.0], w2=[4.0, 3.0, 2.0, 1.0], w_mix=0.03)
+        sub = x[:1024]
+
+        def full():
+            return pl.augment_pcg(sub, fs, cfg, draws={"hpss": hp})
+        full(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); full(); torch.cuda.synchronize()
+        ms_full = 1e3 * (time.perf_counter() - t0)
+        res["augment_full_chain"] = {"workload": "configs[2] full chain incl. HPSS: pipelines.augment_pcg on 1024 of the 4096 windows x 64000 "
+                                                 "@16 kHz (HPSS n_fft 1024 / hop 64 / medians 17, p = 0.75; wall clock incl. host orchestration)",
+                                     "ms_per_1024_windows": ms_full, "windows_per_s": 1024 / (ms_full * 1e-3),
+                                     "ms_for_4096_windows_extrapolated": 4 * ms_full}
+    except Exception as exc:
+        res["augment_full_chain"] = {"error": f"{type(exc).__name__}: {exc}"}
     del x, y
     # configs[3]: log-mel conditioning of 8192 windows x 64000 samples @ 16 kHz on the tensor-core tier
     xm = torch.randn(8192, 64000, device=dev, generator=g)

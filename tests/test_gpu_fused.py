@@ -380,3 +380,41 @@ def test_channel_major_layout_and_host_pipeline_augment(pkg):
     op = plain.empty_output()
     plain(x.cpu().pin_memory(), op)
     assert torch.equal(op, planar.cpu())
+
+
+def test_no_writes_outside_the_output_and_workspace(pkg):
+    """compute-sanitizer is not available on the GPU pool, so the hot kernel's global stores are fenced in by hand: the
+    output tensor and the workspace are carved out of larger buffers whose margins hold a sentinel, for single-tile,
+    multi-tile (despiked, parked rows), 8/1, ragged and channels-last launches; the margins must come back untouched
+    and every output element must have been written (no sentinel left inside)."""
+    import ctypes
+    from wav2vec_heart_sounds_b200 import _lib
+    from wav2vec_heart_sounds_b200.synth import synth_pair
+    SENT = -123456.0
+    pad = 4096
+    x = synth_pair(6, 60000, 2000, seed=17, device="cuda")
+    x[1, 0, 500] += 40.0
+    cases = [dict(fs_out=4125, ws=4.0, kw=dict(kinds=("pcg", "ecg"), channel_major=True), xin=x),
+             dict(fs_out=4125, ws=4.0, kw=dict(kinds=("pcg", "ecg"), channels_last=True), xin=x),
+             dict(fs_out=16000, ws=4.0, kw=dict(), xin=x[:2, 0].contiguous()),
+             dict(fs_out=4125, ws=1.0, kw=dict(mode="numpy"), xin=x[:, 0, :9001].contiguous())]
+    for c in cases:
+        ref = pkg.preprocess_segment(c["xin"], 2000, c["fs_out"], pkg.WindowSpec(c["ws"]), fused=True, **c["kw"])
+        big = torch.full((ref.numel() + 2 * pad,), SENT, device="cuda")
+        out = big[pad:pad + ref.numel()].view(ref.shape)
+        # a private, guarded workspace for this stream: swap it into the shim's cache
+        key = ("pre", c["xin"].device.index, torch.cuda.current_stream().cuda_stream)
+        need = _lib.workspace(c["xin"], 1).numel()
+        wbig = torch.full((need + 2 * pad,), 0x5A, dtype=torch.uint8, device="cuda")
+        lo = (-wbig.data_ptr() - pad) % 16 + pad                      # keep the carved workspace 16-byte aligned
+        old = _lib._workspaces[key]
+        _lib._workspaces[key] = wbig[lo:lo + need]
+        try:
+            pkg.preprocess_segment(c["xin"], 2000, c["fs_out"], pkg.WindowSpec(c["ws"]), fused=True, out=out, **c["kw"])
+            torch.cuda.synchronize()
+        finally:
+            _lib._workspaces[key] = old
+        assert bool((big[:pad] == SENT).all()) and bool((big[pad + ref.numel():] == SENT).all())
+        assert bool((wbig[:lo] == 0x5A).all()) and bool((wbig[lo + need:] == 0x5A).all())
+        assert not bool((out == SENT).any())
+        assert torch.equal(out, ref)
