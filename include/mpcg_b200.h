@@ -337,6 +337,16 @@ int mpcg_noise_combine_f32(const float* bank, float* out, int64_t rows, int64_t 
                            int ncomp, const int64_t* src_row, const int64_t* src_start, const float* scale,
                            int normalise_sum, void* stream);
 
+/* Time-varying sinc delay-and-sum of a multichannel batch (reference classify/beamformer.py:41-55):
+ *   out[b, t] = sum_m ( sum_k xp[b, m, t + k] * kern_k(delays[b, m, t]) )^2,   kern_k(d) = sinc(k - K/2 - d) window[k] / sum_k(..),
+ * xp = x reflect-padded by K/2.  x, delays: device [batch, mics, t]; window: HOST [kernel_size] (Hamming in the reference,
+ * kernel_size odd, <= 129).  aux (optional, device, [batch, mics, t, 4] floats) receives what the backward pass needs.
+ * The backward entry turns grad_out [batch, t] into grad_x and / or grad_delays [batch, mics, t] (either may be NULL). */
+int mpcg_beamform_fwd_f32(const float* x, const float* delays, float* out, float* aux, int64_t batch, int mics, int64_t t,
+                          const float* window, int kernel_size, void* stream);
+int mpcg_beamform_bwd_f32(const float* delays, const float* aux, const float* grad_out, float* grad_x, float* grad_delays,
+                          int64_t batch, int mics, int64_t t, const float* window, int kernel_size, void* stream);
+
 /* Profiling aid (tools/ only): device buffer [ctas, 16] of int64 that the fused kernel fills with clock64 stamps at
  * its phase boundaries; NULL switches it off.  Not part of the data path. */
 void mpcg_debug_set_phase_clock_buffer(void* dev_ptr);

@@ -378,5 +378,43 @@ def gen_condition_fixture(sp, versions):
     np.savez_compressed(OUT / "gen_condition.npz", versions=str(versions), **g)
 
 
+def beamformer_fixture():
+    """G7: the sinc delay-and-sum gather with its gradients, from the reference's own module
+    (classify/beamformer.py:41-55) in float64.  The file is loaded on its own: the package __init__ pulls in
+    transformers, which does not import under the librosa stub."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("ref_beamformer", REF_SRC / "mpcg_wav2vec" / "classify" / "beamformer.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(7)
+    bf = mod.TimeVaryingSincBeamformer(num_mics=3, fs=4125.0).double().eval()
+    b, m, t = 2, 3, 600
+    x = torch.randn(b, m, t, dtype=torch.float64, requires_grad=True)
+    # delays up to 12 samples keep the sinc's main lobe inside the 41-tap window; beyond ~20 the taps that remain sum to
+    # almost nothing and the reference's own normalisation (kernel / kernel.sum()) amplifies rounding by orders of
+    # magnitude -- the module allows it (clamp at 41.25), so one stretch of such delays is kept for a looser check
+    delays = torch.rand(b, m, t, dtype=torch.float64) * 12.0
+    delays[1, 1, 400:420] = torch.rand(20, dtype=torch.float64) * 20.0 + 21.0
+    delays[0, 0, :50] = 0.0                                  # the clamp's lower end
+    delays[1, 2, 100:110] = 3.0                              # an integer delay: the sinc(0) tap
+    delays.requires_grad_(True)
+    out = torch.stack([bf._delay_channel(x[:, i, :], delays[:, i, :]) ** 2 for i in range(m)], dim=1).sum(dim=1)
+    g = torch.randn(b, t, dtype=torch.float64)
+    out.backward(g)
+    with torch.no_grad():
+        full = bf(x.detach())                                # the whole module: predictor + clamp + gather
+        own_delays = torch.clamp(bf.delay_predictor(x.detach()), 0.0, bf.max_delay_samples)
+    state = {k: v.numpy() for k, v in bf.state_dict().items()}
+    np.savez_compressed(OUT / "beamformer.npz", x=x.detach().numpy(), delays=delays.detach().numpy(), out=out.detach().numpy(),
+                        grad_out=g.numpy(), grad_x=x.grad.numpy(), grad_delays=delays.grad.numpy(), kernel_size=41,
+                        module_out=full.numpy(), module_delays=own_delays.numpy(), state_keys=np.array(list(state)),
+                        **{"state__" + k: v for k, v in state.items()}, versions=f"torch {torch.__version__}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "beamformer":
+        beamformer_fixture()
+    else:
+        main()
+        beamformer_fixture()

@@ -225,3 +225,15 @@ def test_load_join_indices(tmp_path):
     path.write_text(json.dumps({"segments": [[0], [1500, 1600], [500], [], [1000, 7], [500]], "last_index": 1500, "fs": 1000}))
     assert H.load_join_indices(path, fs_out=2000) == [1000, 2000, 3000]
     assert H.load_join_indices(path, fs_out=1000) == [500, 1000, 1500]
+
+
+def test_beamformer_oracle_matches_reference_vectors(golden):
+    """oracle/beamformer_path.py against the outputs of the reference's own module (classify/beamformer.py:41-55, float64)."""
+    from oracle import beamformer_path as ob
+    g = golden("beamformer.npz")
+    got = ob.delay_and_sum(g["x"], g["delays"], int(g["kernel_size"]))
+    well = np.ones(g["out"].shape[1], bool)
+    well[400:420] = False                                    # delays beyond the window: ill-conditioned by construction
+    assert np.abs(got - g["out"])[:, well].max() < 1e-11 * np.abs(g["out"][:, well]).max()
+    assert np.abs(got - g["out"]).max() < 1e-7 * np.abs(g["out"]).max()
+    assert np.abs(ob.delay_and_sum(g["x"], g["module_delays"], 41) - g["module_out"]).max() < 1e-11 * np.abs(g["module_out"]).max()

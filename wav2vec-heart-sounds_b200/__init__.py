@@ -10,9 +10,9 @@ from . import torchproc, torchaug
 from .torchaug import AugmentConfig, augment_pcg_batch
 from .pipeline import preprocess_segment
 from .spectrogram import MelConfig, log_mel
-from . import datasets, envelopes, filters, heart_cycles, normalize, pipelines
+from . import beamformer, datasets, envelopes, filters, heart_cycles, normalize, pipelines
 from .datasets import (build_fragments_batched, FragmentBatch, FragmentTensorDataset, device_batch_transform, device_augment_fn,
                        condition_generator_batch)
 
 __all__ = ["torchproc", "MelConfig", "log_mel", "torchaug", "AugmentConfig", "augment_pcg_batch", "preprocess_segment", "WindowSpec", "WINDOWS", "default_window", "design",
-           "datasets", "pipelines", "filters", "envelopes", "normalize", "heart_cycles", "build_fragments_batched", "FragmentBatch", "FragmentTensorDataset", "device_batch_transform", "device_augment_fn", "condition_generator_batch"]
+           "datasets", "pipelines", "beamformer", "filters", "envelopes", "normalize", "heart_cycles", "build_fragments_batched", "FragmentBatch", "FragmentTensorDataset", "device_batch_transform", "device_augment_fn", "condition_generator_batch"]

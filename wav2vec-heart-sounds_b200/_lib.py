@@ -74,6 +74,9 @@ _SIGNATURES = {
     "mpcg_time_warp_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, ctypes.c_double, ctypes.c_void_p]),
     "mpcg_mix_noise_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64, ctypes.c_void_p, ctypes.c_void_p,
                                    c_f32p, ctypes.c_void_p]),
+    "mpcg_beamform_fwd_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p]),
+    "mpcg_beamform_bwd_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_int, c_i64, ctypes.c_void_p, c_int,
+                                      ctypes.c_void_p]),
     "mpcg_noise_combine_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_i64, c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p, c_f32p,
                                        c_int, ctypes.c_void_p]),
     "mpcg_aug_stage_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, ctypes.c_float, c_f32p, c_f32p, c_f32p, c_int,
