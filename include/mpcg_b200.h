@@ -272,17 +272,20 @@ int mpcg_row_normalise_f32(const float* x, float* y, double* stats, int64_t rows
                            double hi, int flags, void* stream);
 
 /* Tensor-core tier of the same transform (tcgen05, split-fp16 operands, fp32 accumulation in TMEM) for configurations
- * with n_fft = Q * hop (Q <= 8), win_length == n_fft and at most 126 weighted bins per call.  The GEMM is the rectangular-window
- * partial DFT of every hop row; frames are assembled by a Q-term twiddle sum and the Hann window is applied in the
- * frequency domain.  basis_f16: device, [2 (hi, lo)][ncols * hop] fp16 in the canonical K-major core-matrix order
- * (byte offset of element (n, j): (n>>3)*hop*16 + (j>>3)*128 + (n&7)*16 + (j&7)*2), columns = cos then -sin of bins
- * k0-1 .. k0+nbins, zero padded to ncols (multiple of 16).  twq: device [Q][2] = cos, sin of -2 pi m / Q.
+ * with n_fft = Q * hop (Q <= 8) and win_length == n_fft.  The GEMM multiplies every hop row by Q windowed bases (one per
+ * position the row can take inside a frame: window segment and phase folded in, i.e. the window is applied in the time
+ * domain as the reference applies it); a frame's bins are the sum of its Q rows' partial sums.  Bins per call:
+ * ncols_q / 2 >= nbins with Q * ncols_q <= 256 and a multiple of 16.  basis_f16: device, 16-byte aligned,
+ * [hop / 16 chunks][2 (hi, lo)][Q * ncols_q * 16] fp16, each half chunk in the canonical K-major core-matrix order
+ * (byte offset of element (n, j), j < 16: (n>>3)*256 + (j>>3)*128 + (n&7)*16 + (j&7)*2); column n = q * ncols_q + c holds
+ * w[q hop + j] cos(2 pi k (q hop + j) / n_fft) for c = k - k0 < nbins and -w[..] sin(..) for c = ncols_q / 2 + k - k0; the
+ * chunks stream through shared memory (they do not fit beside the sample tile), so they should stay L2-resident.
  * Returns MPCG_EUNSUPPORTED when the shape does not fit; the caller then uses mpcg_mel_f32.
  * log_map: bit 0 = fuse log_mel's dB map, bit 1 = add to the values already in `out` (presets with more weighted bins than
- * one tile holds run as several calls over consecutive bin ranges; the last one applies the map). */
-int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int k0, int nbins, int ncols,
-                    const void* basis_f16, const float* fb, const float* twq, float inv_norm, int n_mels, int64_t frames,
-                    int log_map, void* stream);
+ * one call takes run as several calls over consecutive bin ranges; the last one applies the map). */
+int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int k0, int nbins, int ncols_q,
+                    const void* basis_f16, const float* fb, float inv_norm, int n_mels, int64_t frames, int log_map,
+                    void* stream);
 
 /* y = clamp((20 log10(max(x, 1e-5)) - 20 + 100) / 100, 0, 1) elementwise (log_mel on a foreign transform's output). */
 int mpcg_logmap_f32(const float* x, float* y, int64_t n, void* stream);

@@ -96,11 +96,15 @@ def test_config4_size_properties(pkg):
 
 
 def test_tensor_core_tier(pkg, golden):
-    """fast=True on the config-4 preset (n_fft = 4 * hop) runs on tcgen05; broadband inputs stay within 1e-5 of the
-    float64 reference, the fp64 tier and the TC tier agree, and the 16 kHz golden vectors are reproduced."""
+    """fast=True on the config-4 preset (n_fft = 4 * hop) runs on tcgen05 with the window applied in the time domain
+    (folded into the streamed bases: no frequency-domain cancellation): within 1e-5 of the float64 reference on the
+    golden vectors; on white noise all but ~1e-5 of the elements (see below).  Strongly tonal
+    frames are the documented limit of fp32 accumulation (MelConfig.build): mel values more than ~40 dB below the frame's
+    peak carry up to ~3e-4 near the dB map's floor; the default (fp64) tier is the one held to 1e-5 there."""
     kw = PRESETS["c4_16k"]
     tr_tc = pkg.MelConfig(**kw).build(fast=True)
     assert tr_tc.backend.startswith("tcgen05")
+    assert pkg.MelConfig(**kw).build().backend == "fma fp64"
     g = golden("mel_presets.npz")
     x = torch.from_numpy(g["x"]).cuda()
     lm = pkg.log_mel(x, tr_tc).cpu().numpy()
@@ -112,12 +116,17 @@ def test_tensor_core_tier(pkg, golden):
     a = pkg.log_mel(big, tr_tc)
     b = pkg.log_mel(big, pkg.MelConfig(**kw).build())
     assert a.shape == b.shape == (64, 80, 251)
-    # white noise: a bin whose Hann-windowed magnitude happens to be ~1e-3 of its neighbours carries the split-fp16
-    # floor (~4e-7 of the rectangular-window bins) as a larger RELATIVE error; the dB map turns that into <= 1e-4
+    # white noise at this preset: most mel filters sit on ONE bin, and a bin that happens to come out ~300x below the frame's
+    # typical magnitude (a Rayleigh tail: ~1e-5 of all elements) carries fp32 accumulation's floor as a larger relative
+    # error.  Round 1's frequency-domain window left 1e-3 of the elements beyond 1e-5 (max 1e-4); the time-domain bases
+    # leave ~1e-5 of them (max 4e-5)
     d = (a - b).abs()
-    assert float(d.max()) < 1e-4 and float((d > 1e-5).float().mean()) < 1e-3
+    assert float(d.max()) < 1e-4 and float((d > 1e-5).float().mean()) < 1e-4 and float((d > 3e-6).float().mean()) < 1e-3
     short = torch.randn(3, 1000, device="cuda")                      # fewer frames than one tile, odd length
     assert float((pkg.log_mel(short, tr_tc) - pkg.log_mel(short, pkg.MelConfig(**kw).build())).abs().max()) < 1e-4
+    tone = torch.sin(torch.arange(64000, device="cuda") * (2 * np.pi * 97.3 / 16000))[None] * torch.linspace(0.01, 1.0, 8, device="cuda")[:, None]
+    d = (pkg.log_mel(tone, tr_tc) - pkg.log_mel(tone, pkg.MelConfig(**kw).build())).abs()
+    assert float(d.max()) < 1e-3                                      # the documented limit near the -80 dB floor of tonal frames
     assert pkg.MelConfig(**PRESETS["wg4k"]).build(fast=True).backend == "fma fp32"      # win < n_fft: not eligible
 
 
@@ -138,6 +147,5 @@ def test_tensor_core_tier_many_bins(pkg, golden):
     a = pkg.log_mel(big, tr_tc)
     b = pkg.log_mel(big, pkg.MelConfig(**kw).build())
     assert a.shape == b.shape == (512, 80, 97)
-    d = (a - b).abs()
-    assert float(d.max()) < 1e-4 and float((d > 1e-5).float().mean()) < 1e-3
+    assert float((a - b).abs().max()) < 1e-5
     assert rel_err(tr_tc(big).cpu().numpy(), pkg.MelConfig(**kw).build()(big).cpu().numpy()) < 1e-5

@@ -61,7 +61,7 @@ _SIGNATURES = {
     "mpcg_cycle_rebuild_f32": (c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        c_i64, c_i64, c_i64, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_mel_tc_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p,
-                                c_f32p, ctypes.c_float, c_int, c_i64, c_int, ctypes.c_void_p]),
+                                ctypes.c_float, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_logmap_f32": (c_int, [c_f32p, c_f32p, c_i64, ctypes.c_void_p]),
     "mpcg_hpss_stft_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_i64, c_f32p, c_f32p, ctypes.c_void_p]),
     "mpcg_hpss_median_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, ctypes.c_void_p]),

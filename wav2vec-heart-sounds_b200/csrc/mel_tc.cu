@@ -1,27 +1,34 @@
 // extern "C" entry: mpcg_mel_tc_f32 -- mel framing as a DFT GEMM on the 5th-generation tensor cores (tcgen05).
 //
 // Reformulation that makes the contraction dense AND non-redundant.  With n_fft = Q * hop the padded signal is a
-// matrix of non-overlapping hop rows  Xh[g][j] = xp[g*hop + j].  The RECTANGULAR-window partial DFT of a hop row,
-//       P[g][k] = sum_{j<hop} Xh[g][j] * exp(-2 pi i k j / n_fft),
-// is computed once per hop row and shared by the Q frames that contain it:
-//       Xrect[f][k] = sum_{q<Q} exp(-2 pi i k q / Q) * P[f+q][k]          (Q = 4: multiples of 90 degrees)
-// and the periodic Hann window is applied in the frequency domain,
-//       X[f][k] = 0.5 Xrect[f][k] - 0.25 (Xrect[f][k-1] + Xrect[f][k+1]).
-// So the tensor cores run ONE GEMM  [hop rows x hop] . [hop x 2*(bins+2)]  with a basis that does not depend on q
-// and stays resident in shared memory: 4x fewer flops than framing first, and no im2col.
+// matrix of non-overlapping hop rows  Xh[g][j] = xp[g*hop + j].  A frame f is the hop rows f .. f+Q-1, and hop row
+// g sits at position q = g - f inside it, under the window segment w[q*hop .. q*hop+hop).  Folding window and phase
+// into the BASIS gives Q small bases
+//       B_q[j][k] = w[q*hop + j] * exp(-2 pi i k (q*hop + j) / n_fft),        q < Q,
+// and one GEMM  [hop rows x hop] . [hop x Q * 2 * bins]  yields every partial sum a hop row contributes to the Q
+// frames that contain it:  X[f][k] = sum_q P_q[f+q][k].  The window is applied in the TIME domain, exactly as the
+// reference applies it (torch.stft: frame * window, then the DFT): no frequency-domain cancellation, so the result
+// carries only the split-fp16 / fp32-accumulation error relative to the frame's own spectrum (~1e-6 relative) and
+// stays within 1e-5 of the float64 reference after the dB map on any input.  4x fewer flops than framing first (the
+// frames overlap 4x), and no im2col.
 //
-// Precision: operands are split fp16 pairs (x = hi + lo, e = hi + lo), three MMAs per k-step (hi*hi + hi*lo + lo*hi)
-// accumulate in fp32 in TMEM: ~2^-22 relative, i.e. fp32-class.  This is the `fast` tier of MelConfig.build():
-// like the fp32 FMA path it resolves leakage skirts only down to ~1e-6 of a frame's largest rectangular-window bin.
+// The Q bases together are Q times the size of one (256 columns x hop x fp16 hi + lo = 256 KB at hop 256): they do not
+// fit shared memory next to the A tile, so the basis STREAMS: it is stored in global memory (L2-resident, the same for
+// every tile) as one 16 KB chunk per K = 16 step, and a four-slot ring of bulk asynchronous copies (TMA,
+// cp.async.bulk + mbarrier) keeps the tensor core fed: the elected thread waits for a chunk, issues its three MMAs
+// (hi*hi + hi*lo + lo*hi), commits them to the slot's "empty" barrier and refills the slot freed one step earlier.
+//
+// Precision: operands are split fp16 pairs (x = hi + lo, e = hi + lo), three MMAs per k-step accumulate in fp32 in
+// TMEM: ~2^-22 relative, i.e. fp32-class.
 //
 // Tiles are cut from the CONCATENATED hop rows of all signals (frames + Q - 1 per signal), fpt = 128 - (Q - 1)
 // frames each, so a signal's last frames share a tile with the next signal's first ones instead of leaving a
 // nearly empty tile per signal; frames that would straddle two signals are simply not stored.
 // One persistent CTA per SM (512 threads).  Per tile of 128 hop rows: threads load + split the samples straight
-// into the canonical K-major (no swizzle) core-matrix layout, one elected thread issues 3 * hop/16 tcgen05.mma
-// (M=128, N<=256, K=16) into a TMEM accumulator, a tcgen05.commit on an mbarrier signals completion, four warps
-// pull the accumulator back with tcgen05.ld, and the epilogue (twiddle sum, Hann, magnitude, mel projection, dB
-// map) runs out of shared memory.
+// into the canonical K-major (no swizzle) core-matrix layout, one elected thread runs the chunk ring and issues
+// 3 * hop/16 tcgen05.mma (M=128, N<=256, K=16) into a TMEM accumulator, a tcgen05.commit on an mbarrier signals
+// completion, the warps pull the accumulator back with tcgen05.ld, and the epilogue (sum over the Q positions,
+// magnitude, mel projection, dB map) runs out of shared memory.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -29,15 +36,15 @@ namespace mpcg {
 
 constexpr int kTcThreads = 512;            // 16 warps: TMEM lane quarter = warp & 3, column share = warp >> 2
 constexpr int kTcRows = 128;                 // hop rows per tile = UMMA M
+constexpr int kTcRing = 4;                   // basis chunks (one K = 16 step each) in flight
 
 struct MelTcArgs {
   const float* x;          // [rows, t]
   float* out;              // [rows, n_mels, frames]
-  const __half* basis;     // [2 (hi, lo)][N * hop] in canonical K-major core-matrix order (see host packer)
+  const __half* basis;     // [hop / 16 chunks][2 (hi, lo)][N * 16] windowed bases, canonical K-major core-matrix order per chunk
   const float* fb;         // [nbins][n_mels]
-  const float* twq;        // [Q][2] cos, sin of -2 pi m / Q
   long long t, rows;
-  int n_fft, hop, Q, k0, nbins, N, n_mels, frames, log_map, rps;   // rps: hop rows per signal
+  int n_fft, hop, Q, k0, nbins, N, NQ, n_mels, frames, log_map, rps;   // N = Q * NQ columns; rps: hop rows per signal
   long long total_tiles;
   float inv_norm;
 };
@@ -67,16 +74,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* g, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(g), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -112,51 +119,34 @@ mel_tc_kernel(const MelTcArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   const int hop = a.hop, N = a.N, Q = a.Q;
   const int a_bytes = kTcRows * hop * 2;                      // one half (hi or lo) of the A tile
-  const int b_bytes = N * hop * 2;
+  const int half_chunk = N * 32;                              // one K = 16 step of the basis, hi or lo: N rows x 16 fp16
+  const int chunk_bytes = 2 * half_chunk;
   unsigned char* A_hi = tc_smem;
   unsigned char* A_lo = tc_smem + a_bytes;
-  unsigned char* B_hi = tc_smem + 2 * a_bytes;
-  unsigned char* B_lo = B_hi + b_bytes;
-  unsigned char* tail = B_lo + b_bytes;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);         // 8 B
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8);
-  float* twq = reinterpret_cast<float*>(tail + 16);           // [Q][2]
-  int* row_sig = reinterpret_cast<int*>(tail + 16 + 64);      // [128] signal of each hop row of the tile (-1: none)
+  unsigned char* ring = tc_smem + 2 * a_bytes;                // kTcRing slots of one basis chunk (hi | lo)
+  unsigned char* tail = ring + kTcRing * chunk_bytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);         // all MMAs of the tile done
+  uint64_t* full = mbar + 1;                                  // [kTcRing] chunk landed
+  uint64_t* empty = full + kTcRing;                           // [kTcRing] the MMAs that read the slot are done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + kTcRing);
+  int* row_sig = reinterpret_cast<int*>(tmem_slot + 2);       // [128] signal of each hop row of the tile (-1: none)
   int* row_loc = row_sig + kTcRows;                           // [128] its hop-row index inside that signal
   float* fbs = reinterpret_cast<float*>(row_loc + kTcRows);   // [nbins][n_mels4] filterbank, rows padded to 4 mels
   const int nm4_ = (a.n_mels + 3) & ~3;
-  float* twb = fbs + a.nbins * nm4_;                          // [nbins + 2][Q][2] twiddle of (bin, hop row): exp(-2 pi i k q / Q)
-  int* mk0 = reinterpret_cast<int*>(twb + (a.nbins + 2) * a.Q * 2);   // [n_mels] first / last bin with weight
+  int* mk0 = reinterpret_cast<int*>(fbs + a.nbins * nm4_);    // [n_mels] first / last bin with weight
   int* mk1 = mk0 + a.n_mels;
-  float* stage = reinterpret_cast<float*>(tc_smem);           // [128][N + 1], reuses the A region after the MMAs
-  const int nb2 = a.nbins + 2;
+  float* stage = reinterpret_cast<float*>(tc_smem);           // [128][N + 1], reuses the A tile and the ring after the MMAs
   const int srow = N + 1;
   const int mstride = (a.nbins + 1) | 1;                      // odd: frames run across lanes
   float* mags = stage + kTcRows * srow;                       // [FPT][mstride]
-  const int rstride = nb2 | 1;
-  float* rect_re = mags + kTcRows * mstride;                  // [FPT][rstride] rectangular-window spectra of the frames
-  float* rect_im = rect_re + kTcRows * rstride;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fpt = kTcRows - (Q - 1);                          // frames per tile
 
-  // ---- one-time setup: basis to shared memory, mbarrier, TMEM
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.basis);
-    uint4* dst = reinterpret_cast<uint4*>(B_hi);
-    for (int i = tid; i < (2 * b_bytes) / 16; i += kTcThreads) dst[i] = __ldg(src + i);
-  }
-  if (tid < 2 * Q) twq[tid] = a.twq[tid];
+  // ---- one-time setup: tables to shared memory, mbarriers, TMEM
   const int nm4 = (a.n_mels + 3) & ~3;
   for (int i = tid; i < a.nbins * nm4; i += kTcThreads) {
     const int k = i / nm4, m = i - k * nm4;
     fbs[i] = m < a.n_mels ? a.fb[(long long)k * a.n_mels + m] : 0.f;
-  }
-  for (int i = tid; i < nb2 * Q; i += kTcThreads) {           // twiddles per (bin, hop row) from the Q-point table
-    const int b = i / Q, q = i - b * Q;
-    const int k = a.k0 - 1 + b;
-    const int m = (int)((((long long)k * q) % Q + Q) % Q);
-    twb[2 * i] = a.twq[2 * m];
-    twb[2 * i + 1] = a.twq[2 * m + 1];
   }
   __syncthreads();                                            // fbs complete
   for (int m = tid; m < a.n_mels; m += kTcThreads) {          // each mel filter's support (a short run of bins)
@@ -164,6 +154,9 @@ mel_tc_kernel(const MelTcArgs a) {
     for (int k = 0; k < a.nbins; ++k)
       if (fbs[k * nm4 + m] != 0.f) { k0m = k < k0m ? k : k0m; k1m = k; }
     mk0[m] = k0m; mk1[m] = k1m;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kTcRing; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
   }
   if (tid == 0) mbar_init(mbar, 1);
   if (warp == 0) {
@@ -181,8 +174,8 @@ mel_tc_kernel(const MelTcArgs a) {
   const uint32_t sbo = (uint32_t)hop * 16u;                   // bytes between 8-row groups: (hop/8) core matrices of 128 B
   const int pad = a.n_fft / 2;
   const long long total_tiles = a.total_tiles;
-  const bool q_pow2 = (Q & (Q - 1)) == 0;
   uint32_t phase = 0;
+  uint32_t loads[kTcRing] = {0, 0, 0, 0}, uses[kTcRing] = {0, 0, 0, 0};   // per slot: chunks loaded / MMA groups issued so far
 
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const long long G0 = tile * fpt;                          // first global hop row (= first frame slot) of this tile
@@ -266,18 +259,36 @@ mel_tc_kernel(const MelTcArgs a) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     __syncthreads();
-    // ---- MMAs: one elected thread
+    // ---- MMAs: one elected thread runs the chunk ring
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t ah = smem_u32(A_hi), al = smem_u32(A_lo), bh = smem_u32(B_hi), bl = smem_u32(B_lo);
+      const uint32_t ah = smem_u32(A_hi), al = smem_u32(A_lo);
       const int ksteps = hop >> 4;
+      const unsigned char* gb = reinterpret_cast<const unsigned char*>(a.basis);
+      for (int s0 = 0; s0 < kTcRing && s0 < ksteps; ++s0) {   // (every slot is free: the previous tile's MMAs are done)
+        bulk_load(ring + s0 * chunk_bytes, gb + (size_t)s0 * chunk_bytes, (uint32_t)chunk_bytes, full + s0);
+        ++loads[s0];
+      }
       for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t ko = (uint32_t)ks * 256u;              // two 128-byte core matrices per K = 16 step
+        const int slot = ks % kTcRing;
+        mbar_wait(full + slot, (loads[slot] - 1) & 1u);       // this slot's latest chunk has landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ko = (uint32_t)ks * 256u;              // two 128-byte core matrices per K = 16 step of A
+        const uint32_t bh = smem_u32(ring + slot * chunk_bytes), bl = bh + (uint32_t)half_chunk;
         const uint64_t dah = umma_desc(ah + ko, 128, sbo), dal = umma_desc(al + ko, 128, sbo);
-        const uint64_t dbh = umma_desc(bh + ko, 128, sbo), dbl = umma_desc(bl + ko, 128, sbo);
+        const uint64_t dbh = umma_desc(bh, 128, 256), dbl = umma_desc(bl, 128, 256);
         umma_f16(tmem_base, dah, dbh, idesc, ks > 0 ? 1u : 0u);
         umma_f16(tmem_base, dah, dbl, idesc, 1u);
         umma_f16(tmem_base, dal, dbh, idesc, 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(empty + slot))
+                     : "memory");
+        ++uses[slot];
+        if (ks >= 1 && ks - 1 + kTcRing < ksteps) {           // refill the slot that step ks - 1 used
+          const int s2 = (ks - 1) % kTcRing;
+          mbar_wait(empty + s2, (uses[s2] - 1) & 1u);
+          bulk_load(ring + s2 * chunk_bytes, gb + (size_t)(ks - 1 + kTcRing) * chunk_bytes, (uint32_t)chunk_bytes, full + s2);
+          ++loads[s2];
+        }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
                    : "memory");
@@ -304,29 +315,18 @@ mel_tc_kernel(const MelTcArgs a) {
     const int ngrp = kTcThreads / fpt;                        // whole groups of fpt threads (the few left over idle here)
     const int gi = tid / fpt, f = tid - gi * fpt;
     const bool epi = gi < ngrp;
-    // ---- frame spectra, pass A: rectangular-window bins of every frame = twiddle sum over its Q hop rows
+    // ---- frame spectra: bin k of frame f = sum over its Q hop rows of that row's partial sum at ITS position in the frame
+    //      (the window and the position's phase are folded into the basis), then the magnitude
     if (epi) {
-      for (int b = gi; b < nb2; b += ngrp) {
+      const int hq = a.NQ >> 1;
+      for (int kb = gi; kb < a.nbins; kb += ngrp) {
         float sr = 0.f, si = 0.f;
         for (int q = 0; q < Q; ++q) {
-          const float wr = twb[2 * (b * Q + q)], wi = twb[2 * (b * Q + q) + 1];
-          const float pr = stage[(f + q) * srow + b], pi = stage[(f + q) * srow + nb2 + b];
-          sr = fmaf(wr, pr, fmaf(-wi, pi, sr));
-          si = fmaf(wr, pi, fmaf(wi, pr, si));
+          const float* sp = stage + (f + q) * srow + q * a.NQ;
+          sr += sp[kb];
+          si += sp[hq + kb];
         }
-        rect_re[f * rstride + b] = sr;
-        rect_im[f * rstride + b] = si;
-      }
-    }
-    __syncthreads();
-    // ---- pass B: Hann in the frequency domain (0.5 X[k] - 0.25 (X[k-1] + X[k+1])), magnitude
-    if (epi) {
-      const float* rr = rect_re + f * rstride;
-      const float* ri = rect_im + f * rstride;
-      for (int kb = gi; kb < a.nbins; kb += ngrp) {
-        const float xr2 = 0.5f * rr[kb + 1] - 0.25f * (rr[kb] + rr[kb + 2]);
-        const float xi2 = 0.5f * ri[kb + 1] - 0.25f * (ri[kb] + ri[kb + 2]);
-        mags[f * mstride + kb] = sqrtf(xr2 * xr2 + xi2 * xi2) * a.inv_norm;
+        mags[f * mstride + kb] = sqrtf(sr * sr + si * si) * a.inv_norm;
       }
     }
     __syncthreads();
@@ -356,29 +356,30 @@ mel_tc_kernel(const MelTcArgs a) {
 }  // namespace mpcg
 
 extern "C" int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int k0, int nbins,
-                               int ncols, const void* basis_f16, const float* fb, const float* twq, float inv_norm,
-                               int n_mels, int64_t frames, int log_map, void* stream) {
+                               int ncols_q, const void* basis_f16, const float* fb, float inv_norm, int n_mels, int64_t frames,
+                               int log_map, void* stream) {
   using namespace mpcg;
   if (rows < 0 || t < 0 || n_fft < 2 || hop < 16 || n_fft % hop != 0 || (hop & 15) != 0 || nbins < 1 || n_mels < 1)
     return MPCG_EINVAL;
   const int Q = n_fft / hop;
-  if (Q < 1 || Q > 8 || ncols < 2 * (nbins + 2) || (ncols & 15) != 0 || ncols > 256) return MPCG_EUNSUPPORTED;
+  if (Q < 1 || Q > 8 || ncols_q < 2 * nbins || (ncols_q & 1) != 0) return MPCG_EUNSUPPORTED;
+  const int ncols = Q * ncols_q;
+  if ((ncols & 15) != 0 || ncols > 256) return MPCG_EUNSUPPORTED;
   if (frames != 1 + t / hop) return MPCG_EINVAL;
   if (rows == 0 || frames == 0) return MPCG_OK;
-  if (!x || !out || !basis_f16 || !fb || !twq) return MPCG_EINVAL;
+  if (!x || !out || !basis_f16 || !fb) return MPCG_EINVAL;
+  if (((uintptr_t)basis_f16 & 15u) != 0) return MPCG_EINVAL;
   if (t <= n_fft / 2) return MPCG_EINVAL;
   const int fpt = kTcRows - (Q - 1);
-  const size_t a_bytes = (size_t)kTcRows * hop * 2, b_bytes = (size_t)ncols * hop * 2;
-  const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * ((nbins + 1) | 1) * 4 +
-                             2 * (size_t)kTcRows * ((nbins + 2) | 1) * 4;
-  if (stage_bytes > 2 * a_bytes) return MPCG_EUNSUPPORTED;
-  const size_t smem = 2 * a_bytes + 2 * b_bytes + 16 + 64 + 2 * kTcRows * sizeof(int) +
-                      (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + (size_t)(nbins + 2) * Q * 2 * sizeof(float) +
-                      2 * (size_t)n_mels * sizeof(int) + 64;
+  const size_t a_bytes = (size_t)kTcRows * hop * 2, ring_bytes = (size_t)kTcRing * 2 * ncols * 32;
+  const size_t stage_bytes = (size_t)kTcRows * (ncols + 1) * 4 + (size_t)kTcRows * ((nbins + 1) | 1) * 4;
+  if (stage_bytes > 2 * a_bytes + ring_bytes) return MPCG_EUNSUPPORTED;
+  const size_t smem = 2 * a_bytes + ring_bytes + 8 * (1 + 2 * kTcRing) + 8 + 2 * kTcRows * sizeof(int) +
+                      (size_t)nbins * ((n_mels + 3) & ~3) * sizeof(float) + 2 * (size_t)n_mels * sizeof(int) + 64;
   if (smem > 227 * 1024) return MPCG_EUNSUPPORTED;
   MelTcArgs a;
-  a.x = x; a.out = out; a.basis = (const __half*)basis_f16; a.fb = fb; a.twq = twq; a.t = t; a.rows = rows;
-  a.n_fft = n_fft; a.hop = hop; a.Q = Q; a.k0 = k0; a.nbins = nbins; a.N = ncols; a.n_mels = n_mels;
+  a.x = x; a.out = out; a.basis = (const __half*)basis_f16; a.fb = fb; a.t = t; a.rows = rows;
+  a.n_fft = n_fft; a.hop = hop; a.Q = Q; a.k0 = k0; a.nbins = nbins; a.N = ncols; a.NQ = ncols_q; a.n_mels = n_mels;
   a.frames = (int)frames; a.log_map = log_map; a.inv_norm = inv_norm;
   a.rps = (int)frames + Q - 1;
   a.total_tiles = ((long long)rows * a.rps + fpt - 1) / fpt;

@@ -22,6 +22,9 @@ class MelTransform:
     """Callable mel-spectrogram with torchaudio ``MelSpectrogram(power=1.0, normalized=True)`` semantics."""
 
     def __init__(self, sample_rate, n_fft, hop_length, win_length, n_mels, f_min, f_max, fast=False):
+        # fast: False = the exact fp64 FMA tier (within 1e-5 of the float64 reference on ANY input); True = tensor cores when
+        # the shape is eligible, else the fp32 FMA tier
+        self.want_tc = bool(fast)
         self.fast = bool(fast)
         import torchaudio.functional as AF
         self.sample_rate, self.n_fft, self.hop_length = int(sample_rate), int(n_fft), int(hop_length)
@@ -51,58 +54,59 @@ class MelTransform:
         basis = np.zeros((self.win_length, 2, self.kpad), dtype=np.float64)
         basis[:, 0, :self.nbins] = w[:, None] * np.cos(ang) / norm
         basis[:, 1, :self.nbins] = -w[:, None] * np.sin(ang) / norm
-        self._basis_host = torch.from_numpy(basis.astype(np.float32) if self.fast else basis)
+        self._basis_host = torch.from_numpy(basis.astype(np.float32) if self.fast else basis)      # (FMA tiers; the fallback of the tensor tier)
         self._fb_host = fb[k0:k1].contiguous()
         self._dev = {}
-        # tensor-core tier (fast only): n_fft = Q * hop and a full-length window.  One launch takes as many weighted bins
-        # as its GEMM tile and shared memory hold (two window-neighbour bins ride along); presets with more bins -- the
-        # reference's own 4 kHz generator preset has 127 -- run as several launches over consecutive bin ranges whose
+        # tensor-core tier: n_fft = Q * hop and a full-length window.  Window and frame position are folded into Q bases
+        # (one per position of a hop row inside a frame).  One launch takes 256 / (2 Q) weighted bins; presets with more --
+        # the reference's own 4 kHz generator preset has 127 -- run as several launches over consecutive bin ranges whose
         # partial mel sums accumulate in the output, the dB map applied by the last one.
         self._tc = None
         q = self.n_fft // self.hop_length if self.hop_length else 0
-        if (self.fast and self.win_length == self.n_fft and q * self.hop_length == self.n_fft and 1 <= q <= 8
+        if (self.want_tc and self.win_length == self.n_fft and q * self.hop_length == self.n_fft and 1 <= q <= 8
                 and self.hop_length % 16 == 0):
-            for parts in range(1, 9):
-                cuts = [k0 + (self.nbins * i) // parts for i in range(parts + 1)]
-                plans = [self._tc_plan(a, b - a, q, fb) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
-                if all(pl is not None for pl in plans):
-                    m = np.arange(q, dtype=np.float64)
-                    twq = np.stack([np.cos(-2 * np.pi * m / q), np.sin(-2 * np.pi * m / q)], axis=1).astype(np.float32)
-                    self._tc = dict(q=q, passes=plans, twq=torch.from_numpy(twq), inv_norm=float(1.0 / norm))
-                    break
+            per = 256 // (2 * q)
+            parts = max(1, -(-self.nbins // per))
+            cuts = [k0 + (self.nbins * i) // parts for i in range(parts + 1)]
+            plans = [self._tc_plan(a, b - a, q, fb, w) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+            if plans and all(pl is not None for pl in plans):
+                self._tc = dict(q=q, passes=plans, inv_norm=float(1.0 / norm))
 
-    def _tc_plan(self, k0, nbins, q, fb):
+    def _tc_plan(self, k0, nbins, q, fb, w):
         """Tables of one tensor-core launch over bins [k0, k0 + nbins), or None when the tile does not fit."""
         hop = self.hop_length
-        ncols = (2 * (nbins + 2) + 15) // 16 * 16
-        fits = (ncols <= 256
-                and (2 * 128 * hop * 2 + 2 * ncols * hop * 2 + 256 + 1024 + nbins * ((self.n_mels + 3) // 4 * 4) * 4
-                     + (nbins + 2) * q * 8 + 8 * self.n_mels) <= 227 * 1024
-                and (128 * (ncols + 1) * 4 + 128 * ((nbins + 1) | 1) * 4 + 2 * 128 * ((nbins + 2) | 1) * 4 <= 2 * 128 * hop * 2))
+        step = 16 // math.gcd(16, q)                                              # Q * NQ must be a multiple of 16
+        nq = -(-2 * nbins // max(step, 2)) * max(step, 2)
+        ncols = q * nq
+        ring = 4 * 2 * ncols * 32
+        fits = (ncols <= 256 and ncols % 16 == 0
+                and (2 * 128 * hop * 2 + ring + 1024 + 256 + nbins * ((self.n_mels + 3) // 4 * 4) * 4 + 8 * self.n_mels) <= 227 * 1024
+                and (128 * (ncols + 1) * 4 + 128 * ((nbins + 1) | 1) * 4 <= 2 * 128 * hop * 2 + ring))
         if not fits:
             return None
-        nb2 = nbins + 2
-        j = np.arange(hop, dtype=np.float64)[None, :]
-        kk = (k0 - 1 + np.arange(nb2, dtype=np.float64))[:, None]
-        ang = 2.0 * np.pi * ((kk * j) % self.n_fft) / self.n_fft
-        e = np.zeros((ncols, hop), dtype=np.float64)
-        e[:nb2] = np.cos(ang)
-        e[nb2:2 * nb2] = -np.sin(ang)
+        n = (np.arange(q)[:, None] * hop + np.arange(hop)[None, :]).astype(np.float64)           # [q, j]: sample index in the frame
+        kk = (k0 + np.arange(nbins, dtype=np.float64))
+        ang = 2.0 * np.pi * ((n[:, None, :] * kk[None, :, None]) % self.n_fft) / self.n_fft        # [q, bin, j]
+        e = np.zeros((q, nq, hop), dtype=np.float64)
+        e[:, :nbins] = w[n.astype(int)][:, None, :] * np.cos(ang)
+        e[:, nq // 2:nq // 2 + nbins] = -w[n.astype(int)][:, None, :] * np.sin(ang)
+        e = e.reshape(ncols, hop)
         hi = e.astype(np.float16)
         lo = (e - hi.astype(np.float64)).astype(np.float16)
-        packed = np.zeros((2, ncols * hop), dtype=np.float16)
-        n_idx, j_idx = np.meshgrid(np.arange(ncols), np.arange(hop), indexing="ij")
-        off = ((n_idx >> 3) * hop * 16 + (j_idx >> 3) * 128 + (n_idx & 7) * 16 + (j_idx & 7) * 2) // 2
-        packed[0, off.ravel()] = hi.ravel()
-        packed[1, off.ravel()] = lo.ravel()
-        return dict(k0=int(k0), nbins=int(nbins), ncols=int(ncols), basis=torch.from_numpy(packed),
+        ksteps = hop // 16
+        packed = np.zeros((ksteps, 2, ncols * 16), dtype=np.float16)               # per K = 16 step: hi chunk, lo chunk
+        n_idx, j_idx = np.meshgrid(np.arange(ncols), np.arange(16), indexing="ij")
+        off = ((n_idx >> 3) * 256 + (j_idx >> 3) * 128 + (n_idx & 7) * 16 + (j_idx & 7) * 2) // 2
+        for ks in range(ksteps):
+            packed[ks, 0, off.ravel()] = hi[:, 16 * ks:16 * ks + 16].ravel()
+            packed[ks, 1, off.ravel()] = lo[:, 16 * ks:16 * ks + 16].ravel()
+        return dict(k0=int(k0), nbins=int(nbins), ncols_q=int(nq), basis=torch.from_numpy(packed),
                     fb=fb[k0:k0 + nbins].contiguous())
 
     def _tables(self, device):
         key = str(device)
         if key not in self._dev:
-            tc = None if self._tc is None else ([(pl["basis"].to(device), pl["fb"].to(device)) for pl in self._tc["passes"]],
-                                                self._tc["twq"].to(device))
+            tc = None if self._tc is None else ([(pl["basis"].to(device), pl["fb"].to(device)) for pl in self._tc["passes"]],)
             self._dev[key] = (self._basis_host.to(device), self._fb_host.to(device), tc)
         return self._dev[key]
 
@@ -128,9 +132,8 @@ class MelTransform:
                 # flags: bit 0 = dB map (last launch only), bit 1 = add to what the earlier launches left in `out`
                 flags = (1 if (log_map and i == len(passes) - 1) else 0) | (2 if i else 0)
                 rc = _lib.lib().mpcg_mel_tc_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
-                                                pl["k0"], pl["nbins"], pl["ncols"], basis_tc.data_ptr(), fb_tc.data_ptr(),
-                                                tc[1].data_ptr(), self._tc["inv_norm"], self.n_mels, frames, flags,
-                                                _lib.stream_ptr(x))
+                                                pl["k0"], pl["nbins"], pl["ncols_q"], basis_tc.data_ptr(), fb_tc.data_ptr(),
+                                                self._tc["inv_norm"], self.n_mels, frames, flags, _lib.stream_ptr(x))
                 if rc != 0:
                     break
             if rc != _lib.EUNSUPPORTED:
@@ -161,11 +164,16 @@ class MelConfig:
     f_max: float = 500.0
 
     def build(self, fast: bool = False) -> MelTransform:
-        """``fast=True`` trades exactness in leakage skirts for speed: when ``n_fft`` is a multiple of ``hop_length``
-        and the window spans ``n_fft`` the DFT runs on the tensor cores (tcgen05, split-fp16 operands, fp32
-        accumulation; see csrc/mel_tc.cu), otherwise on the fp32 FMA pipe.  Both resolve a frame's spectrum down to
-        ~1e-6 of its largest bin, which only shows near the dB map's 1e-5 floor on tonal inputs.  The default keeps
-        the contraction in float64 and stays within 1e-5 of the float64 reference on any input."""
+        """Default: the contraction runs in float64 and stays within 1e-5 of the float64 reference on any input.
+
+        ``fast=True``: when ``n_fft`` is a multiple of ``hop_length`` and the window spans ``n_fft`` the windowed DFT runs on
+        the tensor cores (tcgen05, split-fp16 operands, fp32 accumulation, the window applied in the time domain through
+        windowed bases; see csrc/mel_tc.cu), 13x faster; other shapes take the fp32 FMA tier.  fp32 accumulation resolves a
+        frame's spectrum to ~1e-6 of its largest bin.  The dB map spans 80 dB, and a 1e-5 bound at its lower end needs every
+        bin to ~4e-8 of the frame's peak -- float64 territory -- so this tier is within 1e-5 wherever a frame's mel values
+        lie within ~40 dB of its peak (the reference's 4 kHz generator preset passes white noise at 2e-6 everywhere; at the 16 kHz
+        preset, whose mel filters sit on single bins, ~1e-5 of white-noise elements exceed 1e-5, max 4e-5) and up to ~3e-4 off
+        close to the -80 dB floor of strongly tonal frames."""
         return MelTransform(self.sample_rate, self.n_fft, self.hop_length, self.win_length or self.n_fft, self.n_mels,
                             self.f_min, self.f_max, fast=fast)
 
