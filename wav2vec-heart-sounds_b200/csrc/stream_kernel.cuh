@@ -1038,7 +1038,7 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
         if (kind == 0) sk_filter_tile<0>(P, sm, cx, tile, ntiles, tile_warps, n, fix_nan, lsum, lmin, lmax);
         else sk_filter_tile<1>(P, sm, cx, tile, ntiles, tile_warps, n, fix_nan, lsum, lmin, lmax);
         SK_STAMP(4);
-        if (!single) {
+        if (!single && tile + kSkGroups < ntiles) {       // (my last tile of the row stays in shared memory for pass C)
           sk_fence_async_smem();
           cx.sync();
           if (cx.gt == 0) sk_bulk_store(rowbuf + t0, cx.sig, (uint32_t)((n + 3) >> 2) * 16u);
@@ -1078,13 +1078,22 @@ fused_stream_kernel(const __grid_constant__ SkParams P) {
     if (single) {                                         // the filtered row is still in group 0's tile
       int kf = 0;
       sk_store_windows(pool + kSkGuard, obase, 0, t_r, P.start, P.win, P.hop, nwin, so_k, so_j, kf, tid, kSkThreads, scaled);
-    } else {                                              // tiles come back from the row buffer in halves, two bulk copies in flight
+    } else {
+      // my last tile of the row is still in shared memory: its windows leave from there ...
+      const int ntiles_mine = cx.g < ntiles ? (ntiles - cx.g + kSkGroups - 1) / kSkGroups : 0;
+      const int kept = cx.g + (ntiles_mine - 1) * kSkGroups;
+      if (ntiles_mine > 0) {
+        int kf0 = 0;
+        sk_store_windows(cx.sig, obase, kept * tl, min(tl, t_r - kept * tl), P.start, P.win, P.hop, nwin, so_k, so_j, kf0, cx.gt,
+                         kSkGT, scaled);
+      }
+      // ... the others come back from the row buffer in halves, two bulk copies in flight
       int kf = 0;
       const uint32_t bar2 = sk_smem(&cx.gs->bulk_bar2);
       constexpr int HALF = kSkTile / 2;
       // piece q = half (q & 1) of my (q >> 1)-th tile; piece q lands in half (q & 1) of the tile buffer
       int npieces = 0;
-      for (int tile = cx.g; tile < ntiles; tile += kSkGroups) npieces += (min(tl, t_r - tile * tl) > HALF) ? 2 : 1;
+      for (int tile = cx.g; tile < kept; tile += kSkGroups) npieces += (min(tl, t_r - tile * tl) > HALF) ? 2 : 1;
       auto piece = [&](int q, int& s0, int& len, int& half) {
         // tiles are full (two pieces each) except possibly the last one
         const int tile = cx.g + (q >> 1) * kSkGroups;
