@@ -290,13 +290,15 @@ __device__ __forceinline__ double sk_step(const SkParams& P, double (&z)[4], dou
   z[3] = fma(-P.kinds[K].c[1][4], y1, P.kinds[K].c[1][2] * y0);
   return y1;
 }
+// acc += M^(2^DD) v.  The two sections form a CASCADE: the first section's two states never see the second's, so every
+// power of the transition matrix is block lower triangular and rows 0-1 need only columns 0-1 (12 products, not 16).
 template <int K, int DD>
 __device__ __forceinline__ void sk_mv_acc(const SkParams& P, const double (&v)[4], double (&acc)[4]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     double a = acc[r];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) a = fma(P.kinds[K].mp[DD][r * 4 + c], v[c], a);
+    for (int c = 0; c < (r < 2 ? 2 : 4); ++c) a = fma(P.kinds[K].mp[DD][r * 4 + c], v[c], a);
     acc[r] = a;
   }
 }
@@ -388,7 +390,7 @@ __device__ __forceinline__ void sk_filter_tile(const SkParams& P, SkShared& sm, 
     for (int r = 0; r < 4; ++r) {
       double a = z[r];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) a = fma(sm.mtab[r * 4 + cc][lane], wc[cc], a);
+      for (int cc = 0; cc < (r < 2 ? 2 : 4); ++cc) a = fma(sm.mtab[r * 4 + cc][lane], wc[cc], a);   // (block lower triangular)
       z[r] = a;
     }
   }
