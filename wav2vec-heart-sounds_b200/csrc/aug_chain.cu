@@ -5,20 +5,24 @@
 // The stage-per-kernel path (aug.cu) reads and writes every row once per stage (ten HBM sweeps and more for the EQ);
 // here a row is read once and written once.
 //
-// A row (a 4 s window at 16 kHz is 256 KB) is spread over a thread-block CLUSTER: CTA `rank` keeps samples
-// [rank*S, rank*S + S) in shared memory, S = 256 * L, three CTAs per SM so that the clusters of different rows
-// overlap their phases.  Every N is a sweep over the resident slice plus one small exchange of (sum, min, max)
-// over distributed shared memory; the normalising map of stage k is applied on the fly by the sweep of stage k+1.
-// The EQ cascade runs in place as the chunked linear-recurrence scan of the preprocessing kernel (fp64 state, two
-// sections per 4-state group), slices chained through (A^S)^j tables; rows whose Bernoulli mask is off skip it.
-// While the cascade overwrites the slice, the stage's input is parked in the row's OUTPUT buffer (re-read from L2).
-// Transforms follow aug.cu's rounding sequence.  The normalising map runs in float32 with the mean split hi + lo
-// ((v - hi) - lo) * inv -- no cancellation error, within 1-2 ulp of aug.cu's float64 map -- and row sums are formed as
-// float32 partial sums of four samples added up in float64: the float64 <-> float32 conversion unit (16 lanes per
-// clock per SM) would otherwise bound a kernel that sweeps its row six times.
+// A row (a 4 s window at 16 kHz is 256 KB) is spread over a thread-block CLUSTER: CTA `rank` owns samples
+// [rank*S, rank*S + S), S = 512 * L, two CTAs per SM.  The slice arrives in shared memory as one bulk asynchronous copy
+// (TMA) and from there every thread takes its chunk of L CONSECUTIVE samples into REGISTERS (L is a template parameter:
+// 9, 17, 25 or 33; odd, so the lanes' strided shared-memory accesses are conflict-free).  All stages are straight-line
+// code over that register chunk -- no index arithmetic, no shared-memory traffic between stages -- and every N is the
+// thread's (sum, min, max) plus one small exchange over (distributed) shared memory; the normalising map of stage k is
+// applied on the fly by stage k + 1 as one FFMA + clamp.  Shared memory is free in between: it stages the Philox
+// normals of the noise stages (drawn in aligned groups of four, like aug.cu draws them) and holds the EQ cascade's
+// intermediate signal while the EQ input stays in registers.  The cascade runs as the chunked linear-recurrence scan
+// of the preprocessing kernel (fp64 state, two sections per 4-state group, recipe as constant-bank operands, slices
+// chained through (A^S)^j); rows whose Bernoulli mask is off skip it.  The wandering-volume sinusoids are evaluated
+// once per thread with the reference's rounding sequence and advanced sample by sample with the two-multiply
+// recurrence  c -= k s; s += k c  (k = 2 sin(theta / 2): an exact sinusoid in exact arithmetic, 33 steps at most).
+// Transforms follow aug.cu's rounding sequence; the final slice leaves as one bulk copy shared -> global.
 #include <cooperative_groups.h>
 #include <string.h>
 #include <stdlib.h>
+#include <math.h>
 #include "aug.cuh"
 #include "biquad.cuh"
 
@@ -26,19 +30,25 @@ namespace cg = cooperative_groups;
 
 namespace mpcg {
 
+#ifndef MPCG_AC_P1_WEIGHTS
+#define MPCG_AC_P1_WEIGHTS 1            // 1: pass 1 as the weighted sum (a fresh constant per DFMA); 0: as the recurrence
+#endif
+#ifndef MPCG_AC_UNROLL_SMEM
+#define MPCG_AC_UNROLL_SMEM 3          // unroll factor of the filter loops that read shared memory (0: full)
+#endif
+constexpr int kAcUnrollSmem = MPCG_AC_UNROLL_SMEM;
 constexpr int kAcThreads = 512;
 constexpr int kAcWarps = kAcThreads / 32;
-constexpr int kAcLmax = 33;                 // longest filter chunk (odd)
+constexpr int kAcLmax = 33;                 // longest chunk (odd)
 constexpr int kAcMaxCluster = 8;
 constexpr int kAcMaxGroups = 3;             // up to six sections
 
-struct AcGroup {                            // one 4-state group (two sections) of the EQ cascade
+struct AcGroupK {                           // one 4-state group (two sections) of the EQ cascade: kernel parameter
   double c[2][5];                           // b0 b1 b2 a1 a2 per section
+#if MPCG_AC_P1_WEIGHTS
   double wt[kAcLmax][4];                    // A^(L-1-j) B
-  double mp[9][16];                         // M^(2^d), M = A^L
-  double mlane[32][16];                     // M^lane
-  double mwarp[kAcWarps][16];               // M^(32 w)
-  double prop_pow[kAcMaxCluster][16];       // (A^S)^j
+#endif
+  double mp[9][16];                         // M^(2^d), M = A^L (block lower triangular: a cascade)
 };
 
 struct AcParams {
@@ -46,39 +56,44 @@ struct AcParams {
   float* y;
   int t;
   float fs;
-  int ncl, S, L;
+  int ncl, S;
+  int ahead;                                // CTAs resident at a time: the slice of block b + ahead is requested into L2 by block b
   const float *rowp1, *noise1, *mask1;      // stage 1: noise
   const float *rowp2, *mask2;               // stage 2: wandering volume
   const float* mask3;                       // stage 3: EQ
   const float *rowp4, *noise4, *mask4;      // stage 4: noise
   unsigned long long seed1, sid1, seed4, sid4;
-  int ngroups;
+  int ngroups, odd_tail;                    // odd_tail: the last group holds ONE section
   int collapse;                             // 1: a stage whose mask is off keeps the pending map (N(N(x)) == N(x) up to rounding)
-  const AcGroup* groups;                    // device
+  const double* mlane;                      // device (the caller's workspace): AcTables
+  AcGroupK k[kAcMaxGroups];
+};
+
+// The part of the recipe that is indexed by lane, warp or rank lives in the caller's workspace (a big parameter block
+// costs every block's launch: 19 KB of parameters made the plain load-normalise-store path 7 % slower than 16 KB).
+struct AcTables {
+  double mlane[kAcMaxGroups][16][32];       // M^lane, element-major
+  double mwarp[kAcMaxGroups][kAcWarps][16]; // M^(32 w)
+  double prop_pow[kAcMaxGroups][kAcMaxCluster][16];   // (A^S)^j
 };
 
 struct AcStat {
   double sum;
   float lo, hi;
 };
-struct AcTables {                           // current group's recipe in shared memory
-  double mtab[16][32];                      // M^lane, element-major
-  double wt[kAcLmax][4];
-  double mp[9][16];
-  double mwarp[kAcWarps][16];
-  double prop_pow[kAcMaxCluster][16];
-  double c[2][5];
+struct AcShared {
+  double mtab[kAcMaxGroups][16][32];            // M^lane per group, element-major
   double wagg[kAcWarps][4];
   double wcar[kAcWarps][4];
-};
-struct AcShared {
-  AcTables f;
   AcStat xstat[3][kAcMaxCluster][kAcWarps];      // [exchange parity (set 0) | 2 (set 1)][rank][warp]
   double xE[2][kAcMaxCluster][4];               // [group parity][rank]: end states exported by each rank
   unsigned long long load_bar;                  // mbarrier of the bulk load
   unsigned long long pad_;
-  float mapv[2][4];                             // (mean hi, mean lo, 1 / peak) of the exchange in flight
+  float volc[2][4];                             // wandering volume, per band: k = 2 sin(theta/2), cos(theta/2), sin(theta/2)
+  float rowc[8];                                // the row's parameters: 0-5 wandering volume (amp, freq, phase) x 2, 6 / 7 noise scales
 };
+
+static_assert(sizeof(AcShared) % 16 == 0, "the sample slice behind AcShared must stay 16-byte aligned");
 
 __device__ __forceinline__ void ac_cluster_sync(int ncl) {
   if (ncl > 1) {
@@ -89,28 +104,58 @@ __device__ __forceinline__ void ac_cluster_sync(int ncl) {
   }
 }
 
-struct AcMap {                              // the pending N of the previous stage
-  float mh, ml, inv;
-  __device__ __forceinline__ float operator()(float v) const {
-    return fminf(fmaxf(((v - mh) - ml) * inv, -1.f), 1.f);
-  }
+// The pending N of the previous stage:  clamp(v * inv + c),  c = -mean * inv split hi + lo.  The FMA cancels exactly
+// (one rounding, of the result), so (v * inv + hi) + lo is within an ulp of the float64 map whatever the row's offset;
+// once a row has been normalised its mean is ~0 and `lo` is below 1e-7 of the output range: the one-FFMA form `fast`.
+struct AcMap {
+  float inv, chi, clo;
+  __device__ __forceinline__ float fast(float v) const { return fminf(fmaxf(fmaf(v, inv, chi), -1.f), 1.f); }
+  __device__ __forceinline__ float exact(float v) const { return fminf(fmaxf(fmaf(v, inv, chi) + clo, -1.f), 1.f); }
+  __device__ __forceinline__ bool needs_exact() const { return !(fabsf(chi) <= 1.f); }
 };
-struct AcAcc {                              // (sum, min, max) of a thread's share: float32 partial sums -> float64
+struct AcAcc {                              // (sum, min, max) of a thread's chunk
   double sum;
-  float part, lo, hi;
-  __device__ __forceinline__ void init() { sum = 0.0; part = 0.f; lo = INFINITY; hi = -INFINITY; }
-  __device__ __forceinline__ void add(float v) { part += v; lo = fminf(lo, v); hi = fmaxf(hi, v); }
-  __device__ __forceinline__ void flush() { sum += (double)part; part = 0.f; }
+  float lo, hi;
+  __device__ __forceinline__ void init() { sum = 0.0; lo = INFINITY; hi = -INFINITY; }
 };
 
-// Exchange NSETS row statistics across the cluster; every thread receives the maps.
+// (sum, min, max) of the first `valid` of the L register samples: float32 partial sums of every fourth sample, added
+// up in float64 (the float64 <-> float32 conversion unit runs at a quarter of the FMA rate).
+template <int L, typename V>
+__device__ __forceinline__ void ac_acc_chunk(const V& v, int valid, AcAcc& a) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  float lo = a.lo, hi = a.hi;
+  if (valid == L) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      s[j & 3] += v[j];
+      lo = fminf(lo, v[j]);
+      hi = fmaxf(hi, v[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      if (j < valid) {
+        s[j & 3] += v[j];
+        lo = fminf(lo, v[j]);
+        hi = fmaxf(hi, v[j]);
+      }
+    }
+  }
+  a.lo = lo;
+  a.hi = hi;
+  a.sum += ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
+}
+
+// Exchange NSETS row statistics across the cluster; every thread receives the maps.  ONE barrier: each warp leaves its
+// partials in every rank's table, and after the barrier every warp folds the whole table itself (no second barrier, no
+// warp waiting for another one's divisions).
 template <int NSETS>
-__device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& cluster, int ncl, int rank, int t, int& parity,
+__device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& cluster, int ncl, int rank, double inv_t, int& parity,
                                             AcAcc (&st)[NSETS], AcMap (&out)[NSETS]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) {
-    st[s].flush();
     const double sum = warp_sum(st[s].sum);
     const float lo = warp_min(st[s].lo), hi = warp_max(st[s].hi);
     if (lane < ncl) {
@@ -120,168 +165,190 @@ __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& clu
     }
   }
   ac_cluster_sync(ncl);
-  if (warp == 0) {                                          // one warp folds the partials and forms the maps
-#pragma unroll
-    for (int s = 0; s < NSETS; ++s) {
-      const AcStat* all = &sm.xstat[s == 0 ? parity : 2][0][0];
-      double tot = 0.0;
-      float lo = INFINITY, hi = -INFINITY;
-      for (int e = lane; e < ncl * kAcWarps; e += 32) {
-        tot += all[e].sum;
-        lo = fminf(lo, all[e].lo);
-        hi = fmaxf(hi, all[e].hi);
-      }
-      tot = warp_sum(tot);
-      lo = warp_min(lo);
-      hi = warp_max(hi);
-      const double mean = tot / (double)t;
-      const double peak = fmax((double)hi - mean, mean - (double)lo);
-      if (lane == 0) {
-        const float mh = (float)mean;
-        sm.mapv[s][0] = mh;
-        sm.mapv[s][1] = (float)(mean - (double)mh);
-        sm.mapv[s][2] = (float)(1.0 / fmax(peak, 1e-12));
-      }
-    }
-  }
-  __syncthreads();
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) {
-    out[s].mh = sm.mapv[s][0];
-    out[s].ml = sm.mapv[s][1];
-    out[s].inv = sm.mapv[s][2];
+    const AcStat* all = &sm.xstat[s == 0 ? parity : 2][0][0];
+    double tot = 0.0;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int e = lane; e < ncl * kAcWarps; e += 32) {
+      tot += all[e].sum;
+      lo = fminf(lo, all[e].lo);
+      hi = fmaxf(hi, all[e].hi);
+    }
+    tot = warp_sum(tot);
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    const double mean = tot * inv_t;
+    const double peak = fmax((double)hi - mean, mean - (double)lo);
+    const float inv = __frcp_rn((float)fmax(peak, 1e-12));
+    const double c = -mean * (double)inv;                   // consistent with the ROUNDED scale: the FMA then cancels exactly
+    out[s].inv = inv;
+    out[s].chi = (float)c;
+    out[s].clo = (float)(c - (double)out[s].chi);
   }
   parity ^= 1;
 }
 
-__device__ __forceinline__ void ac_mv4_lane_acc(const double (*tab)[32], int lane, const double (&v)[4], double (&acc)[4]) {
+// x / 50 correctly rounded (the reference divides): one Newton step on the product with the rounded reciprocal.
+__device__ __forceinline__ float ac_div50(float x) {
+  const float q = x * 0.02f;
+  return fmaf(fmaf(-50.f, q, x), 0.02f, q);
+}
+
+// One group G of the cascade over the slice: NS = 2 sections (four states) or, for the odd section at the end of the
+// cascade, NS = 1 (two states: half the work; its transition matrices are the upper-left 2x2 blocks of the group's
+// tables, because the missing second section is the identity).  Input: the register chunk (G == 0) or the thread's
+// chunk of `mine` (shared memory, G > 0); output: `mine`.  Chunks beyond the row's end see their own finite leftovers,
+// whose outputs nobody reads (the filter is causal).  All recurrence state is float64: a float32 first pass was tried
+// on the host (1e-4 .. 6e-4 of the coloured signal's peak on tonal rows with narrow low bands, against 5e-8) and dropped.
+//   pass 1  the chunk's end state from a zero start, as the recurrence itself: ten constants that stay in uniform
+//           registers (the weight form  sum_j A^(L-1-j) B x_j  needs a fresh constant for every DFMA and runs at a
+//           third of the DFMA rate on the constant loads: tools/ubench_iir.cu)
+//   scan    Hillis-Steele inside the warp with M^(2^d), warp 0 chains the warp aggregates, M^lane fixes up each lane
+//   pass 2  the chunk again from its true start state, transposed direct form II.
+template <int NS>
+__device__ __forceinline__ void ac_mv(const double* __restrict__ m, const double (&v)[2 * NS], double (&acc)[2 * NS]) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < 2 * NS; ++r) {
     double a = acc[r];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) a = fma(tab[r * 4 + c][lane], v[c], a);
+    for (int c = 0; c < (r < 2 ? 2 : 4); ++c) a = fma(m[r * 4 + c], v[c], a);
     acc[r] = a;
   }
 }
-__device__ __forceinline__ void ac_mv4_set(const double* __restrict__ m, const double (&v)[4], double (&out)[4]) {
+template <int NS>
+__device__ __forceinline__ void ac_mv_lane(const double (*tab)[32], int lane, const double (&v)[2 * NS], double (&acc)[2 * NS]) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    double a = m[r * 4] * v[0];
+  for (int r = 0; r < 2 * NS; ++r) {
+    double a = acc[r];
 #pragma unroll
-    for (int c = 1; c < 4; ++c) a = fma(m[r * 4 + c], v[c], a);
-    out[r] = a;
+    for (int c = 0; c < (r < 2 ? 2 : 4); ++c) a = fma(tab[r * 4 + c][lane], v[c], a);
+    acc[r] = a;
   }
 }
+// one sample through the group's sections (transposed direct form II); returns the last section's output
+template <int NS>
+__device__ __forceinline__ double ac_step(const AcGroupK& K, double xv, double (&z)[2 * NS]) {
+  const double y0 = fma(K.c[0][0], xv, z[0]);
+  z[0] = fma(-K.c[0][3], y0, fma(K.c[0][1], xv, z[1]));
+  z[1] = fma(-K.c[0][4], y0, K.c[0][2] * xv);
+  if (NS == 1) return y0;
+  const double y1 = fma(K.c[1][0], y0, z[2 * NS - 2]);
+  z[2 * NS - 2] = fma(-K.c[1][3], y1, fma(K.c[1][1], y0, z[2 * NS - 1]));
+  z[2 * NS - 1] = fma(-K.c[1][4], y1, K.c[1][2] * y0);
+  return y1;
+}
 
-// One 4-state group of the cascade, in place over the resident slice (all S samples; beyond the row's end the slice
-// holds zeros, whose outputs nobody reads).
-__device__ __forceinline__ void ac_filter_group(AcShared& sm, cg::cluster_group& cluster, float* buf, const AcGroup* G,
-                                                int L, int ncl, int rank, int gpar) {
+template <int L, int G, int NS>
+__device__ __forceinline__ void ac_filter_group(const AcParams& P, AcShared& sm, cg::cluster_group& cluster, float* mine,
+                                                const float (&v)[L], int ncl, int rank) {
+  constexpr int NST = 2 * NS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __syncthreads();                                        // previous users of the tables / of buf are done
-  for (int i = tid; i < 512; i += kAcThreads) sm.f.mtab[i & 15][i >> 4] = (&G->mlane[0][0])[i];
-  for (int i = tid; i < L * 4; i += kAcThreads) (&sm.f.wt[0][0])[i] = (&G->wt[0][0])[i];
-  for (int i = tid; i < 144; i += kAcThreads) (&sm.f.mp[0][0])[i] = (&G->mp[0][0])[i];
-  for (int i = tid; i < kAcWarps * 16; i += kAcThreads) (&sm.f.mwarp[0][0])[i] = (&G->mwarp[0][0])[i];
-  for (int i = tid; i < kAcMaxCluster * 16; i += kAcThreads) (&sm.f.prop_pow[0][0])[i] = (&G->prop_pow[0][0])[i];
-  if (tid < 10) (&sm.f.c[0][0])[tid] = (&G->c[0][0])[tid];
-  __syncthreads();
-  float* mine = buf + tid * L;
-  double p[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
+  const AcGroupK& K = P.k[G];
+  double p[NST];
+#pragma unroll
+  for (int s = 0; s < NST; ++s) p[s] = 0.0;
+#if MPCG_AC_P1_WEIGHTS
+#pragma unroll
   for (int j = 0; j < L; ++j) {
-    const double2 w01 = *reinterpret_cast<const double2*>(&sm.f.wt[j][0]);
-    const double2 w23 = *reinterpret_cast<const double2*>(&sm.f.wt[j][2]);
-    const double xv = (double)mine[j];
-    p[0] = fma(w01.x, xv, p[0]);
-    p[1] = fma(w01.y, xv, p[1]);
-    p[2] = fma(w23.x, xv, p[2]);
-    p[3] = fma(w23.y, xv, p[3]);
+    const double xv = (double)(G == 0 ? v[j] : mine[j]);
+#pragma unroll
+    for (int s = 0; s < NST; ++s) p[s] = fma(K.wt[j][s], xv, p[s]);
   }
-  const double raw[4] = {p[0], p[1], p[2], p[3]};
+#else
+  if (G == 0 || MPCG_AC_UNROLL_SMEM == 0) {               // straight-line code
 #pragma unroll
-  for (int d = 0; d < 5; ++d) {                           // inclusive scan inside the warp
-    double u[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, p[s], 1 << d);
-    if (lane >= (1 << d)) mv4_acc(sm.f.mp[d], u, p);
+    for (int j = 0; j < L; ++j) ac_step<NS>(K, (double)(G == 0 ? v[j] : mine[j]), p);
+  } else {                                                // from shared memory: a short loop body keeps the code small
+#pragma unroll(kAcUnrollSmem > 0 ? kAcUnrollSmem : 1)
+    for (int j = 0; j < L; ++j) ac_step<NS>(K, (double)mine[j], p);
+  }
+#endif
+  {
+    double u[NST];
+#define MPCG_AC_LEVEL(DD)                                                                       \
+    _Pragma("unroll") for (int s = 0; s < NST; ++s) u[s] = __shfl_up_sync(kFull, p[s], 1 << DD); \
+    if (lane >= (1 << DD)) ac_mv<NS>(K.mp[DD], u, p);
+    MPCG_AC_LEVEL(0) MPCG_AC_LEVEL(1) MPCG_AC_LEVEL(2) MPCG_AC_LEVEL(3) MPCG_AC_LEVEL(4)
+#undef MPCG_AC_LEVEL
   }
   if (lane == 31) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) sm.f.wagg[warp][s] = p[s];
+    for (int s = 0; s < NST; ++s) sm.wagg[warp][s] = p[s];
   }
   __syncthreads();
   if (warp == 0) {                                        // scan the sixteen warp aggregates
-    double v[4];
+    double a[NST], u[NST];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) v[s] = (lane < kAcWarps) ? sm.f.wagg[lane][s] : 0.0;
+    for (int s = 0; s < NST; ++s) a[s] = (lane < kAcWarps) ? sm.wagg[lane][s] : 0.0;
+#define MPCG_AC_LEVEL(DD)                                                                       \
+    _Pragma("unroll") for (int s = 0; s < NST; ++s) u[s] = __shfl_up_sync(kFull, a[s], 1 << DD); \
+    if (lane >= (1 << DD)) ac_mv<NS>(K.mp[5 + DD], u, a);
+    MPCG_AC_LEVEL(0) MPCG_AC_LEVEL(1) MPCG_AC_LEVEL(2) MPCG_AC_LEVEL(3)
+#undef MPCG_AC_LEVEL
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      double u[4];
-#pragma unroll
-      for (int s = 0; s < 4; ++s) u[s] = __shfl_up_sync(kFull, v[s], 1 << d);
-      if (lane >= (1 << d)) mv4_acc(sm.f.mp[5 + d], u, v);
+    for (int s = 0; s < NST; ++s) {
+      const double e = __shfl_up_sync(kFull, a[s], 1);
+      if (lane < kAcWarps) sm.wcar[lane][s] = lane ? e : 0.0;
     }
+    if (ncl > 1 && lane == kAcWarps - 1) {                 // the slice's end state for a zero slice start, to every rank
+      for (int rk = 0; rk < ncl; ++rk) {
+        double* dst = cluster.map_shared_rank(&sm.xE[G & 1][rank][0], rk);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const double e = __shfl_up_sync(kFull, v[s], 1);
-      if (lane < kAcWarps) sm.f.wcar[lane][s] = lane ? e : 0.0;
+        for (int s = 0; s < NST; ++s) dst[s] = a[s];
+      }
     }
   }
   __syncthreads();
-  double z[4];
+  double z[NST];
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
+  for (int s = 0; s < NST; ++s) {
     const double e = __shfl_up_sync(kFull, p[s], 1);
     z[s] = lane ? e : 0.0;
   }
   {
-    double wc[4];
+    double wc[NST];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) wc[s] = sm.f.wcar[warp][s];
-    ac_mv4_lane_acc(sm.f.mtab, lane, wc, z);                 // chunk start state for a zero slice start
+    for (int s = 0; s < NST; ++s) wc[s] = sm.wcar[warp][s];
+    ac_mv_lane<NS>(sm.mtab[G], lane, wc, z);                // chunk start state for a zero slice start
   }
   if (ncl > 1) {
-    if (tid == kAcThreads - 1) {                            // S = threads * L: the slice ends with the last chunk
-      double e[4] = {raw[0], raw[1], raw[2], raw[3]};
-      mv4_acc(sm.f.mp[0], z, e);                            // E = M z + p
-      for (int rk = 0; rk < ncl; ++rk) {
-        double* dst = cluster.map_shared_rank(&sm.xE[gpar][rank][0], rk);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) dst[s] = e[s];
-      }
-    }
     ac_cluster_sync(ncl);
-    double c0[4] = {0.0, 0.0, 0.0, 0.0}, c1[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int r = 0; r < rank; r += 2) {
-      double e0[4], e1[4];
+    double c0[NST];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) { e0[s] = sm.xE[gpar][r][s]; e1[s] = (r + 1 < rank) ? sm.xE[gpar][r + 1][s] : 0.0; }
-      mv4_acc(sm.f.prop_pow[rank - 1 - r], e0, c0);
-      if (r + 1 < rank) mv4_acc(sm.f.prop_pow[rank - 2 - r], e1, c1);
+    for (int s = 0; s < NST; ++s) c0[s] = 0.0;
+    for (int r = 0; r < rank; ++r) {
+      double e0[NST];
+#pragma unroll
+      for (int s = 0; s < NST; ++s) e0[s] = sm.xE[G & 1][r][s];
+      double m[16];
+      const double* src = reinterpret_cast<const AcTables*>(P.mlane)->prop_pow[G][rank - 1 - r];
+#pragma unroll
+      for (int i = 0; i < 4 * NST; ++i) m[i] = __ldg(src + i);
+      ac_mv<NS>(m, e0, c0);
     }
-    double cs[4], c[4];
+    double c[NST];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) cs[s] = c0[s] + c1[s];
-    ac_mv4_set(sm.f.mwarp[warp], cs, c);
-    ac_mv4_lane_acc(sm.f.mtab, lane, c, z);
+    for (int s = 0; s < NST; ++s) c[s] = 0.0;
+    {
+      double m[16];
+      const double* src = reinterpret_cast<const AcTables*>(P.mlane)->mwarp[G][warp];
+#pragma unroll
+      for (int i = 0; i < 4 * NST; ++i) m[i] = __ldg(src + i);
+      ac_mv<NS>(m, c0, c);
+    }
+    ac_mv_lane<NS>(sm.mtab[G], lane, c, z);
   }
-  const double b00 = sm.f.c[0][0], b01 = sm.f.c[0][1], b02 = sm.f.c[0][2], a01 = sm.f.c[0][3], a02 = sm.f.c[0][4];
-  const double b10 = sm.f.c[1][0], b11 = sm.f.c[1][1], b12 = sm.f.c[1][2], a11 = sm.f.c[1][3], a12 = sm.f.c[1][4];
-#pragma unroll 4
-  for (int j = 0; j < L; ++j) {
-    const double xv = (double)mine[j];
-    const double y0 = fma(b00, xv, z[0]);
-    z[0] = fma(-a01, y0, fma(b01, xv, z[1]));
-    z[1] = fma(-a02, y0, b02 * xv);
-    const double y1 = fma(b10, y0, z[2]);
-    z[2] = fma(-a11, y1, fma(b11, y0, z[3]));
-    z[3] = fma(-a12, y1, b12 * y0);
-    mine[j] = (float)y1;
+  if (G == 0 || MPCG_AC_UNROLL_SMEM == 0) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) mine[j] = (float)ac_step<NS>(K, (double)(G == 0 ? v[j] : mine[j]), z);
+  } else {
+#pragma unroll(kAcUnrollSmem > 0 ? kAcUnrollSmem : 1)
+    for (int j = 0; j < L; ++j) mine[j] = (float)ac_step<NS>(K, (double)mine[j], z);
   }
-  __syncthreads();
 }
 
+template <int L>
 __global__ void __launch_bounds__(kAcThreads, 2)
 aug_chain_kernel(const __grid_constant__ AcParams P) {
   extern __shared__ __align__(16) unsigned char ac_raw[];
@@ -297,31 +364,63 @@ aug_chain_kernel(const __grid_constant__ AcParams P) {
   n = n < 0 ? 0 : (n > P.S ? P.S : n);
   const float* xr = P.x + (long long)row * P.t + s0;
   float* yr = P.y + (long long)row * P.t + s0;
-  const int nq = (n + 3) >> 2;                               // groups of four samples (s0 is a multiple of 4)
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(yr)) & 15u) == 0;
+  float* mine = buf + tid * L;
+  int valid = n - tid * L;
+  valid = valid < 0 ? 0 : (valid > L ? L : valid);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(yr)) & 15u) == 0 && n > 0 && (n & 3) == 0;
+  // everything the stages need from global memory is requested here, before the slice is waited for; the per-row
+  // parameters go to shared memory (sm.rowc: 0-5 wandering volume, 6 / 7 the noise scales)
+  const float mk1 = P.mask1 ? P.mask1[row] : 1.f, mk2 = P.mask2 ? P.mask2[row] : 1.f;
+  const float mk3 = P.mask3 ? P.mask3[row] : 1.f, mk4 = P.mask4 ? P.mask4[row] : 1.f;
+  if (tid < 8) sm.rowc[tid] = tid < 6 ? P.rowp2[(long long)row * 8 + tid] : (tid == 6 ? P.rowp1 : P.rowp4)[(long long)row * 8];
+  const bool vol_on = mk2 != 0.f;
+  const bool eq_on = P.ngroups > 0 && mk3 != 0.f;
+  const unsigned on_bits = (mk1 != 0.f ? 1u : 0u) | (vol_on ? 2u : 0u) | (eq_on ? 4u : 0u) | (mk4 != 0.f ? 16u : 0u);
   int parity = 0;
 
-  // ---- load + statistics of the raw row.  A 16-byte aligned slice arrives as ONE bulk asynchronous copy (TMA,
-  //      cp.async.bulk global -> shared, completion counted on an mbarrier): no load instructions in the sweep and the
-  //      whole HBM latency paid once; otherwise plain loads.
-  AcAcc st[1];
-  AcMap map[1];
-  st[0].init();
-  const bool bulk = vec_ok && n > 0 && (n & 3) == 0;
-  if (bulk) {
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.load_bar);
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const uint32_t bytes = (uint32_t)n * 4u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       (uint32_t)__cvta_generic_to_shared(buf)),
-                   "l"(xr), "r"(bytes), "r"(bar)
-                   : "memory");
-    }
-    for (int i = n + tid; i < P.S; i += kAcThreads) buf[i] = 0.f;       // the slice's tail while the copy flies
-    __syncthreads();                                                     // the barrier is initialised for everybody
+  // ---- the slice: ONE bulk asynchronous copy (TMA, cp.async.bulk global -> shared, completion counted on an mbarrier)
+  //      when it is 16-byte aligned, plain loads otherwise.  While it flies: zero the slice's tail, fetch the M^lane
+  //      tables of an EQ row, derive the per-row constants of the wandering volume.
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm.load_bar);
+  if (aligned && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)n * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(buf)),
+                 "l"(xr), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  if (tid == 32 && blockIdx.x + (unsigned)P.ahead < gridDim.x) {
+    // the slice of the block that will take this block's place: ask L2 for it now, so that its bulk copy finds it there
+    const unsigned nb = blockIdx.x + (unsigned)P.ahead;
+    const int sb = (int)(nb % (unsigned)ncl) * P.S;
+    int n2 = P.t - sb;
+    n2 = n2 > P.S ? P.S : n2;
+    const float* src = P.x + (long long)(nb / (unsigned)ncl) * P.t + sb;
+    if (n2 > 0 && (n2 & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)n2 * 4u) : "memory");
+  }
+  for (int i = n + tid; i < P.S; i += kAcThreads) buf[i] = 0.f;
+  if (!aligned)
+    for (int i = tid; i < n; i += kAcThreads) buf[i] = ld_stream(xr + i);
+  if (eq_on) {
+    const double* src = P.mlane;
+    double* dst = &sm.mtab[0][0][0];
+    for (int i = tid; i < P.ngroups * 512; i += kAcThreads) dst[i] = src[i];
+  }
+  if (vol_on && tid < 2) {
+    const float f = P.rowp2[(long long)row * 8 + 3 * tid + 1];
+    const double half = 3.141592653589793 * (double)f / (double)P.fs;      // theta / 2
+    double sh, ch;
+    sincos(half, &sh, &ch);
+    sm.volc[tid][0] = (float)(2.0 * sh);
+    sm.volc[tid][1] = (float)ch;
+    sm.volc[tid][2] = (float)sh;
+  }
+  __syncthreads();                                                       // the barrier is initialised, the tail zeroed
+  if (aligned) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -332,178 +431,162 @@ aug_chain_kernel(const __grid_constant__ AcParams P) {
         "AC_DONE:\n\t"
         "}\n" ::"r"(bar)
         : "memory");
-    const float4* buf4 = reinterpret_cast<const float4*>(buf);
-    for (int q = tid; q < nq; q += kAcThreads) {
-      const float4 w = buf4[q];
-      st[0].add(w.x); st[0].add(w.y); st[0].add(w.z); st[0].add(w.w);
-      st[0].flush();
-    }
-  } else {
-    for (int q = tid; q < (P.S >> 2); q += kAcThreads) {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const int i = 4 * q;
-      if (i + 3 < n && vec_ok) {
-        const float4 w = ld_stream4(reinterpret_cast<const float4*>(xr + i));
-        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (i + k < n) v[k] = ld_stream(xr + i + k);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        buf[i + k] = v[k];
-        if (i + k < n) st[0].add(v[k]);
-      }
-      st[0].flush();
-    }
   }
-  ac_exchange<1>(sm, cluster, ncl, rank, P.t, parity, st, map);
+  float v[L];
+#pragma unroll
+  for (int j = 0; j < L; ++j) v[j] = mine[j];
 
-  // ---- one elementwise stage: buf <- blend(transform(N_prev(buf))), statistics of the result
-  auto stage = [&](int op, const float* rowp, const float* noise, const float* mask, unsigned long long seed,
-                   unsigned long long sid) {
-    StageArgs a;
-    a.op = op; a.fs = P.fs; a.rowp = rowp; a.noise = noise; a.mask = mask; a.seed = seed; a.stream = sid;
-    const float* p = rowp ? rowp + (long long)row * 8 : nullptr;
-    const float* nz = noise ? noise + (long long)row * P.t : nullptr;
-    const bool on = op != MPCG_AUG_IDENTITY && (mask == nullptr || mask[row] != 0.f);
-    const bool philox = on && op == MPCG_AUG_NOISE && nz == nullptr;
-    // A stage that leaves the row alone would only normalise an already normalised row again: mean 0 and peak 1 up to
-    // float32 rounding, i.e. the identity to ~1e-7.  With P.collapse the pending map simply stays pending (unless the
-    // row is degenerate: a peak below 1e-6 means the previous map amplified rounding residue).
-    if (!on && P.collapse && map[0].inv < 1e6f) return;
-    st[0].init();
+  const double inv_t = 1.0 / (double)P.t;
+  AcAcc st[1];
+  AcMap map[1];
+  st[0].init();
+  ac_acc_chunk<L>(v, valid, st[0]);
+  ac_exchange<1>(sm, cluster, ncl, rank, inv_t, parity, st, map);
+  // A raw row whose offset dwarfs its swing needs the two-term map: apply it now, once.  From here on every pending
+  // map belongs to a row that was centred one stage ago (|mean| / peak <= ~4 at the very worst: the one-FFMA form is
+  // within 1.2e-7 of the output range, typically 1e-9).
+  if (map[0].needs_exact()) {
     const AcMap m = map[0];
-    float4* buf4 = reinterpret_cast<float4*>(buf);
-    if (on && op == MPCG_AUG_SINE_MUL) {
-      // wandering volume: each thread evaluates the two sinusoids exactly once (at its first sample, with the
-      // reference's rounding sequence) and then ROTATES: by one sample inside a group of four, by kAcThreads groups from
-      // one of its groups to the next.  At most ~40 rotations per thread: ~3e-6 rad of phase, < 1e-6 of the output.
+#pragma unroll
+    for (int j = 0; j < L; ++j) v[j] = m.exact(v[j]);
+    map[0].inv = 1.f; map[0].chi = 0.f; map[0].clo = 0.f;
+  }
+
+  // ---- the stages, one after the other: 0 noise, 1 wandering volume, 2 EQ, 3 the N that follows the EQ's own N, 4 noise.
+  //      Every pass ends with the statistics of the chunk, the exchange and the next pending map.
+#pragma unroll 1
+  for (int stage = 0; stage < 5; ++stage) {
+    bool on = (on_bits >> stage) & 1u;
+    if (stage == 3) {
+      if (!eq_on) continue;                                   // no EQ: nothing of it to re-normalise
+      on = false;
+    }
+    const AcMap m = map[0];
+    if (!on) {
+      // A stage that leaves the row alone would only normalise an already normalised row again: mean 0 and peak 1 up
+      // to float32 rounding, i.e. the identity to ~1e-7.  With P.collapse the pending map simply stays pending (unless
+      // the row is degenerate: a peak below 1e-6 means the previous map amplified rounding residue).
+      if (P.collapse && m.inv < 1e6f) continue;
+#pragma unroll
+      for (int j = 0; j < L; ++j) v[j] = m.fast(v[j]);
+    } else if (stage == 1) {
+      // ---- wandering volume
       const float two_pi = 6.283185307179586f;
-      float cd[2], sd[2], cj[2], sj[2], sg[2], cg[2];
-      const float tt0 = __fdiv_rn((float)(s0 + 4 * tid), P.fs);
+      const float tt0 = __fdiv_rn((float)(s0 + tid * L), P.fs);
+      const float a0 = sm.rowc[0], a1 = sm.rowc[3];
+      float sn[2], cs[2], kk[2];
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        const float dw = __fdiv_rn(__fmul_rn(two_pi, p[3 * b + 1]), P.fs);          // phase step per sample
-        sincosf(dw, &sd[b], &cd[b]);
-        sincosf(dw * (float)(4 * kAcThreads), &sj[b], &cj[b]);
-        sincosf(__fmul_rn(two_pi, __fadd_rn(__fmul_rn(p[3 * b + 1], tt0), p[3 * b + 2])), &sg[b], &cg[b]);
+        float s_, c_;
+        sincosf(__fmul_rn(two_pi, __fadd_rn(__fmul_rn(sm.rowc[3 * b + 1], tt0), sm.rowc[3 * b + 2])), &s_, &c_);
+        kk[b] = sm.volc[b][0];
+        sn[b] = s_;
+        cs[b] = fmaf(c_, sm.volc[b][1], s_ * sm.volc[b][2]);     // cos(phase - theta/2)
       }
-      for (int q = tid; q < nq; q += kAcThreads) {
-        const float4 b4 = buf4[q];
-        float w[4] = {b4.x, b4.y, b4.z, b4.w};
-        float sn[2] = {sg[0], sg[1]}, cs[2] = {cg[0], cg[1]};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float mod = __fadd_rn(__fadd_rn(0.f, __fmul_rn(p[0], sn[0])), __fmul_rn(p[3], sn[1]));
-          const float v = m(w[k]);
-          w[k] = __fmul_rn(v, __fadd_rn(1.f, mod));
-          if (4 * q + k < n) st[0].add(w[k]);
-          if (k < 3) {
+      for (int j = 0; j < L; ++j) {
+        const float mod = __fadd_rn(__fmul_rn(a0, sn[0]), __fmul_rn(a1, sn[1]));
+        v[j] = __fmul_rn(m.fast(v[j]), __fadd_rn(1.f, mod));
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const float s_n = fmaf(sn[b], cd[b], cs[b] * sd[b]), c_n = fmaf(cs[b], cd[b], -sn[b] * sd[b]);
-              sn[b] = s_n; cs[b] = c_n;
-            }
-          }
-        }
-        buf4[q] = make_float4(w[0], w[1], w[2], w[3]);
-        st[0].flush();
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {                         // on to this thread's next group
-          const float s_n = fmaf(sg[b], cj[b], cg[b] * sj[b]), c_n = fmaf(cg[b], cj[b], -sg[b] * sj[b]);
-          sg[b] = s_n; cg[b] = c_n;
+        for (int b = 0; b < 2; ++b) {
+          cs[b] = fmaf(-kk[b], sn[b], cs[b]);
+          sn[b] = fmaf(kk[b], cs[b], sn[b]);
         }
       }
+    } else if (stage == 2) {
+      // ---- EQ: v <- N(cascade(x2)) / 50 + N(x2), x2 = N(previous) kept in registers, the cascade's signal in `mine`
+      AcAcc s2[2];
+      AcMap m2[2];
+      s2[0].init(); s2[1].init();
+#pragma unroll
+      for (int j = 0; j < L; ++j) v[j] = m.fast(v[j]);
+      ac_acc_chunk<L>(v, valid, s2[1]);
+      // (the odd section at the end of the cascade is a group of its own with half the work)
+#define MPCG_AC_GROUP(GG)                                                                                 \
+      if (P.ngroups > GG) {                                                                              \
+        if (P.ngroups == GG + 1 && P.odd_tail) ac_filter_group<L, GG, 1>(P, sm, cluster, mine, v, ncl, rank); \
+        else ac_filter_group<L, GG, 2>(P, sm, cluster, mine, v, ncl, rank);                              \
+      }
+      MPCG_AC_GROUP(0) MPCG_AC_GROUP(1) MPCG_AC_GROUP(2)
+#undef MPCG_AC_GROUP
+      ac_acc_chunk<L>(mine, valid, s2[0]);                                // statistics of the coloured signal
+      ac_exchange<2>(sm, cluster, ncl, rank, inv_t, parity, s2, m2);      // N(c) and N(x2)
+#pragma unroll
+      for (int j = 0; j < L; ++j) v[j] = __fadd_rn(ac_div50(m2[0].exact(mine[j])), m2[1].exact(v[j]));
     } else {
-    for (int q = tid; q < nq; q += kAcThreads) {
-      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (philox) z4 = philox_normal4(seed, sid, row, (long long)((s0 >> 2) + q));
-      const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-      const float4 b4 = buf4[q];
-      float w[4] = {b4.x, b4.y, b4.z, b4.w};
+      // ---- noise: the normals of the slice go through shared memory, drawn (or loaded) in aligned groups of four and
+      //      read back chunk-wise (whoever read the buffer last did so before the barrier of the exchange that followed)
+      const float* noise = stage == 0 ? P.noise1 : P.noise4;
+      if (noise == nullptr) {
+        const unsigned long long seed = stage == 0 ? P.seed1 : P.seed4, sid = stage == 0 ? P.sid1 : P.sid4;
+        float4* buf4 = reinterpret_cast<float4*>(buf);
+        const int nq = (n + 3) >> 2;
+        for (int q = tid; q < nq; q += kAcThreads) buf4[q] = philox_normal4(seed, sid, row, (long long)((s0 >> 2) + q));
+      } else {
+        const float* nz = noise + (long long)row * P.t + s0;
+        for (int i = tid; i < n; i += kAcThreads) buf[i] = ld_stream(nz + i);
+      }
+      __syncthreads();
+      const float scale = sm.rowc[stage == 0 ? 6 : 7];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = 4 * q + k;
-        const float v = m(w[k]);
-        w[k] = (on && i < n) ? stage_value(a, p, nz, row, (long long)s0 + i, v, zz[k]) : v;
-        if (i < n) st[0].add(w[k]);
-      }
-      buf4[q] = make_float4(w[0], w[1], w[2], w[3]);
-      st[0].flush();
+      for (int j = 0; j < L; ++j) v[j] = __fadd_rn(m.fast(v[j]), __fmul_rn(scale, mine[j]));      // x + (scale*std) * noise
     }
-    }
-    ac_exchange<1>(sm, cluster, ncl, rank, P.t, parity, st, map);
-  };
-
-  stage(MPCG_AUG_NOISE, P.rowp1, P.noise1, P.mask1, P.seed1, P.sid1);
-  stage(MPCG_AUG_SINE_MUL, P.rowp2, nullptr, P.mask2, 0, 0);
-
-  // ---- EQ
-  const bool eq_on = P.ngroups > 0 && (P.mask3 == nullptr || P.mask3[row] != 0.f);
-  if (!eq_on) {
-    stage(MPCG_AUG_IDENTITY, nullptr, nullptr, nullptr, 0, 0);
-  } else {
-    // x2 = N(previous) replaces the slice and is parked in the output row; its statistics ride along
-    AcAcc s2[2];
-    AcMap m2[2];
-    s2[0].init(); s2[1].init();
-    {
-      const AcMap m = map[0];
-      for (int i = tid; i < P.S; i += kAcThreads) {
-        float v = 0.f;
-        if (i < n) {
-          v = m(buf[i]);
-          yr[i] = v;
-          s2[1].add(v);
-        }
-        buf[i] = v;                                          // zeros beyond the row's end feed the filter
-        if ((i / kAcThreads & 3) == 3) s2[1].flush();
-      }
-    }
-    for (int g = 0; g < P.ngroups; ++g) ac_filter_group(sm, cluster, buf, P.groups + g, P.L, ncl, rank, g & 1);
-    for (int i = tid; i < n; i += kAcThreads) {
-      s2[0].add(buf[i]);
-      if ((i / kAcThreads & 3) == 3) s2[0].flush();
-    }
-    ac_exchange<2>(sm, cluster, ncl, rank, P.t, parity, s2, m2);        // N(c) and N(x2)
     st[0].init();
-    for (int i = tid; i < n; i += kAcThreads) {
-      const float v = __fadd_rn(__fdiv_rn(m2[0](buf[i]), 50.f), m2[1](yr[i]));
-      buf[i] = v;
-      st[0].add(v);
-      if ((i / kAcThreads & 3) == 3) st[0].flush();
-    }
-    ac_exchange<1>(sm, cluster, ncl, rank, P.t, parity, st, map);       // e = N(v)
-    stage(MPCG_AUG_IDENTITY, nullptr, nullptr, nullptr, 0, 0);         // x3 = N(e)
+    ac_acc_chunk<L>(v, valid, st[0]);
+    ac_exchange<1>(sm, cluster, ncl, rank, inv_t, parity, st, map);
   }
 
-  stage(MPCG_AUG_NOISE, P.rowp4, P.noise4, P.mask4, P.seed4, P.sid4);
-
-  // ---- final map + store
+  // ---- final map + store: the slice goes back through shared memory and leaves as one bulk copy
   {
     const AcMap m = map[0];
-    for (int q = tid; q < nq; q += kAcThreads) {
-      const int i = 4 * q;
-      if (i + 3 < n && vec_ok) {
-        const float4 b4 = reinterpret_cast<const float4*>(buf)[q];
-        st_stream4(reinterpret_cast<float4*>(yr + i), make_float4(m(b4.x), m(b4.y), m(b4.z), m(b4.w)));
-      } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (i + k < n) yr[i + k] = m(buf[i + k]);
+    for (int j = 0; j < L; ++j) mine[j] = m.fast(v[j]);
+    if (aligned) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(yr),
+                     "r"((uint32_t)__cvta_generic_to_shared(buf)), "r"((uint32_t)n * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < n; i += kAcThreads) st_stream(yr + i, buf[i]);
     }
   }
 }
 
+template <int L>
+static int ac_launch(const AcParams& P, long long rows, cudaStream_t stream) {
+  const size_t smem = sizeof(AcShared) + (size_t)P.S * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(aug_chain_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(rows * P.ncl));
+  cfg.blockDim = dim3(kAcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)P.ncl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, aug_chain_kernel<L>, P);
+  if (e != cudaSuccess) return (int)e;
+  return MPCG_OK;
+}
+
 }  // namespace mpcg
 
-// EQ recipes travel through the caller's workspace (the ABI never allocates and keeps no device state between calls):
-// uploaded on the caller's stream right before the launch, so calls on different streams or from different host
-// threads cannot disturb each other as long as each brings its own workspace.
-extern "C" int64_t mpcg_aug_chain_work_bytes(void) { return (int64_t)sizeof(mpcg::AcGroup) * mpcg::kAcMaxGroups; }
+// The lane-indexed part of the EQ recipe (M^lane per group) travels through the caller's workspace (the ABI never
+// allocates and keeps no device state between calls): uploaded on the caller's stream right before the launch, so calls
+// on different streams or from different host threads cannot disturb each other as long as each brings its own
+// workspace.  Everything else of the recipe is a kernel parameter.
+extern "C" int64_t mpcg_aug_chain_work_bytes(void) { return (int64_t)sizeof(mpcg::AcTables); }
 
 extern "C" int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float fs, const float* rowp1,
                                   const float* noise1, const float* mask1, uint64_t seed1, uint64_t sid1,
@@ -516,81 +599,83 @@ extern "C" int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_
   if (eq_sections > 2 * kAcMaxGroups) return MPCG_EUNSUPPORTED;
   if (rows == 0 || t == 0) return MPCG_OK;
   if (!x || !y || !rowp1 || !rowp2 || !rowp4 || (eq_sections > 0 && !eq_sos)) return MPCG_EINVAL;
-  if (x == y) return MPCG_EINVAL;                            // the output row is scratch while the EQ runs
-  // geometry: slices of S = threads * L samples, the smallest power-of-two cluster with L <= kAcLmax (a 66 KB slice,
-  // two CTAs per SM).  MPCG_AC_CLUSTER overrides (experiments).
+  if (x == y) return MPCG_EINVAL;
+  if (t > 0x7fffffffLL) return MPCG_ERANGE;
+  // geometry: slices of S = threads * L samples; the smallest power-of-two cluster whose chunk length fits, and the
+  // smallest compiled chunk length (9 / 17 / 25 / 33) that covers it.  MPCG_AC_CLUSTER overrides (experiments).
   int ncl = 0, L = 0;
   {
     const char* env = getenv("MPCG_AC_CLUSTER");
     const int forced = env ? atoi(env) : 0;
-    for (int c = 1; c <= kAcMaxCluster; c *= 2) {
+    for (int c = 1; c <= kAcMaxCluster && ncl == 0; c *= 2) {
       if (forced > 0 && c != forced) continue;
       const long long per = (t + c - 1) / c;
-      long long l = (per + kAcThreads - 1) / kAcThreads;
-      l |= 1;
-      if (l <= kAcLmax) { ncl = c; L = (int)l; break; }
+      const long long l = (per + kAcThreads - 1) / kAcThreads;
+      for (int cand = 9; cand <= kAcLmax; cand += 8)
+        if (l <= cand) { ncl = c; L = cand; break; }
     }
   }
   if (ncl == 0) return MPCG_EUNSUPPORTED;
   const int S = kAcThreads * L;
-  if ((long long)(ncl - 1) * S >= t && ncl > 1) return MPCG_EUNSUPPORTED;   // every rank must own part of the row
   if (rows * ncl > 0x7fffffffLL) return MPCG_ERANGE;
   const int ngroups = (eq_sections + 1) / 2;
 
-  AcGroup groups[kAcMaxGroups];
-  memset(groups, 0, sizeof(groups));
+  AcParams P;
+  memset(&P, 0, sizeof(P));
+  static thread_local AcTables tab;                            // (21 KB: off the stack)
   for (int g = 0; g < ngroups; ++g) {
-    AcGroup& k = groups[g];
+    AcGroupK& k = P.k[g];
     bool ok;
     bq_group_coeffs(eq_sos, eq_sections, 2 * g, k.c, &ok);
     if (!ok) return MPCG_EINVAL;
     double A[16], B[4];
     bq_group_AB(k.c, A, B);
-    double v[4] = {B[0], B[1], B[2], B[3]};
-    for (int j = L - 1; j >= 0; --j) {
-      for (int s = 0; s < 4; ++s) k.wt[j][s] = v[s];
-      bq_group_step(k.c, v, 0.0);
+#if MPCG_AC_P1_WEIGHTS
+    {
+      double v[4] = {B[0], B[1], B[2], B[3]};
+      for (int j = L - 1; j >= 0; --j) {
+        for (int s = 0; s < 4; ++s) k.wt[j][s] = v[s];
+        bq_group_step(k.c, v, 0.0);
+      }
     }
+#endif
     bq_mat_pow(A, L, k.mp[0]);
     for (int d = 1; d < 9; ++d) bq_mat_mul(k.mp[d - 1], k.mp[d - 1], k.mp[d]);
-    for (int l = 0; l < 32; ++l) bq_mat_pow(k.mp[0], l, k.mlane[l]);
-    for (int w = 0; w < kAcWarps; ++w) bq_mat_pow(k.mp[0], 32LL * w, k.mwarp[w]);
-    for (int j = 0; j < kAcMaxCluster; ++j) bq_mat_pow(A, (long long)S * j, k.prop_pow[j]);
+    for (int l = 0; l < 32; ++l) {
+      double m[16];
+      bq_mat_pow(k.mp[0], l, m);
+      for (int i = 0; i < 16; ++i) tab.mlane[g][i][l] = m[i];
+    }
+    for (int w = 0; w < kAcWarps; ++w) bq_mat_pow(k.mp[0], 32LL * w, tab.mwarp[g][w]);
+    for (int j = 0; j < kAcMaxCluster; ++j) bq_mat_pow(A, (long long)S * j, tab.prop_pow[g][j]);
   }
-  const AcGroup* dev_groups = nullptr;
   if (ngroups > 0) {
-    if (!work || ((uintptr_t)work & 15u) || work_bytes < (int64_t)sizeof(groups)) return MPCG_EINVAL;
-    // (pageable source: the runtime stages the bytes before returning, so `groups` may leave scope)
-    cudaError_t e = cudaMemcpyAsync(work, groups, sizeof(AcGroup) * ngroups, cudaMemcpyHostToDevice, stream);
+    if (!work || ((uintptr_t)work & 15u) || work_bytes < (int64_t)sizeof(AcTables)) return MPCG_EINVAL;
+    // (pageable source: the runtime stages the bytes before returning, so the next call on this thread may refill `tab`)
+    cudaError_t e = cudaMemcpyAsync(work, &tab, sizeof(AcTables), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return (int)e;
-    dev_groups = reinterpret_cast<const AcGroup*>(work);
+    P.mlane = reinterpret_cast<const double*>(work);
   }
 
-  AcParams P;
-  memset(&P, 0, sizeof(P));
-  P.x = x; P.y = y; P.t = (int)t; P.fs = fs; P.ncl = ncl; P.S = S; P.L = L;
+  P.x = x; P.y = y; P.t = (int)t; P.fs = fs; P.ncl = ncl; P.S = S;
+  {
+    static int sms = 0;                                       // two blocks per SM are resident (launch bounds, shared memory)
+    if (sms == 0) {
+      int dev = 0, v = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 148;
+      sms = v;
+    }
+    const char* env = getenv("MPCG_AC_AHEAD");
+    P.ahead = env ? atoi(env) : 2 * sms / ncl * ncl;
+  }
   P.rowp1 = rowp1; P.noise1 = noise1; P.mask1 = mask1; P.seed1 = seed1; P.sid1 = sid1;
   P.rowp2 = rowp2; P.mask2 = mask2; P.mask3 = mask3;
   P.rowp4 = rowp4; P.noise4 = noise4; P.mask4 = mask4; P.seed4 = seed4; P.sid4 = sid4;
-  P.ngroups = ngroups; P.groups = dev_groups; P.collapse = (flags & MPCG_AUG_CHAIN_COLLAPSE) ? 1 : 0;
-  if (t > 0x7fffffffLL) return MPCG_ERANGE;
-
-  const size_t smem = sizeof(AcShared) + (size_t)S * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(aug_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(rows * ncl));
-  cfg.blockDim = dim3(kAcThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)ncl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, aug_chain_kernel, P);
-  if (e != cudaSuccess) return (int)e;
-  return MPCG_OK;
+  P.ngroups = ngroups; P.odd_tail = eq_sections & 1; P.collapse = (flags & MPCG_AUG_CHAIN_COLLAPSE) ? 1 : 0;
+  switch (L) {
+    case 9: return ac_launch<9>(P, rows, stream);
+    case 17: return ac_launch<17>(P, rows, stream);
+    case 25: return ac_launch<25>(P, rows, stream);
+    default: return ac_launch<33>(P, rows, stream);
+  }
 }
