@@ -27,6 +27,44 @@ __global__ void __launch_bounds__(512, 2) k_pass1(double* out, const __grid_cons
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = p[0] + p[1] + p[2] + p[3];
 }
+// pass 1 with the chunk split in NSUB equal parts that share ONE weight table (each constant feeds NSUB DFMAs), joined
+// with M^(L/NSUB):  p = M (M p_0 + p_1) + p_2
+template <int NSUB>
+__global__ void __launch_bounds__(512, 2) k_pass1_split(double* out, const __grid_constant__ K k) {
+  extern __shared__ float buf[];
+  constexpr int LS = L / NSUB;
+  float* mine = buf + threadIdx.x * L;
+  for (int j = 0; j < L; ++j) mine[j] = threadIdx.x * 0.01f + j;
+  double acc = 0;
+  for (int r = 0; r < REP; ++r) {
+    double p[NSUB][4];
+#pragma unroll
+    for (int u = 0; u < NSUB; ++u) { p[u][0] = p[u][1] = p[u][2] = p[u][3] = 0; }
+#pragma unroll
+    for (int j = 0; j < LS; ++j) {
+#pragma unroll
+      for (int u = 0; u < NSUB; ++u) {
+        const double xv = (double)mine[u * LS + j];
+        p[u][0] = fma(k.wt[j][0], xv, p[u][0]); p[u][1] = fma(k.wt[j][1], xv, p[u][1]);
+        p[u][2] = fma(k.wt[j][2], xv, p[u][2]); p[u][3] = fma(k.wt[j][3], xv, p[u][3]);
+      }
+    }
+    double q[4] = {p[0][0], p[0][1], p[0][2], p[0][3]};
+#pragma unroll
+    for (int u = 1; u < NSUB; ++u) {
+      double n[4] = {p[u][0], p[u][1], p[u][2], p[u][3]};
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int c = 0; c < (rr < 2 ? 2 : 4); ++c) n[rr] = fma(k.mp[0][rr * 4 + c], q[c], n[rr]);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) q[rr] = n[rr];
+    }
+    acc += q[0] + q[1] + q[2] + q[3];
+    mine[r % L] = (float)q[0];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 // pass 1 with the weights in shared memory (two broadcast 128-bit loads per sample)
 __global__ void __launch_bounds__(512, 2) k_pass1_smem(double* out, const __grid_constant__ K k) {
   extern __shared__ float buf[];
@@ -174,6 +212,10 @@ int main() {
   cudaFuncSetAttribute(k_pass1_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_pass1_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k_pass2_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_pass1_split<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_pass1_split<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  rep("pass 1 in 3 parts sharing one weight table", timeit([&] { k_pass1_split<3><<<sms * 2, 512, smem>>>(dout, k); }), 4);
+  rep("pass 1 in 11 parts sharing one weight table", timeit([&] { k_pass1_split<11><<<sms * 2, 512, smem>>>(dout, k); }), 4);
   rep("pass 1, weights from shared memory", timeit([&] { k_pass1_smem<<<sms * 2, 512, smem>>>(dout, k); }), 4);
   rep("pass 1 as the zero-state recurrence (10 DFMA)", timeit([&] { k_pass1_rec<<<sms * 2, 512, smem>>>(dout, k); }), 10);
   rep("pass 2 + next group's pass 1 (14 DFMA)", timeit([&] { k_pass2_fused<<<sms * 2, 512, smem>>>(dout, k); }), 14);

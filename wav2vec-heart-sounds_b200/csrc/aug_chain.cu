@@ -57,7 +57,7 @@ struct AcParams {
   int t;
   float fs;
   int ncl, S;
-  int ahead;                                // CTAs resident at a time: the slice of block b + ahead is requested into L2 by block b
+  int ahead;                                // the slice of block b + ahead is requested into L2 by block b
   const float *rowp1, *noise1, *mask1;      // stage 1: noise
   const float *rowp2, *mask2;               // stage 2: wandering volume
   const float* mask3;                       // stage 3: EQ
@@ -147,6 +147,21 @@ __device__ __forceinline__ void ac_acc_chunk(const V& v, int valid, AcAcc& a) {
   a.sum += ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
 }
 
+// min / max of a float over the warp as ONE integer reduction (REDUX) on the order-preserving image of the bits
+// (five shuffle + compare rounds otherwise; the statistics never hold NaNs that matter: a NaN row is NaN either way).
+__device__ __forceinline__ int ac_ord(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ac_warp_min(float v) {
+  const int o = __reduce_min_sync(kFull, ac_ord(v));
+  return __int_as_float(o ^ ((o >> 31) & 0x7fffffff));
+}
+__device__ __forceinline__ float ac_warp_max(float v) {
+  const int o = __reduce_max_sync(kFull, ac_ord(v));
+  return __int_as_float(o ^ ((o >> 31) & 0x7fffffff));
+}
+
 // Exchange NSETS row statistics across the cluster; every thread receives the maps.  ONE barrier: each warp leaves its
 // partials in every rank's table, and after the barrier every warp folds the whole table itself (no second barrier, no
 // warp waiting for another one's divisions).
@@ -157,7 +172,7 @@ __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& clu
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) {
     const double sum = warp_sum(st[s].sum);
-    const float lo = warp_min(st[s].lo), hi = warp_max(st[s].hi);
+    const float lo = ac_warp_min(st[s].lo), hi = ac_warp_max(st[s].hi);
     if (lane < ncl) {
       AcStat* slot = &sm.xstat[s == 0 ? parity : 2][rank][warp];
       AcStat* dst = ncl > 1 ? cluster.map_shared_rank(slot, lane) : slot;
@@ -176,8 +191,8 @@ __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& clu
       hi = fmaxf(hi, all[e].hi);
     }
     tot = warp_sum(tot);
-    lo = warp_min(lo);
-    hi = warp_max(hi);
+    lo = ac_warp_min(lo);
+    hi = ac_warp_max(hi);
     const double mean = tot * inv_t;
     const double peak = fmax((double)hi - mean, mean - (double)lo);
     const float inv = __frcp_rn((float)fmax(peak, 1e-12));
@@ -392,7 +407,7 @@ aug_chain_kernel(const __grid_constant__ AcParams P) {
                  "l"(xr), "r"(bytes), "r"(bar)
                  : "memory");
   }
-  if (tid == 32 && blockIdx.x + (unsigned)P.ahead < gridDim.x) {
+  if (tid == 32 && P.ahead > 0 && blockIdx.x + (unsigned)P.ahead < gridDim.x) {
     // the slice of the block that will take this block's place: ask L2 for it now, so that its bulk copy finds it there
     const unsigned nb = blockIdx.x + (unsigned)P.ahead;
     const int sb = (int)(nb % (unsigned)ncl) * P.S;
@@ -659,14 +674,15 @@ extern "C" int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_
 
   P.x = x; P.y = y; P.t = (int)t; P.fs = fs; P.ncl = ncl; P.S = S;
   {
-    static int sms = 0;                                       // two blocks per SM are resident (launch bounds, shared memory)
+    static int sms = 0;                                       // two blocks per SM are resident; half a wave ahead measured best
+                                                              // (0 / 148 / 296 / 592 blocks: 1.257 / 1.235 / 1.239 / 1.269 ms at configs[2])
     if (sms == 0) {
       int dev = 0, v = 0;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 148;
       sms = v;
     }
     const char* env = getenv("MPCG_AC_AHEAD");
-    P.ahead = env ? atoi(env) : 2 * sms / ncl * ncl;
+    P.ahead = env ? atoi(env) : sms / ncl * ncl;
   }
   P.rowp1 = rowp1; P.noise1 = noise1; P.mask1 = mask1; P.seed1 = seed1; P.sid1 = sid1;
   P.rowp2 = rowp2; P.mask2 = mask2; P.mask3 = mask3;
