@@ -530,6 +530,13 @@ def other_paths(dev, peak):
                       "ms": ms, "windows_per_s": 8192 / (ms * 1e-3), "algorithmic_bytes": nbytes,
                       "GB/s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
                       "tensor_TFLOP/s": flops / ms / 1e9}
+    # the default tier of MelConfig.build(): float64 on the fp64 tensor path (DMMA), within 1e-5 on any input
+    tr64 = MelConfig(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build()
+    ms64 = best_ms(lambda: log_mel(xm, tr64), reps=3)
+    fma64 = 8192.0 * 256 * 1024 * 2 * tr64.kpad                  # frames padded to whole 32-frame tiles x samples x (cos, sin) x bins
+    res["log_mel_default"] = {"workload": "same input, MelConfig.build() default: " + tr64.backend,
+                              "ms": ms64, "windows_per_s": 8192 / (ms64 * 1e-3), "fp64_TFLOP/s": 2 * fma64 / ms64 / 1e9,
+                              "GB/s": nbytes / ms64 / 1e6, "frac_of_hbm_peak": nbytes / ms64 / 1e6 / peak}
     return res
 
 

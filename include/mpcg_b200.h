@@ -287,6 +287,17 @@ int mpcg_mel_tc_f32(const float* x, float* out, int64_t rows, int64_t t, int n_f
                     const void* basis_f16, const float* fb, float inv_norm, int n_mels, int64_t frames, int log_map,
                     void* stream);
 
+/* mpcg_mel_f32's float64 tier on the fp64 tensor path (mma.sync.m8n8k4.f64; csrc/mel_dm.cu): same arguments and the same
+ * 1e-5 bound against the float64 reference on any input (signalproc/spectrogram.py:13-45), 2-3x faster.  basis_dm: the
+ * windowed, normalised basis in fragment order, float64 [kpad / 32][ceil((n_hi - n_lo) / 16)][64][20]: block b, slice s,
+ * column c = 2 (bin - 32 b) + part (0: cos, 1: -sin), entry j < 16 = sample n_lo + 16 s + j (zero beyond the window / the
+ * weighted bins; entries 16..19 are padding).  mel_range: device int32 [n_mels][2], the run of bins [lo, hi) (relative to the
+ * first weighted bin) on which filter m is non-zero (HTK triangles; lo = hi for an empty filter): the projection skips the
+ * zeros.  MPCG_EUNSUPPORTED (hop < 4, shared memory) -> use mpcg_mel_f32. */
+int mpcg_mel_dm_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int n_lo, int n_hi, int nbins,
+                    int kpad, const double* basis_dm, const float* fb, const int* mel_range, int n_mels, int64_t frames,
+                    int log_map, void* stream);
+
 /* y = clamp((20 log10(max(x, 1e-5)) - 20 + 100) / 100, 0, 1) elementwise (log_mel on a foreign transform's output). */
 int mpcg_logmap_f32(const float* x, float* y, int64_t n, void* stream);
 

@@ -53,10 +53,11 @@ def test_split_vs_oracle(hp, n_fft, hop, margin, kernel):
         wh, wp, wr = oh.hpss_split(x[row], n_fft, hop, margin, kernel)
         scale = max(np.abs(wh).max(), np.abs(wp).max())
         assert h.shape[1] == len(wh)
-        # a selection that flips between two near-equal magnitudes moves a mask by O(1e-6); allow 5e-5 of scale
-        assert np.abs(h[row].cpu().numpy() - wh).max() < 5e-5 * scale
-        assert np.abs(p[row].cpu().numpy() - wp).max() < 5e-5 * scale
-        assert np.abs(r[row].cpu().numpy() - wr).max() < 5e-5 * scale
+        # 1e-5 of the scale (measured: 1e-7 .. 5e-7, tools/hpss_err.py; a selection that flips between two near-equal
+        # magnitudes moves a mask by O(1e-6))
+        assert np.abs(h[row].cpu().numpy() - wh).max() < 1e-5 * scale
+        assert np.abs(p[row].cpu().numpy() - wp).max() < 1e-5 * scale
+        assert np.abs(r[row].cpu().numpy() - wr).max() < 1e-5 * scale
     tot = (h + p + r).cpu().numpy()
     assert rel_err(tot, x[:, :tot.shape[1]]) < 1e-5                               # the three parts add up to the input
 
@@ -72,7 +73,7 @@ def test_recombine_vs_oracle(hp, residual):
     for row in range(2):
         want, mw = oh.hpss_recombine(x[row], p, residual)
         assert m == mw
-        assert np.abs(got[row].cpu().numpy() - want).max() < 1e-4
+        assert np.abs(got[row].cpu().numpy() - want).max() < 1e-5          # outputs are normalised to [-1, 1]; measured 2e-7 .. 4e-7
     assert float(got.abs().max()) <= 1.0
     out, m2 = hp.hpss_recombine(torch.from_numpy(x).cuda(), residual)            # random draws: shape and bounds only
     assert out.shape == (2, m2) and torch.isfinite(out).all() and float(out.abs().max()) <= 1.0

@@ -104,7 +104,7 @@ def test_tensor_core_tier(pkg, golden):
     kw = PRESETS["c4_16k"]
     tr_tc = pkg.MelConfig(**kw).build(fast=True)
     assert tr_tc.backend.startswith("tcgen05")
-    assert pkg.MelConfig(**kw).build().backend == "fma fp64"
+    assert pkg.MelConfig(**kw).build().backend == "dmma fp64"
     g = golden("mel_presets.npz")
     x = torch.from_numpy(g["x"]).cuda()
     lm = pkg.log_mel(x, tr_tc).cpu().numpy()
@@ -149,3 +149,29 @@ def test_tensor_core_tier_many_bins(pkg, golden):
     assert a.shape == b.shape == (512, 80, 97)
     assert float((a - b).abs().max()) < 1e-5
     assert rel_err(tr_tc(big).cpu().numpy(), pkg.MelConfig(**kw).build()(big).cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("kw,t", [(dict(sample_rate=4000, n_fft=512, hop_length=16, n_mels=40, f_max=500.0), 3000),
+                                  (dict(sample_rate=4000, n_fft=1024, win_length=700, hop_length=101, n_mels=64, f_max=900.0), 5003),
+                                  (dict(sample_rate=2000, n_fft=256, hop_length=5, n_mels=32, f_max=400.0), 1111),
+                                  (dict(sample_rate=2000, n_fft=256, hop_length=3, n_mels=32, f_max=400.0), 700)])
+def test_float64_tier_on_odd_shapes(pkg, kw, t):
+    """The default tier runs on the fp64 tensor path (DMMA) for any hop >= 4 -- odd hops, windows shorter than n_fft, row
+    lengths that leave ragged last frames, more than 32 weighted bins -- and on the scalar-DFMA kernel below that; both
+    within 1e-5 of the float64 oracle, reflect padding included."""
+    rng = np.random.default_rng(11)
+    tt = np.arange(t) / kw["sample_rate"]
+    x = np.stack([rng.standard_normal(t), np.sin(2 * np.pi * 61.0 * tt) + 0.5, 1e-3 * rng.standard_normal(t)]).astype(np.float32)
+    tr = pkg.MelConfig(**kw).build()
+    assert tr.backend == "dmma fp64"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = otp.mel_transform(**kw).double()
+    xd = torch.from_numpy(x)
+    want_mel = ref(xd.double()).numpy()
+    got_mel = tr(xd.cuda()).cpu().numpy()
+    assert got_mel.shape == want_mel.shape
+    assert rel_err(got_mel, want_mel) < 1e-5
+    want = otp.log_mel(xd.double(), ref).numpy()
+    got = pkg.log_mel(xd.cuda(), tr).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-5

@@ -60,6 +60,8 @@ _SIGNATURES = {
                                             ctypes.c_double, c_int, ctypes.c_void_p]),
     "mpcg_cycle_rebuild_f32": (c_int, [c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        c_i64, c_i64, c_i64, c_int, c_i64, c_int, ctypes.c_void_p]),
+    "mpcg_mel_dm_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p,
+                                c_f32p, ctypes.c_void_p, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_mel_tc_f32": (c_int, [c_f32p, c_f32p, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p,
                                 ctypes.c_float, c_int, c_i64, c_int, ctypes.c_void_p]),
     "mpcg_logmap_f32": (c_int, [c_f32p, c_f32p, c_i64, ctypes.c_void_p]),

@@ -57,6 +57,23 @@ class MelTransform:
         self._basis_host = torch.from_numpy(basis.astype(np.float32) if self.fast else basis)      # (FMA tiers; the fallback of the tensor tier)
         self._fb_host = fb[k0:k1].contiguous()
         self._dev = {}
+        # float64 tier on the fp64 tensor path (csrc/mel_dm.cu): the same basis in the kernel's fragment order,
+        # [bin block of 32][slice of 16 samples][64 columns = (cos, -sin) per bin][16 + 4 pad]
+        self._dm_host = None
+        if not self.fast:
+            nn16 = -(-self.win_length // 16) * 16
+            full = np.zeros((nn16, 2, self.kpad), dtype=np.float64)
+            full[:self.win_length] = basis
+            dm = np.zeros((self.kpad // 32, nn16 // 16, 64, 20), dtype=np.float64)
+            blk = full.reshape(nn16 // 16, 16, 2, self.kpad // 32, 32)                 # [slice, kk, part, block, bin]
+            dm[..., :16] = blk.transpose(3, 0, 4, 2, 1).reshape(self.kpad // 32, nn16 // 16, 64, 16)   # col = 2 * bin + part
+            nz = (self._fb_host != 0).numpy()                                            # [nbins, n_mels]
+            rng = np.zeros((self.n_mels, 2), dtype=np.int32)
+            for m in range(self.n_mels):
+                ks = np.nonzero(nz[:, m])[0]
+                if ks.size:
+                    rng[m] = (ks[0], ks[-1] + 1)
+            self._dm_host = (torch.from_numpy(dm), torch.from_numpy(rng))
         # tensor-core tier: n_fft = Q * hop and a full-length window.  Window and frame position are folded into Q bases
         # (one per position of a hop row inside a frame).  One launch takes 256 / (2 Q) weighted bins; presets with more --
         # the reference's own 4 kHz generator preset has 127 -- run as several launches over consecutive bin ranges whose
@@ -107,12 +124,13 @@ class MelTransform:
         key = str(device)
         if key not in self._dev:
             tc = None if self._tc is None else ([(pl["basis"].to(device), pl["fb"].to(device)) for pl in self._tc["passes"]],)
-            self._dev[key] = (self._basis_host.to(device), self._fb_host.to(device), tc)
+            dm = None if self._dm_host is None else tuple(v.to(device) for v in self._dm_host)
+            self._dev[key] = (self._basis_host.to(device), self._fb_host.to(device), tc, dm)
         return self._dev[key]
 
     @property
     def backend(self) -> str:
-        return "tcgen05 split-fp16" if self._tc is not None else ("fma fp32" if self.fast else "fma fp64")
+        return "tcgen05 split-fp16" if self._tc is not None else ("fma fp32" if self.fast else "dmma fp64")
 
     def num_frames(self, t: int) -> int:
         return 1 + t // self.hop_length
@@ -124,7 +142,7 @@ class MelTransform:
         if t <= self.n_fft // 2:
             raise ValueError(f"signal of {t} samples is too short for reflect padding of {self.n_fft // 2}")
         frames = self.num_frames(t)
-        basis, fb, tc = self._tables(x.device)
+        basis, fb, tc, dm = self._tables(x.device)
         out = torch.empty((rows.shape[0], self.n_mels, frames), device=x.device, dtype=torch.float32)
         if tc is not None:
             passes, rc = self._tc["passes"], 0
@@ -138,6 +156,13 @@ class MelTransform:
                     break
             if rc != _lib.EUNSUPPORTED:
                 _lib.check(rc, "mel (tensor cores)")
+                return out.reshape(*lead, self.n_mels, frames)
+        if dm is not None:
+            rc = _lib.lib().mpcg_mel_dm_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
+                                            self.n_lo, self.n_hi, self.nbins, self.kpad, dm[0].data_ptr(), fb.data_ptr(),
+                                            dm[1].data_ptr(), self.n_mels, frames, 1 if log_map else 0, _lib.stream_ptr(x))
+            if rc != _lib.EUNSUPPORTED:
+                _lib.check(rc, "mel (fp64 tensor path)")
                 return out.reshape(*lead, self.n_mels, frames)
         _lib.check(_lib.lib().mpcg_mel_f32(rows.data_ptr(), out.data_ptr(), rows.shape[0], t, self.n_fft, self.hop_length,
                                            self.n_lo, self.n_hi, self.nbins, self.kpad, basis.data_ptr(),
