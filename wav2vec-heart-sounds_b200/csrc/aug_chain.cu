@@ -215,10 +215,13 @@ __device__ __forceinline__ float ac_div50(float x) {
 // tables, because the missing second section is the identity).  Input: the register chunk (G == 0) or the thread's
 // chunk of `mine` (shared memory, G > 0); output: `mine`.  Chunks beyond the row's end see their own finite leftovers,
 // whose outputs nobody reads (the filter is causal).  All recurrence state is float64: a float32 first pass was tried
-// on the host (1e-4 .. 6e-4 of the coloured signal's peak on tonal rows with narrow low bands, against 5e-8) and dropped.
-//   pass 1  the chunk's end state from a zero start, as the recurrence itself: ten constants that stay in uniform
-//           registers (the weight form  sum_j A^(L-1-j) B x_j  needs a fresh constant for every DFMA and runs at a
-//           third of the DFMA rate on the constant loads: tools/ubench_iir.cu)
+// on the host (tools/eq_precision_study.py: 1e-4 .. 6e-4 of the coloured signal's peak on tonal rows with narrow low
+// bands, against 5e-8) and dropped.
+//   pass 1  the chunk's end state from a zero start, p = sum_j A^(L-1-j) B x_j, the weights as constant-bank operands.
+//           (In isolation this form is bound by the constant loads, a third of the DFMA rate, and the recurrence
+//           itself -- 10 DFMA per sample, ten resident constants -- is faster: tools/ubench_iir.cu.  Inside the kernel
+//           the weighted sum wins, 1.26 against 1.34 ms at configs[2]: what it leaves of the fp64 pipe serves the
+//           co-resident CTA.  -DMPCG_AC_P1_WEIGHTS=0 builds the other form.)
 //   scan    Hillis-Steele inside the warp with M^(2^d), warp 0 chains the warp aggregates, M^lane fixes up each lane
 //   pass 2  the chunk again from its true start state, transposed direct form II.
 template <int NS>
