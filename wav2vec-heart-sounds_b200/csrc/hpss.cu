@@ -341,18 +341,16 @@ __device__ __forceinline__ float softmask2(float x, float ref, bool split_zeros)
 // A CTA transforms kIstftGroup consecutive frames of one row and overlap-adds them in shared memory first: with n_fft / hop
 // = 16 or 32 overlapping frames per sample, one global atomic per sample and FRAME was the bound of this kernel; now it is
 // one per sample and GROUP ((group - 1) hop + n_fft atomics instead of group * n_fft).
+constexpr int kIstftSlots = 3;                      // bins per thread fetched one frame ahead (n_fft <= 1024)
 constexpr int kIstftGroup = 16;                     // at most; fewer when (group - 1) hop + n_fft would not fit
-__global__ void __launch_bounds__(kFftThreads)
+__global__ void __launch_bounds__(kFftThreads, 4)
 hpss_istft_kernel(const float2* __restrict__ spec, const float* __restrict__ harm, const float* __restrict__ perc,
                   float* __restrict__ acc, int n_fft, int log2n, int hop, int frames, long long acc_len,
                   float margin_h, float margin_p, const float* __restrict__ window, const float2* __restrict__ tw, int group) {
-  extern __shared__ float2 fft_buf[];            // [n_fft] work + [bins] frame spectrum + 2*[bins] masks + 2*[span] overlap-add
+  extern __shared__ float2 fft_buf[];            // [n_fft] work + 2*[span] overlap-add
   const int bins = n_fft / 2 + 1;
-  float2* sp = fft_buf + fpad(n_fft);
-  float* mh = reinterpret_cast<float*>(sp + bins);
-  float* mp = mh + bins;
   const int span = (group - 1) * hop + n_fft;
-  float* oh = mp + bins;
+  float* oh = reinterpret_cast<float*>(fft_buf + fpad(n_fft));
   float* op = oh + span;
   const int frame0 = blockIdx.x * group;
   const int nfr = min(group, frames - frame0);
@@ -360,27 +358,45 @@ hpss_istft_kernel(const float2* __restrict__ spec, const float* __restrict__ har
   const bool split = (margin_h == 1.f && margin_p == 1.f);
   const float scale = 1.f / (float)n_fft;
   for (int i = threadIdx.x; i < 2 * span; i += kFftThreads) oh[i] = 0.f;
-  for (int f = 0; f < nfr; ++f) {
+  // A frame's spectrum and medians are fetched into REGISTERS one frame ahead (kIstftSlots bins per thread), so their
+  // DRAM latency hides behind the previous frame's transform; frames with more bins per thread take the direct path.
+  const bool pre = bins <= kIstftSlots * kFftThreads;
+  float2 nsv[kIstftSlots];
+  float nh[kIstftSlots], np_[kIstftSlots];
+  auto fetch = [&](int f) {
     const long long off = ((long long)row * frames + frame0 + f) * bins;
-    for (int k = threadIdx.x; k < bins; k += kFftThreads) {
-      sp[k] = spec[off + k];
-      const float h = harm[off + k], p = perc[off + k];
-      mh[k] = softmask2(h, p * margin_h, split);
-      mp[k] = softmask2(p, h * margin_p, split);
+#pragma unroll
+    for (int u = 0; u < kIstftSlots; ++u) {
+      const int k = threadIdx.x + u * kFftThreads;
+      if (k < bins) { nsv[u] = spec[off + k]; nh[u] = harm[off + k]; np_[u] = perc[off + k]; }
     }
-    __syncthreads();
+  };
+  auto scatter = [&](int k, float2 sv, float h, float p) {
+    const float wh = softmask2(h, p * margin_h, split), wp = softmask2(p, h * margin_p, split);
     // ONE inverse FFT per frame: H and P are spectra of real signals, so ifft(H + i P) = h + i p (h, p real).  The
     // residual needs no transform at all: istft is linear and istft(stft(x)) = x, hence r = x - h - p (finish kernel).
-    for (int k = threadIdx.x; k < bins; k += kFftThreads) {
-      const float2 sv = sp[k];
-      float2 hv = make_float2(sv.x * mh[k], sv.y * mh[k]), pv = make_float2(sv.x * mp[k], sv.y * mp[k]);
-      if (k == 0 || k == n_fft / 2) { hv.y = 0.f; pv.y = 0.f; }       // irfft ignores the imaginary part of DC / Nyquist
-      fft_buf[fpad(bitrev((unsigned)k, log2n))] = make_float2(hv.x - pv.y, hv.y + pv.x);
-      if (k > 0 && k < n_fft / 2) fft_buf[fpad(bitrev((unsigned)(n_fft - k), log2n))] = make_float2(hv.x + pv.y, pv.x - hv.y);
+    float2 hv = make_float2(sv.x * wh, sv.y * wh), pv = make_float2(sv.x * wp, sv.y * wp);
+    if (k == 0 || k == n_fft / 2) { hv.y = 0.f; pv.y = 0.f; }         // irfft ignores the imaginary part of DC / Nyquist
+    fft_buf[fpad(bitrev((unsigned)k, log2n))] = make_float2(hv.x - pv.y, hv.y + pv.x);
+    if (k > 0 && k < n_fft / 2) fft_buf[fpad(bitrev((unsigned)(n_fft - k), log2n))] = make_float2(hv.x + pv.y, pv.x - hv.y);
+  };
+  if (pre && nfr > 0) fetch(0);
+  for (int f = 0; f < nfr; ++f) {
+    __syncthreads();                             // the previous frame's overlap-add has read the work buffer
+    if (pre) {
+#pragma unroll
+      for (int u = 0; u < kIstftSlots; ++u) {
+        const int k = threadIdx.x + u * kFftThreads;
+        if (k < bins) scatter(k, nsv[u], nh[u], np_[u]);
+      }
+      if (f + 1 < nfr) fetch(f + 1);
+    } else {
+      const long long off = ((long long)row * frames + frame0 + f) * bins;
+      for (int k = threadIdx.x; k < bins; k += kFftThreads) scatter(k, spec[off + k], harm[off + k], perc[off + k]);
     }
     __syncthreads();
     fft_shared(fft_buf, n_fft, log2n, true, tw);
-    // frames are added one after the other (barriers above separate them), each thread on its own samples of the frame
+    // frames are added one after the other (the barrier above separates them), each thread on its own samples of the frame
     for (int i = threadIdx.x; i < n_fft; i += kFftThreads) {
       const float w = scale * __ldg(window + i);
       const float2 v = fft_buf[fpad(i)];
@@ -579,8 +595,7 @@ extern "C" int mpcg_hpss_istft_f32(const float* spec, const float* harm, const f
   if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
   const int bins = n_fft / 2 + 1;
   const long long acc_len = (long long)n_fft + (long long)hop * (frames - 1);
-  const size_t fixed = (size_t)fpad(n_fft) * sizeof(float2) + (size_t)bins * (sizeof(float2) + 2 * sizeof(float)) +
-                       2 * (size_t)n_fft * sizeof(float);
+  const size_t fixed = (size_t)fpad(n_fft) * sizeof(float2) + 2 * (size_t)n_fft * sizeof(float);
   int group = kIstftGroup;
   while (group > 1 && fixed + 2 * (size_t)(group - 1) * hop * sizeof(float) > 160 * 1024) --group;
   const size_t smem = fixed + 2 * (size_t)(group - 1) * hop * sizeof(float);
