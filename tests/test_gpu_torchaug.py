@@ -177,13 +177,15 @@ def test_mix_noise_arithmetic(ta):
             ta.mix_noise(torch.from_numpy(x).cuda(), torch.from_numpy(bank).cuda(), scale=scale, **bad)
 
 
-@pytest.mark.parametrize("t,rows", [(64000, 24), (8250, 40), (12347, 16), (133000, 5), (600, 9)])
+@pytest.mark.parametrize("t,rows", [(64000, 24), (8250, 40), (12347, 16), (133000, 5), (600, 9), (38000, 6)])
 @pytest.mark.parametrize("noise", [None, "philox"])
 def test_fused_chain_equals_stage_kernels(ta, t, rows, noise):
     """The one-kernel chain (rows resident in cluster shared memory) against the kernel-per-stage path on the same
     random draws: the per-element arithmetic is the same, only the summation order of the row means differs, so the
-    two agree to float32 rounding (1e-6 of the [-1, 1] range).  Covers 1-, 2-, 4- and 8-CTA clusters, ragged tails,
-    rows with every mask on and with every mask off."""
+    two agree to float32 rounding (1e-6 of the [-1, 1] range).  Covers 1-, 2-, 4- and 8-CTA clusters, all four compiled
+    chunk lengths (600 -> 9, 8250 -> 17, 12347 -> 25, the others 33), rows that do not start on 16-byte boundaries
+    (12347), a cluster whose last CTA owns nothing (38000: four slices of 12800), ragged tails, rows with every mask
+    on and with every mask off."""
     from wav2vec_heart_sounds_b200 import AugmentConfig
     g = torch.Generator(device="cuda").manual_seed(t)
     x = torch.randn(rows, t, device="cuda", generator=g) * 0.3 + torch.sin(torch.arange(t, device="cuda") / 37.0)[None]
@@ -197,6 +199,28 @@ def test_fused_chain_equals_stage_kernels(ta, t, rows, noise):
         assert torch.isfinite(outs[0]).all()
         assert float((outs[1] - outs[2]).abs().max()) < 2e-6       # every stage re-normalised: float32 rounding apart
         assert float((outs[0] - outs[2]).abs().max()) < 4e-6       # idempotent re-normalisations collapsed
+
+
+def test_fused_chain_on_rows_with_a_large_offset(ta):
+    """A raw row whose offset dwarfs its swing (mean / peak up to 1e4) takes the two-term form of the first map; later
+    maps are the one-FFMA form.  Same result as the stage kernels (float64 maps) to float32 rounding, and as the
+    chain on the centred rows (N removes the offset)."""
+    from wav2vec_heart_sounds_b200 import AugmentConfig
+    g = torch.Generator(device="cuda").manual_seed(9)
+    base = torch.randn(12, 16500, device="cuda", generator=g) * 0.01
+    off = torch.tensor([0.0, 1.0, -3.0, 50.0, -100.0, 0.5, 7.0, -0.2, 20.0, 100.0, -60.0, 2.0], device="cuda")[:, None]
+    x = base + off
+    cfg = AugmentConfig(prob_noise=4.0, prob_wandering_volume=1.0, prob_banding=1.0)
+    outs = []
+    for fused in (True, False):
+        torch.manual_seed(3); np.random.seed(3)
+        outs.append(ta.augment_pcg_batch(x, 4125, cfg, noise="philox", fused=fused, collapse=False,
+                                         fast_draws=False if fused else None))
+    assert torch.isfinite(outs[0]).all() and float(outs[0].abs().max()) <= 1.0
+    assert float((outs[0] - outs[1]).abs().max()) < 2e-6
+    const = torch.full((3, 4000), 2.5, device="cuda")                       # degenerate rows: zero swing
+    y = ta.augment_pcg_batch(const, 4125, AugmentConfig(prob_noise=0.0, prob_wandering_volume=0.0, prob_banding=0.0))
+    assert torch.isfinite(y).all() and float(y.abs().max()) <= 1.0
 
 
 def test_fused_chain_rejects_rows_beyond_a_cluster(ta):
