@@ -12,6 +12,7 @@
 // branch-free pass over the k slots),
 // O(k) per output instead of a fresh selection.  Median results are bit-exact functions of the magnitudes:
 // window [i - k/2, i - k/2 + k - 1], half-sample-symmetric reflection, rank k/2 (upper median for even k).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mpcg {
@@ -331,11 +332,13 @@ hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int
 
 // ---------------------------------------------------------------------------------------------- masks + ISTFT
 __device__ __forceinline__ float softmask2(float x, float ref, bool split_zeros) {
+  // librosa.util.softmask with power 2:  (x/z)^2 / ((x/z)^2 + (ref/z)^2),  z = max(x, ref).  One of the two ratios is
+  // exactly 1 (z / z), so only the other one is divided: same bits as the three-division form, two divisions.
   const float z = fmaxf(x, ref);
   if (z < FLT_MIN) return split_zeros ? 0.5f : 0.f;
-  const float a = x / z, b = ref / z;
-  const float m = a * a, r = b * b;
-  return m / (m + r);
+  const float q = fminf(x, ref) / z;
+  const float q2 = q * q;
+  return (x >= ref ? 1.f : q2) / (q2 + 1.f);
 }
 
 // A CTA transforms kIstftGroup consecutive frames of one row and overlap-adds them in shared memory first: with n_fft / hop
@@ -515,6 +518,138 @@ hpss_mix_kernel(const MixArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- 1024-point transforms, one WARP per frame
+// The block FFT above spends a 1024-point frame on 256 threads and four barrier-separated passes: at n_fft = 1024 it is
+// latency bound (1.3 us per frame and SM).  Here a warp owns a frame: lane l holds x[l + 32 j], j = 0..31, in REGISTERS,
+//   1. a 32-point FFT over j in registers (radix-2 DIF, twiddles are immediates; the result sits in bit-reversed
+//      registers, which costs nothing: register indices are compile-time),
+//   2. the twiddles W_1024^(l k1) from a 32 x 32 shared table and a transpose through the warp's private shared tile
+//      (row stride 33: conflict-free both ways),
+//   3. a second 32-point FFT in registers: lane k1 ends with X[k1 + 32 k2], k2 = 0..31,
+// no CTA barrier anywhere.  The forward kernel packs two real frames into one transform and unpacks them with one
+// shuffle pair per bin (Z[N - k] lives in lane 32 - k1, register 31 - k2): 6.7 -> 3.0 ms for the 1536 window transforms of
+// the composed pipeline.  Other transform sizes keep the block FFT, and so does the inverse direction: the same scheme
+// there (Hermitian halves of H + i P mirrored with shuffles, a round of four frames overlap-added cooperatively) came
+// out at 16.8 - 19.6 ms against 16.3 ms -- its frame is bound by the three input streams and the mask divisions, not
+// by the transform, and 106 registers leave 12 - 16 warps per SM to hide them.
+constexpr int kWfWarps = 4;
+constexpr int kWfThreads = 32 * kWfWarps;
+constexpr int kWfN = 1024;
+constexpr int kWfRow = 33;                          // float2 elements per row of a warp's transpose tile
+constexpr int kWfPairsPerWarp = 8;                  // forward: frame pairs a warp walks through
+
+__host__ __device__ constexpr int wf_br5(int k) {
+  return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+// d * exp(-/+ 2 pi i m / 32), m a compile-time constant after unrolling
+template <bool INV>
+__device__ __forceinline__ float2 wf_mul_root32(float2 d, int m) {
+  float c, s;
+  switch (m) {
+    case 0: return d;
+    case 1: c = 0.98078528040323043f; s = 0.19509032201612825f; break;
+    case 2: c = 0.92387953251128674f; s = 0.38268343236508978f; break;
+    case 3: c = 0.83146961230254524f; s = 0.55557023301960218f; break;
+    case 4: c = 0.70710678118654752f; s = 0.70710678118654752f; break;
+    case 5: c = 0.55557023301960218f; s = 0.83146961230254524f; break;
+    case 6: c = 0.38268343236508978f; s = 0.92387953251128674f; break;
+    case 7: c = 0.19509032201612825f; s = 0.98078528040323043f; break;
+    case 8: return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    case 9: c = -0.19509032201612825f; s = 0.98078528040323043f; break;
+    case 10: c = -0.38268343236508978f; s = 0.92387953251128674f; break;
+    case 11: c = -0.55557023301960218f; s = 0.83146961230254524f; break;
+    case 12: c = -0.70710678118654752f; s = 0.70710678118654752f; break;
+    case 13: c = -0.83146961230254524f; s = 0.55557023301960218f; break;
+    case 14: c = -0.92387953251128674f; s = 0.38268343236508978f; break;
+    default: c = -0.98078528040323043f; s = 0.19509032201612825f; break;
+  }
+  // forward: (c - i s); inverse: (c + i s)
+  return INV ? make_float2(d.x * c - d.y * s, d.x * s + d.y * c) : make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
+}
+// in-place 32-point DFT of a[0..31]; X[k] ends in a[wf_br5(k)]
+template <bool INV>
+__device__ __forceinline__ void wf_fft32(float2 (&a)[32]) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int b = 0; b < 32; b += 2 * h) {
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const float2 u = a[b + i], v = a[b + i + h];
+        a[b + i] = make_float2(u.x + v.x, u.y + v.y);
+        a[b + i + h] = wf_mul_root32<INV>(make_float2(u.x - v.x, u.y - v.y), i * (16 / h));
+      }
+    }
+  }
+}
+// The whole transform: in: a[j] = x[lane + 32 j]; out: X[lane + 32 k2] in a[wf_br5(k2)].  tws: [32][32] twiddles
+// W^(l k1) at tws[k1 * 32 + l] (already conjugated for the inverse); tile: this warp's [32][kWfRow] scratch.
+template <bool INV>
+__device__ __forceinline__ void wf_fft1024(float2 (&a)[32], const float2* __restrict__ tws, float2* __restrict__ tile, int lane) {
+  wf_fft32<INV>(a);
+  __syncwarp();                                      // the tile's previous readers are done
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) tile[k1 * kWfRow + lane] = fmulc(a[wf_br5(k1)], tws[k1 * 32 + lane]);
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) a[n2] = tile[lane * kWfRow + n2];
+  wf_fft32<INV>(a);
+}
+__device__ __forceinline__ void wf_build_twiddles(float2* tws, const float2* __restrict__ tw, bool inverse) {
+  for (int e = threadIdx.x; e < 1024; e += kWfThreads) {
+    const int m = ((e >> 5) * (e & 31)) & 1023;      // k1 * l
+    float2 w = __ldg(tw + (m & 511));                // exp(-2 pi i m / 1024), m < 512
+    if (m >= 512) w = make_float2(-w.x, -w.y);
+    if (inverse) w.y = -w.y;
+    tws[e] = w;
+  }
+}
+
+__global__ void __launch_bounds__(kWfThreads)
+hpss_stft_w1024_kernel(const float* __restrict__ x, float2* __restrict__ spec, long long t, int hop, int frames,
+                       const float* __restrict__ window, const float2* __restrict__ tw) {
+  __shared__ float2 tws[1024];
+  __shared__ float2 tiles[kWfWarps][32 * kWfRow];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = blockIdx.y;
+  const float* xr = x + row * t;
+  constexpr int bins = kWfN / 2 + 1;
+  wf_build_twiddles(tws, tw, false);
+  __syncthreads();
+  const int npairs = (frames + 1) / 2;
+  const int p0 = (blockIdx.x * kWfWarps + warp) * kWfPairsPerWarp;
+  for (int pp = p0; pp < p0 + kWfPairsPerWarp && pp < npairs; ++pp) {
+    const int frame = 2 * pp;
+    const bool two = frame + 1 < frames;
+    const long long base = (long long)frame * hop - kWfN / 2 + lane;
+    float2 a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const long long i0 = base + 32 * j, i1 = i0 + hop;
+      const float w = __ldg(window + lane + 32 * j);
+      a[j] = make_float2((i0 >= 0 && i0 < t) ? __ldg(xr + i0) * w : 0.f, (two && i1 >= 0 && i1 < t) ? __ldg(xr + i1) * w : 0.f);
+    }
+    wf_fft1024<false>(a, tws, tiles[warp], lane);
+    // two real frames from one transform: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / (2i)
+    float2* out_a = spec + ((long long)row * frames + frame) * bins;
+    float2* out_b = out_a + bins;
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int k2 = 0; k2 <= 16; ++k2) {
+      const float2 z = a[wf_br5(k2)];
+      const float2 other = a[wf_br5(31 - (k2 & 15))];                 // (k2 = 16: unused for lanes > 0)
+      const float ox = __shfl_sync(kFull, other.x, src), oy = __shfl_sync(kFull, other.y, src);
+      const float2 self = a[wf_br5((32 - k2) & 31)];
+      const float2 zc = lane ? make_float2(ox, oy) : self;
+      if (k2 < 16 || lane == 0) {
+        const int k = lane + 32 * k2;
+        out_a[k] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+        if (two) out_b[k] = make_float2(0.5f * (z.y + zc.y), 0.5f * (zc.x - z.x));
+      }
+    }
+  }
+}
+
 static int log2_exact(int n) {
   int l = 0;
   while ((1 << l) < n) ++l;
@@ -531,6 +666,14 @@ extern "C" int mpcg_hpss_stft_f32(const float* x, float* spec, int64_t rows, int
   if (rows == 0) return MPCG_OK;
   if (!x || !spec || !window || !twiddle) return MPCG_EINVAL;
   if (rows > 65535 || frames > 0x7fffffffLL) return MPCG_ERANGE;
+  if (n_fft == kWfN && !getenv("MPCG_HPSS_BLOCK_FFT")) {           // one warp per frame pair (no block barriers)
+    const int64_t pairs = (frames + 1) / 2;
+    dim3 grid((unsigned)((pairs + kWfWarps * kWfPairsPerWarp - 1) / (kWfWarps * kWfPairsPerWarp)), (unsigned)rows);
+    hpss_stft_w1024_kernel<<<grid, kWfThreads, 0, (cudaStream_t)stream>>>(x, (float2*)spec, (long long)t, hop, (int)frames,
+                                                                        window, (const float2*)twiddle);
+    MPCG_LAUNCH_CHECK();
+    return MPCG_OK;
+  }
   const size_t smem = (size_t)fpad(n_fft) * sizeof(float2);
   cudaError_t e = cudaFuncSetAttribute(hpss_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
