@@ -120,11 +120,14 @@ struct AcAcc {                              // (sum, min, max) of a thread's chu
 };
 
 // (sum, min, max) of the first `valid` of the L register samples: float32 partial sums of every fourth sample, added
-// up in float64 (the float64 <-> float32 conversion unit runs at a quarter of the FMA rate).
+// up in float64 (the float64 <-> float32 conversion unit runs at a quarter of the FMA rate).  A chunk whose offset
+// dwarfs its swing (raw rows that were never centred: |v| > 4 (max - min)) would lose the swing in those float32
+// partial sums -- the row mean came out 5e-5 of the range off for values around -300 +- 0.003 -- so such a chunk is
+// summed again as  n * min + sum (v - min):  the differences are exact (Sterbenz) and small.
 template <int L, typename V>
 __device__ __forceinline__ void ac_acc_chunk(const V& v, int valid, AcAcc& a) {
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  float lo = a.lo, hi = a.hi;
+  float lo = INFINITY, hi = -INFINITY;
   if (valid == L) {
 #pragma unroll
     for (int j = 0; j < L; ++j) {
@@ -142,9 +145,17 @@ __device__ __forceinline__ void ac_acc_chunk(const V& v, int valid, AcAcc& a) {
       }
     }
   }
-  a.lo = lo;
-  a.hi = hi;
-  a.sum += ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
+  double sum = ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
+  if (valid > 0 && fmaxf(fabsf(lo), fabsf(hi)) > 4.f * (hi - lo)) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < L; ++j)
+      if (j < valid) d[j & 3] += v[j] - lo;
+    sum = (double)valid * (double)lo + (((double)d[0] + (double)d[1]) + ((double)d[2] + (double)d[3]));
+  }
+  a.lo = fminf(a.lo, lo);
+  a.hi = fmaxf(a.hi, hi);
+  a.sum += sum;
 }
 
 // min / max of a float over the warp as ONE integer reduction (REDUX) on the order-preserving image of the bits
