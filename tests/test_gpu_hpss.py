@@ -16,7 +16,7 @@ def hp(built_lib):
     return hpss
 
 
-@pytest.mark.parametrize("n_fft,hop,t", [(512, 16, 4000), (1024, 128, 8192), (2048, 64, 5001)])
+@pytest.mark.parametrize("n_fft,hop,t", [(512, 16, 4000), (1024, 128, 8192), (2048, 64, 5001), (1024, 50, 5003), (1024, 64, 700)])
 def test_stft_vs_oracle(hp, n_fft, hop, t):
     x = np.random.default_rng(0).standard_normal((2, t)).astype(np.float32)
     got = hp.stft(torch.from_numpy(x).cuda(), n_fft, hop).cpu().numpy()            # [B, frames, bins]
