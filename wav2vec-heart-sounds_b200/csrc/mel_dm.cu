@@ -27,7 +27,10 @@ namespace mpcg {
 #define MPCG_DM_NT 4                  // 4-bin tiles per warp
 #endif
 constexpr int kDmMT = MPCG_DM_MT, kDmNT = MPCG_DM_NT;
-constexpr int kDmFT = 32;                        // frames per CTA (x 32 bins per pass over the samples)
+#ifndef MPCG_DM_FT
+#define MPCG_DM_FT 32
+#endif
+constexpr int kDmFT = MPCG_DM_FT;                // frames per CTA (x 32 bins per pass over the samples)
 constexpr int kDmWarps = (kDmFT / 8 / kDmMT) * (8 / kDmNT);
 constexpr int kDmThreads = 32 * kDmWarps;
 #ifndef MPCG_DM_SLOTS
