@@ -162,3 +162,34 @@ def test_fragment_dataset_item_list_matches_reference_rule():
         ref = FragmentDataset([Fragment(np.zeros(8), lab, f"p{i}") for i, lab in enumerate(labels)], 1000, augment_num=3,
                               augment_fn=lambda w, fs: w)
         assert ref.labels == ds.labels and [a for _, a in ref._items] == ds._aug.tolist()
+
+
+def test_mel_tables_of_the_float64_tensor_tier():
+    """The host-side tables of mpcg_mel_dm_f32 (include/mpcg_b200.h): the basis in fragment order reproduces the plain
+    windowed DFT basis entry for entry (column = 2 * bin + part, 16-sample slices, 4 pad entries), and the per-filter
+    bin ranges cover exactly the non-zero weights of the HTK filterbank."""
+    import warnings
+    from wav2vec_heart_sounds_b200 import MelConfig
+    for kw in (dict(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=80, f_max=500.0),
+               dict(sample_rate=4000, n_fft=1024, hop_length=256, n_mels=80, f_max=500.0),
+               dict(sample_rate=4000, n_fft=2048, win_length=1200, hop_length=300, n_mels=128, f_max=500.0)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr = MelConfig(**kw).build()
+        dm, rng = (t.numpy() for t in tr._dm_host)
+        basis = tr._basis_host.numpy()                                   # [win, 2, kpad] float64
+        win = basis.shape[0]
+        assert dm.shape == (tr.kpad // 32, -(-win // 16), 64, 20) and dm.dtype == np.float64
+        assert np.all(dm[..., 16:] == 0)
+        r = np.random.default_rng(0)
+        for _ in range(400):
+            n, k, part = int(r.integers(win)), int(r.integers(tr.kpad)), int(r.integers(2))
+            assert dm[k // 32, n // 16, 2 * (k % 32) + part, n % 16] == basis[n, part, k]
+        pad_rows = dm.reshape(dm.shape[0], -1, 64, 20)[:, -1, :, :16]    # samples beyond the window are zero rows
+        assert np.all(pad_rows[..., (win - 1) % 16 + 1:] == 0)
+        fb = tr._fb_host.numpy()                                         # [nbins, n_mels]
+        for m in range(tr.n_mels):
+            nz = np.nonzero(fb[:, m])[0]
+            lo, hi = int(rng[m, 0]), int(rng[m, 1])
+            assert (lo, hi) == ((int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 0))
+            assert np.all(fb[:lo, m] == 0) and np.all(fb[hi:, m] == 0)
