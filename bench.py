@@ -345,7 +345,7 @@ def run_ours(args):
                            "mode": "torch", "augment": "default AugmentConfig, in-kernel Philox noise, fresh draws every step",
                            "cache": "inputs (492 MB), windows (946 MB) and augmented windows (473 MB) per step exceed the 126 MB L2",
                            "sharding": f"{world} x index-sharded, no collective"},
-                "gpu_launches": 2 * args.steps,
+                "gpu_launches": 3 * args.steps,          # fused preprocess, per-row draws, augmentation chain
                 "stages": {"preprocess_segment_ms": pre_ms, "augment_chain_ms": aug_ms,
                            "preprocess_only_audio_s_per_s": RECORDINGS * SECONDS / (pre_ms * 1e-3),
                            "augment_GB/s": aug_bytes / (aug_ms * 1e-3) / 1e9},

@@ -198,6 +198,14 @@ int mpcg_mel_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft,
                  int kpad, const void* basis, int basis_f64, const float* fb, int n_mels, int64_t frames, int log_map,
                  void* stream);
 
+/* Per-row random draws of augment_pcg_batch's throughput mode in ONE launch (its own Philox stream; the reference draws
+ * the same quantities with ~40 small tensor operations, augment/torchaug.py:39-54,103-111): tab[i][row][j] = offset[i][j] +
+ * U * scale[i][j], an independent U per entry (scale 0 leaves offset[i][j]; i = noise 1 | wandering volume |
+ * noise 2, the [rows, 8] parameter tables of mpcg_aug_chain_f32); masks[i][row] = (U < prob[i]) as 0 / 1 floats.
+ * scale / offset: HOST [3][8]; prob: HOST [4]; tab: device [3][rows][8], 16-byte aligned; masks: device [4][rows]. */
+int mpcg_aug_draw_f32(float* tab, float* masks, int64_t rows, const float* scale, const float* offset, const float* prob,
+                      uint64_t seed, uint64_t sid, void* stream);
+
 /* The whole of augment_pcg_batch (augment/torchaug.py:103-111) in one kernel: N(x), noise, wandering volume, EQ, noise,
  * every stage behind its per-row mask and followed by the row re-normalisation, rows resident in cluster shared memory
  * (read once, written once).  rowp1 / rowp4: [rows, 8], [0] = scale*std of the noise stages; noise1 / noise4: injected

@@ -278,6 +278,29 @@ def test_fast_draws_distributions(ta):
     assert 0.01 <= float(amp.min()) and float(amp.max()) <= 0.25 and abs(float(amp.mean()) - 0.13) < 0.005
     assert 0.05 <= float(freq.min()) and float(freq.max()) <= 0.5 and 0.001 <= float(tab[1, :, 4].min()) and float(tab[1, :, 4].max()) <= 0.05
     assert 0 <= float(phase.min()) and float(phase.max()) < 1 and float(tab[1, :, 6:].abs().max()) == 0
+    # the one-launch draw kernel augment_pcg_batch uses (mpcg_aug_draw_f32): the same table from its own Philox stream
+    from wav2vec_heart_sounds_b200 import _lib
+    sc, of = ta._fast_draw_affine_host(0.01, 0.001)
+    probs = np.array([0.075, 0.75, 0.25, 0.075], np.float32)
+    t2, mk = torch.empty(3, b, 8, device="cuda"), torch.empty(4, b, device="cuda")
+    _lib.check(_lib.lib().mpcg_aug_draw_f32(t2.data_ptr(), mk.data_ptr(), b, sc.ctypes.data, of.ctypes.data, probs.ctypes.data,
+                                            5, 6, torch.cuda.current_stream().cuda_stream), "draw")
+    assert np.allclose(sc, scale.cpu().numpy()[:, 0]) and np.allclose(of, offset.cpu().numpy()[:, 0])
+    assert float(t2[0, :, 0].min()) >= 0 and float(t2[0, :, 0].max()) <= 0.1 * 0.01 and float(t2[0, :, 1:].abs().max()) == 0
+    assert abs(float(t2[0, :, 0].mean()) - 0.5e-3) < 2e-5 and abs(float(t2[2, :, 0].mean()) - 0.5e-4) < 2e-6
+    assert 0.01 <= float(t2[1, :, 0].min()) and float(t2[1, :, 0].max()) <= 0.25 and abs(float(t2[1, :, 0].mean()) - 0.13) < 0.005
+    assert 0.05 <= float(t2[1, :, 1].min()) and float(t2[1, :, 1].max()) <= 0.5 and abs(float(t2[1, :, 1].mean()) - 0.275) < 0.01
+    assert 0.001 <= float(t2[1, :, 4].min()) and float(t2[1, :, 4].max()) <= 0.05 and float(t2[1, :, 6:].abs().max()) == 0
+    assert 0 <= float(t2[1, :, 5].min()) and float(t2[1, :, 5].max()) < 1 and abs(float(t2[1, :, 5].mean()) - 0.5) < 0.01
+    for i in range(4):
+        assert set(mk[i].unique().tolist()) <= {0.0, 1.0} and abs(float(mk[i].mean()) - float(probs[i])) < 0.012
+    cols = torch.stack([t2[0, :, 0], t2[1, :, 0], t2[1, :, 1], t2[1, :, 2], t2[1, :, 3], t2[2, :, 0], mk[1], mk[2]])
+    cc = torch.corrcoef(cols)                                           # the draws of a row are independent of each other
+    assert float((cc - torch.eye(8, device="cuda")).abs().max()) < 0.03
+    t3, mk3 = torch.empty_like(t2), torch.empty_like(mk)
+    _lib.check(_lib.lib().mpcg_aug_draw_f32(t3.data_ptr(), mk3.data_ptr(), b, sc.ctypes.data, of.ctypes.data, probs.ctypes.data,
+                                            5, 7, torch.cuda.current_stream().cuda_stream), "draw")
+    assert not torch.equal(t2, t3)                                       # another stream id: another table
     x = torch.randn(512, 4125, device="cuda")
     outs = []
     for _ in range(2):

@@ -46,6 +46,8 @@ _SIGNATURES = {
                                    ctypes.c_uint64, c_f32p, c_f32p, ctypes.c_void_p, c_int, c_f32p, c_f32p, c_f32p, c_f32p,
                                    ctypes.c_uint64, ctypes.c_uint64, c_int, ctypes.c_void_p, c_i64, ctypes.c_void_p]),
     "mpcg_aug_chain_work_bytes": (c_i64, []),
+    "mpcg_aug_draw_f32": (c_int, [c_f32p, c_f32p, c_i64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                  ctypes.c_uint64, ctypes.c_void_p]),
     "mpcg_sosfiltfilt_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p, c_i64,
                                      ctypes.c_void_p]),
     "mpcg_sosfiltfilt_epi_f32": (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_i64, ctypes.c_void_p, c_int, ctypes.c_void_p, c_i64,

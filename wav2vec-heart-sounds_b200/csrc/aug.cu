@@ -231,3 +231,58 @@ extern "C" int mpcg_aug_eq_mix_f32(const float* x, const float* coloured, float*
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- per-row draws in one launch
+// The throughput mode of augment_pcg_batch (torchaug.py, fast_draws) needs, per row, the parameters of the three
+// elementwise stages and four Bernoulli masks.  One thread per row draws them from Philox (keyed by the
+// call's seed and the row) and writes the [3][rows][8] parameter table and the [4][rows] mask table the chain kernel
+// reads -- instead of five small framework launches per call.
+namespace mpcg {
+struct DrawSpec {
+  float scale[3][8], offset[3][8];           // table[i][row][j] = offset[i][j] + U * scale[i][j]   (scale 0: no draw)
+  float prob[4];                             // mask[i][row] = U < prob[i]
+};
+__global__ void aug_draw_kernel(float* __restrict__ tab, float* __restrict__ masks, long long rows, const DrawSpec s,
+                                unsigned long long seed, unsigned long long sid) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const uint2 key = make_uint2((unsigned)(seed ^ (sid * 0x9E3779B97F4A7C15ull)), (unsigned)((seed >> 32) ^ sid));
+  float u[28];                                 // one uniform per table entry (those without a draw are not used) + 4 masks
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)row, (unsigned)(row >> 32), (unsigned)c, 0x6d706367u), key);
+    u[4 * c + 0] = (float)(r.x >> 8) * 5.9604644775390625e-08f;     // 24 bits -> [0, 1)
+    u[4 * c + 1] = (float)(r.y >> 8) * 5.9604644775390625e-08f;
+    u[4 * c + 2] = (float)(r.z >> 8) * 5.9604644775390625e-08f;
+    u[4 * c + 3] = (float)(r.w >> 8) * 5.9604644775390625e-08f;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(u[8 * i + j], s.scale[i][j], s.offset[i][j]);
+    float4* dst = reinterpret_cast<float4*>(tab + ((long long)i * rows + row) * 8);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) masks[(long long)i * rows + row] = u[24 + i] < s.prob[i] ? 1.f : 0.f;
+}
+}  // namespace mpcg
+
+extern "C" int mpcg_aug_draw_f32(float* tab, float* masks, int64_t rows, const float* scale, const float* offset,
+                                 const float* prob, uint64_t seed, uint64_t sid, void* stream) {
+  using namespace mpcg;
+  if (rows < 0) return MPCG_EINVAL;
+  if (rows == 0) return MPCG_OK;
+  if (!tab || !masks || !scale || !offset || !prob || ((uintptr_t)tab & 15u)) return MPCG_EINVAL;
+  DrawSpec s;
+  for (int i = 0; i < 24; ++i) {
+    (&s.scale[0][0])[i] = scale[i];
+    (&s.offset[0][0])[i] = offset[i];
+  }
+  for (int i = 0; i < 4; ++i) s.prob[i] = prob[i];
+  aug_draw_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(tab, masks, (long long)rows, s, seed, sid);
+  MPCG_LAUNCH_CHECK();
+  return MPCG_OK;
+}

@@ -134,6 +134,17 @@ def _draw_bands(low, high, num_bands, bands=None):
 
 
 @functools.lru_cache(maxsize=64)
+def _fast_draw_affine_host(std1: float, std4: float):
+    """The same (scale, offset) tables as :func:`_fast_draw_affine`, contiguous float32 on the host ([3, 8] each)."""
+    scale, offset = np.zeros((3, 8), np.float32), np.zeros((3, 8), np.float32)
+    scale[0, 0], scale[2, 0] = np.float32(0.1) * np.float32(std1), np.float32(0.1) * np.float32(std4)
+    for k, (lo, hi) in enumerate(_SINE_BANDS):
+        scale[1, 3 * k:3 * k + 3] = (0.24, hi - lo, 1.0)
+        offset[1, 3 * k:3 * k + 3] = (0.01, lo, 0.0)
+    return scale, offset
+
+
+@functools.lru_cache(maxsize=64)
 def _fast_draw_affine(std1: float, std4: float, device):
     """(scale, offset) [3, 1, 8] turning U(0,1) into the rows of (noise 1 | wandering volume | noise 2) parameter tables:
     noise p[0] = U * 0.1 * std; volume (amp, freq, phase) per band = 0.01 + U * 0.24, lo + U * (hi - lo), U."""
@@ -241,7 +252,7 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
     second time -- ``N(N(x)) == N(x)`` up to float32 rounding (~1e-7 of the [-1, 1] range, far inside the 1e-5
     tolerance) -- which saves that stage's sweep and its cluster exchange; ``False`` re-normalises every time.
     ``fast_draws`` (default with ``noise="philox"`` and no injected ``draws``): the per-row random quantities come from
-    two device draws (same distributions as the reference, its own random stream) instead of the reference's sequence
+    ONE device launch (``mpcg_aug_draw_f32``: same distributions as the reference, its own Philox stream) instead of the reference's sequence
     of ~40 small launches; ``False`` keeps the reference's draw order."""
     cfg = cfg or AugmentConfig()
     x = _rows2d(x)
@@ -265,13 +276,16 @@ def augment_pcg_batch(x: torch.Tensor, fs: int, cfg: AugmentConfig | None = None
         if fast_draws and (noise != "philox" or d):
             raise ValueError("fast_draws goes with noise='philox' and no injected draws")
         if fast_draws:
-            # throughput mode: every per-row quantity from two device draws (a [3, B, 8] parameter table and a [4, B]
+            # throughput mode: every per-row quantity from one draw kernel (a [3, B, 8] parameter table and a [4, B]
             # mask table) instead of the reference's ~40 small launches; same distributions, its own random stream
             std1, std4 = float(np.random.choice(_NOISE_STDS)), float(np.random.choice(_NOISE_STDS))
-            scale, offset = _fast_draw_affine(std1, std4, dev)
-            tab = torch.addcmul(offset, torch.rand(3, b, 8, device=dev), scale)
-            probs = _fast_draw_probs(cfg.prob_noise / 4, cfg.prob_wandering_volume, cfg.prob_banding, dev)
-            masks = (torch.rand(4, b, device=dev) < probs).float()
+            scale, offset = _fast_draw_affine_host(std1, std4)
+            probs = np.array([cfg.prob_noise / 4, cfg.prob_wandering_volume, cfg.prob_banding, cfg.prob_noise / 4], np.float32)
+            tab = torch.empty(3, b, 8, device=dev)
+            masks = torch.empty(4, b, device=dev)
+            dseed, dsid = _philox_key()
+            _lib.check(_lib.lib().mpcg_aug_draw_f32(tab.data_ptr(), masks.data_ptr(), b, scale.ctypes.data, offset.ctypes.data,
+                                                    probs.ctypes.data, dseed, dsid, _lib.stream_ptr(x)), "per-row draws")
             rowp1, rowp2, rowp4 = tab[0], tab[1], tab[2]
             m1, m2, m3, m4 = masks[0], masks[1], masks[2], masks[3]
             nz1 = nz4 = None
