@@ -92,11 +92,20 @@ mel_dm_kernel(const DmArgs a) {
   {
     const long long base = (long long)f0 * a.hop + a.n_lo - a.n_fft / 2;
     for (int seg = warp; seg < a.nsegs; seg += kDmWarps) {
-      for (int jj = lane; jj < a.hop; jj += 32) {
-        long long j = base + (long long)seg * a.hop + jj;
-        if (j < 0) j = -j;
-        if (j >= a.t) j = 2 * (a.t - 1) - j;
-        xs[seg * a.segw + jj] = (j >= 0 && j < a.t) ? __ldg(xr + j) : 0.f;
+      const long long j0 = base + (long long)seg * a.hop;
+      float* dst = xs + seg * a.segw;
+      if (j0 >= 0 && j0 + a.hop <= a.t && (a.hop & 3) == 0 && (a.segw & 3) == 0 &&
+          ((reinterpret_cast<uintptr_t>(xr + j0)) & 15u) == 0) {            // interior row: 128-bit loads and stores
+        const float4* src4 = reinterpret_cast<const float4*>(xr + j0);
+        float4* dst4 = reinterpret_cast<float4*>(dst);
+        for (int q = lane; q < (a.hop >> 2); q += 32) dst4[q] = __ldg(src4 + q);
+      } else {
+        for (int jj = lane; jj < a.hop; jj += 32) {
+          long long j = j0 + jj;
+          if (j < 0) j = -j;
+          if (j >= a.t) j = 2 * (a.t - 1) - j;
+          dst[jj] = (j >= 0 && j < a.t) ? __ldg(xr + j) : 0.f;
+        }
       }
     }
   }
