@@ -207,14 +207,14 @@ int mpcg_aug_draw_f32(float* tab, float* masks, int64_t rows, const float* scale
                       uint64_t seed, uint64_t sid, void* stream);
 
 /* The whole of augment_pcg_batch (augment/torchaug.py:103-111) in one kernel: N(x), noise, wandering volume, EQ, noise,
- * every stage behind its per-row mask and followed by the row re-normalisation, rows resident in cluster shared memory
+ * every stage behind its per-row mask and followed by the row re-normalisation, rows resident in the registers of a thread-block cluster
  * (read once, written once).  rowp1 / rowp4: [rows, 8], [0] = scale*std of the noise stages; noise1 / noise4: injected
  * standard normals [rows, t] or NULL (in-kernel Philox keyed by (seedN, sidN, row, sample)); rowp2: [rows, 8] =
  * (amp, freq, phase) x 2 of sinusoidal_envelope; eq_sos: [eq_sections, 6] SciPy-layout sections shared by the batch
  * (0 sections = no EQ stage transform); maskN: [rows] 0/1 or NULL (= all rows).  y must not alias x.
  * flags: MPCG_AUG_CHAIN_COLLAPSE = a stage whose mask is off for a row does not re-normalise that (already normalised)
  * row again -- N(N(x)) equals N(x) to ~1e-7 -- which saves its sweep and its exchange; 0 = re-normalise every time.
- * MPCG_EUNSUPPORTED when a row does not fit an 8-CTA cluster (t > 133120): compose mpcg_aug_stage_f32 instead. */
+ * MPCG_EUNSUPPORTED when a row does not fit an 8-CTA cluster (t > 135168): compose mpcg_aug_stage_f32 instead. */
 int mpcg_aug_chain_f32(const float* x, float* y, int64_t rows, int64_t t, float fs, const float* rowp1,
                        const float* noise1, const float* mask1, uint64_t seed1, uint64_t sid1, const float* rowp2,
                        const float* mask2, const double* eq_sos, int eq_sections, const float* mask3,

@@ -168,7 +168,8 @@ class _WholeRow:
 
 def _fused_rows(x: torch.Tensor, fs_in: float, fs_out: float, kind: str, despike: bool, mode: str):
     """One fused launch (resample -> [despike] -> band -> normalise, the row written once) or None when the row does
-    not fit the cluster kernel (the caller then chains the stand-alone kernels: same arithmetic, more HBM traffic)."""
+    suit the fused kernel, e.g. a resampling ratio without baked taps (the caller then chains the stand-alone kernels:
+    same arithmetic, more HBM traffic)."""
     from .pipeline import preprocess_segment           # late: pipeline imports this module
     lead, t_in = x.shape[:-1], x.shape[-1]
     if t_in == 0 or x.numel() == 0:
