@@ -175,3 +175,13 @@ def test_float64_tier_on_odd_shapes(pkg, kw, t):
     want = otp.log_mel(xd.double(), ref).numpy()
     got = pkg.log_mel(xd.cuda(), tr).cpu().numpy()
     assert np.abs(got - want).max() < 1e-5
+
+
+def test_more_rows_than_one_launch_takes(pkg):
+    """Batches beyond 65 535 rows (a grid dimension) run as consecutive launches over row blocks."""
+    tr = pkg.MelConfig(sample_rate=2000, n_fft=64, hop_length=16, n_mels=8, f_max=400.0).build()
+    x = torch.randn(70000, 200, device="cuda")
+    y = pkg.log_mel(x, tr)
+    assert y.shape == (70000, 8, 13)
+    assert torch.equal(y[65530:65540], pkg.log_mel(x[65530:65540], tr))
+    assert torch.equal(y[:5], pkg.log_mel(x[:5], tr))

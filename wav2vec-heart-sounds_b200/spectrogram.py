@@ -135,10 +135,15 @@ class MelTransform:
     def num_frames(self, t: int) -> int:
         return 1 + t // self.hop_length
 
+    _MAX_ROWS = 65535                                 # rows of one launch (a grid dimension of the FMA / DMMA kernels)
+
     def _run(self, signal: torch.Tensor, log_map: bool) -> torch.Tensor:
         x = _lib.require_cuda_f32(signal)
         lead, t = x.shape[:-1], x.shape[-1]
         rows = x.reshape(-1, t)
+        if rows.shape[0] > self._MAX_ROWS:                # bigger batches: consecutive launches over row blocks
+            parts = [self._run(rows[i:i + self._MAX_ROWS], log_map) for i in range(0, rows.shape[0], self._MAX_ROWS)]
+            return torch.cat(parts, dim=0).reshape(*lead, self.n_mels, parts[0].shape[-1])
         if t <= self.n_fft // 2:
             raise ValueError(f"signal of {t} samples is too short for reflect padding of {self.n_fft // 2}")
         frames = self.num_frames(t)
