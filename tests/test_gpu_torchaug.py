@@ -328,3 +328,14 @@ def test_chain_degenerate_inputs(ta):
     assert torch.equal(a, b)
     with pytest.raises(ValueError):
         ta.augment_pcg_batch(torch.randn(10, device="cuda"), 4125)
+
+
+def test_more_rows_than_a_grid_dimension(ta):
+    """amplitude_warp and time_warp put rows on gridDim.y (65 535 at most): bigger batches run as consecutive launches."""
+    x = torch.randn(66000, 300, device="cuda")
+    amps = 0.7 + torch.rand(66000, 12) * 0.6
+    y = ta.amplitude_warp(x, amps=amps)
+    for sl in (slice(0, 3), slice(65533, 65538), slice(65997, 66000)):
+        assert torch.equal(y[sl], ta.amplitude_warp(x[sl], amps=amps[sl]))
+    z = ta.time_warp(x, 4125, 1.02)
+    assert torch.equal(z[65530:65540], ta.time_warp(x[65530:65540].contiguous(), 4125, 1.02))

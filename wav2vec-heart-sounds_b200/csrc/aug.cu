@@ -209,10 +209,12 @@ extern "C" int mpcg_aug_warp_f32(const float* x, float* y, int64_t rows, int64_t
   if (rows == 0 || t == 0) return MPCG_OK;
   if (!x || !y || !curves) return MPCG_EINVAL;
   if (t <= ntaps / 2) return MPCG_EINVAL;                           // reflect padding needs pad < length
-  if (rows > 65535) return MPCG_ERANGE;
   const size_t smem = (size_t)(wp_skew(kWpTile + ntaps - 1 + kWpOut) + 1 + ntaps) * sizeof(float);
-  dim3 grid((unsigned)((t + kWpTile - 1) / kWpTile), (unsigned)rows);
-  aug_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, y, (long long)t, curves, ntaps);
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {                      // (rows are a grid dimension: blocks of 65 535)
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid((unsigned)((t + kWpTile - 1) / kWpTile), (unsigned)nr);
+    aug_warp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x + r0 * t, y + r0 * t, (long long)t, curves + r0 * ntaps, ntaps);
+  }
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }

@@ -104,9 +104,12 @@ static int launch_frames(const float* x, float* y, int64_t rows, int64_t t_in, i
   if (e != cudaSuccess) return (int)e;
   const int64_t frames = (t_out + UP - 1) / UP;
   const int64_t tiles = (frames + S::T::NF - 1) / S::T::NF;
-  if (tiles > 0x7fffffffLL || rows > 65535) return MPCG_ERANGE;
-  dim3 grid((unsigned)tiles, (unsigned)rows);
-  kern<<<grid, kRsThreads, S::SMEM, stream>>>(x, y, (long long)t_in, (long long)t_out, (long long)off);
+  if (tiles > 0x7fffffffLL) return MPCG_ERANGE;
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {                      // (rows are a grid dimension: blocks of 65 535)
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid((unsigned)tiles, (unsigned)nr);
+    kern<<<grid, kRsThreads, S::SMEM, stream>>>(x + r0 * t_in, y + r0 * t_out, (long long)t_in, (long long)t_out, (long long)off);
+  }
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }

@@ -163,9 +163,11 @@ extern "C" int mpcg_time_warp_f32(const float* x, float* y, int64_t rows, int64_
   if (rows < 0 || t < 0 || n_out < 0 || !(rate > 0.0)) return MPCG_EINVAL;
   if (rows == 0 || n_out == 0) return MPCG_OK;
   if (t < 1 || !x || !y) return MPCG_EINVAL;
-  if (rows > 65535) return MPCG_ERANGE;
-  dim3 grid((unsigned)((n_out + 1023) / 1024), (unsigned)rows);
-  time_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, (long long)t, (long long)n_out, rate);
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {                      // (rows are a grid dimension: blocks of 65 535)
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid((unsigned)((n_out + 1023) / 1024), (unsigned)nr);
+    time_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x + r0 * t, y + r0 * n_out, (long long)t, (long long)n_out, rate);
+  }
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }
