@@ -537,6 +537,27 @@ def other_paths(dev, peak):
     res["log_mel_default"] = {"workload": "same input, MelConfig.build() default: " + tr64.backend,
                               "ms": ms64, "windows_per_s": 8192 / (ms64 * 1e-3), "fp64_TFLOP/s": 2 * fma64 / ms64 / 1e9,
                               "GB/s": nbytes / ms64 / 1e6, "frac_of_hbm_peak": nbytes / ms64 / 1e6 / peak}
+    del xm
+    # row H: one HPSS split (STFT, two medians, masks + inverse transform) at the composed pipeline's transform size
+    try:
+        from wav2vec_heart_sounds_b200 import hpss as _hpss
+        xh = torch.randn(256, 64000, device=dev, generator=g)
+        ms_h = best_ms(lambda: _hpss.hpss_split(xh, 1024, 64, (1.5, 2.0), (17, 17)), reps=3)
+        res["hpss_split"] = {"workload": "hpss_split of 256 windows x 64000 @16 kHz, n_fft 1024 / hop 64 / medians (17, 17)",
+                             "ms": ms_h, "windows_per_s": 256 / (ms_h * 1e-3)}
+        del xh
+    except Exception as exc:
+        res["hpss_split"] = {"error": f"{type(exc).__name__}: {exc}"}
+    # generator conditioning: normalise, fade, fit, default log-mel, crop of 4096 x 32000 @4 kHz
+    try:
+        xs = torch.randn(4096, 32000, device=dev, generator=g)
+        melc = MelConfig(sample_rate=4000, n_fft=1024, hop_length=256, n_mels=80, f_max=500).build()
+        ms_c = best_ms(lambda: pkg.condition_generator_batch(xs, xs, 4000, melc, 96, 256), reps=3)
+        res["condition_generator_batch"] = {"workload": "condition_generator_batch, 4096 x 32000 @4 kHz, DiffWave preset (127 weighted bins), "
+                                                        + melc.backend, "ms": ms_c, "items_per_s": 4096 / (ms_c * 1e-3)}
+        del xs
+    except Exception as exc:
+        res["condition_generator_batch"] = {"error": f"{type(exc).__name__}: {exc}"}
     return res
 
 
