@@ -6,7 +6,9 @@ installed here and cannot be (no network); no reference test exercises it either
 ``prob_hpss=0``).  This module therefore restates librosa's *published* algorithm in NumPy, and calls
 ``scipy.ndimage.median_filter`` -- the routine librosa itself calls for the selection step -- for the medians.
 It is pinned only by internal identities (``tests/test_oracle_hpss.py``: H + P + R == S, ISTFT(STFT(x)) == x on the
-trimmed span, median rank/reflection rules against hand-worked cases), not by reference outputs.
+trimmed span, median rank/reflection rules against hand-worked cases) and by agreement of its transforms with
+``torch.stft`` / ``torch.istft`` (same centring, window and normalisation) and of its medians with
+``scipy.ndimage.median_filter``, not by reference outputs.
 
 librosa semantics restated:
 * ``stft``: periodic Hann of length n_fft, ``center=True`` with ZERO padding of n_fft//2, frames = 1 + len//hop,

@@ -54,3 +54,30 @@ def test_recombine_is_normalised_and_deterministic():
     assert n == 2048 and y.shape == (2048,) and np.abs(y).max() <= 1.0 and abs(np.abs(y).max() - 1.0) < 1e-12
     y4, n4 = oh.hpss_recombine(x, dict(p, w1=p["w1"][:4], w2=p["w2"][:4]), include_residual=False)
     assert n4 == 2048 and not np.allclose(y, y4)
+
+
+def test_transforms_equal_the_torch_and_scipy_equivalents():
+    """librosa's stft / istft (centre padding with zeros, periodic Hann of n_fft, istft normalised by the window's
+    sum of squares and trimmed) are the same transforms as ``torch.stft`` / ``torch.istft`` with those arguments and
+    as ``scipy.signal.ShortTimeFFT``-style framing; the restatement must agree with those independent implementations
+    to float64 rounding.  (Not a substitute for reference outputs -- the module stays "parity unpinned" -- but it ties
+    two of its three stages to library code that is installed here.)"""
+    import torch
+    from scipy import ndimage
+    rng = np.random.default_rng(12)
+    for n_fft, hop, t in ((512, 32, 3000), (1024, 64, 5003), (2048, 128, 9000), (256, 50, 1234)):
+        y = rng.standard_normal(t)
+        s = oh.stft(y, n_fft, hop)                                             # [bins, frames]
+        w = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+        ts = torch.stft(torch.from_numpy(y), n_fft, hop_length=hop, win_length=n_fft, window=w, center=True,
+                        pad_mode="constant", return_complex=True).numpy()
+        assert s.shape == ts.shape == (n_fft // 2 + 1, 1 + t // hop)
+        assert np.abs(s - ts).max() < 1e-10 * np.abs(ts).max()
+        back = oh.istft(s, n_fft, hop)
+        tb = torch.istft(torch.from_numpy(ts), n_fft, hop_length=hop, win_length=n_fft, window=w, center=True).numpy()
+        assert back.shape == tb.shape == (hop * (t // hop),)
+        assert np.abs(back - tb).max() < 1e-10
+        mag = np.abs(s)
+        for k in (5, 17, 30):
+            np.testing.assert_array_equal(oh.median_time(mag, k), ndimage.median_filter(mag, size=(1, k), mode="reflect"))
+            np.testing.assert_array_equal(oh.median_freq(mag, k), ndimage.median_filter(mag, size=(k, 1), mode="reflect"))
