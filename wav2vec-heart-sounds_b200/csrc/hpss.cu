@@ -175,13 +175,18 @@ __device__ __forceinline__ void med_first_window(const MedLine& ln, float* sw, f
   }
 }
 
-__device__ __forceinline__ bool med_setup(MedLine& ln, const float2* spec, float* out, int frames, int bins, int along_time) {
-  const long long row = blockIdx.y;
-  const int line = blockIdx.x * kMedThreads + threadIdx.x;
-  if (line >= (along_time ? bins : frames)) return false;
+__device__ __forceinline__ bool med_setup(MedLine& ln, const float2* spec, float* out, int frames, int bins, int along_time,
+                                          long long rows) {
+  // lines are numbered across the whole batch (a CTA's 128 threads may straddle two rows): no CTA is left with the one
+  // or two lines that 513 bins leave over after four full CTAs -- a lone lane costs a whole warp's issue slots
+  const long long per_row = along_time ? bins : frames;
+  const long long gline = (long long)blockIdx.x * kMedThreads + threadIdx.x;
+  if (gline >= rows * per_row) return false;
+  const long long row = gline / per_row;
+  const int line = (int)(gline - row * per_row);
   ln.len = along_time ? frames : bins;
   ln.stride = along_time ? bins : 1;
-  const long long off = (long long)row * frames * bins + (along_time ? line : (long long)line * bins);
+  const long long off = row * frames * bins + (along_time ? line : (long long)line * bins);
   ln.src = spec + off;
   ln.dst = out + off;
   return true;
@@ -269,10 +274,11 @@ hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out
 
 template <int K>
 __global__ void __launch_bounds__(kMedThreads)
-hpss_median_reg_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time) {
+hpss_median_reg_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time,
+                       long long rows) {
   extern __shared__ float med_sorted[];                          // [k][kMedThreads] first window + [k][kMedThreads] ring
   MedLine ln;
-  if (!med_setup(ln, spec, out, frames, bins, along_time)) return;
+  if (!med_setup(ln, spec, out, frames, bins, along_time, rows)) return;
   float* sw = med_sorted + threadIdx.x;
   float* ring = med_sorted + k * kMedThreads + threadIdx.x;
   const int left = k / 2, below = K / 2 - left;                  // -inf sentinels under the window
@@ -300,10 +306,11 @@ hpss_median_reg_kernel(const float2* __restrict__ spec, float* __restrict__ out,
 }
 
 __global__ void __launch_bounds__(kMedThreads)
-hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time) {
+hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k, int along_time,
+                   long long rows) {
   extern __shared__ float med_sorted[];                          // [k][kMedThreads] sorted + [k][kMedThreads] ring
   MedLine ln;
-  if (!med_setup(ln, spec, out, frames, bins, along_time)) return;
+  if (!med_setup(ln, spec, out, frames, bins, along_time, rows)) return;
   float* sw = med_sorted + threadIdx.x;
   float* ring = med_sorted + k * kMedThreads + threadIdx.x;
   const int left = k / 2;
@@ -695,6 +702,9 @@ extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows,
   const int64_t nlines = along_time ? bins : frames;
   const size_t smem = 2 * (size_t)k * kMedThreads * sizeof(float);
   dim3 grid((unsigned)((nlines + kMedThreads - 1) / kMedThreads), (unsigned)rows);
+  const long long flat_ctas = (rows * nlines + kMedThreads - 1) / kMedThreads;      // lines numbered across the batch
+  if (flat_ctas > 0x7fffffffLL) return MPCG_ERANGE;
+  dim3 flat((unsigned)flat_ctas);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(hpss_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -704,7 +714,7 @@ extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows,
   const size_t smem_f = (size_t)k * kMedThreads * sizeof(float) + 2 * (size_t)kMedChunk * (kMedThreads + 1) * sizeof(float);
 #define MED_REG(KK)                                                                                                  \
   if (along_time) {                                                                                                  \
-    hpss_median_reg_kernel<KK><<<grid, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, 1);                      \
+    hpss_median_reg_kernel<KK><<<flat, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, 1, (long long)rows);     \
   } else {                                                                                                           \
     cudaError_t e = cudaFuncSetAttribute(hpss_median_freq_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                          (int)smem_f);                                                               \
@@ -720,7 +730,7 @@ extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows,
     case 6: MED_REG(24); break;
     case 7: MED_REG(28); break;
     case 8: MED_REG(32); break;
-    default: hpss_median_kernel<<<grid, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, along_time);
+    default: hpss_median_kernel<<<flat, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, along_time, (long long)rows);
   }
 #undef MED_REG
   MPCG_LAUNCH_CHECK();
