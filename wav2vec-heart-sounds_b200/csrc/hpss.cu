@@ -207,15 +207,17 @@ __device__ __forceinline__ void med_slide(float (&a)[K], float gone, float come)
 // memory, so the magnitudes are staged through shared memory -- every warp loads 32 consecutive bins of one frame
 // (256 contiguous bytes), the medians of a chunk go back the same way.  The walk consumes the reflected input stream
 // position by position: stream position s is bin s - k/2, output i is complete once position i + k - 1 has arrived.
-constexpr int kMedChunk = 32;
-template <int K>
+// CH = bins staged per round (32 or 16: a warp loads 32 / CH frames at a time).  Windows of up to 20 samples take 16: the
+// tiles shrink to 8 KB each, 25 KB per CTA instead of 42, nine CTAs per SM instead of five (1.28 -> 1.12 ms at k = 17);
+// longer windows keep 32 (their first-window scratch sets the size of the output tile anyway).
+template <int K, int CH>
 __global__ void __launch_bounds__(kMedThreads)
 hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out, int frames, int bins, int k) {
   extern __shared__ float med_sorted[];                          // ring [k][T] | in [32][T+1] | out [32][T+1] (first-window sort inside out)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* ring = med_sorted + tid;
   float* tin = med_sorted + k * kMedThreads;
-  float* tout = tin + kMedChunk * (kMedThreads + 1);
+  float* tout = tin + CH * (kMedThreads + 1);
   float* sw = tout + tid;                                        // first-window scratch: dead before tout is written
   const long long row = blockIdx.y;
   const int f0 = blockIdx.x * kMedThreads;
@@ -224,24 +226,29 @@ hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out
   const int nf = min(kMedThreads, frames - f0);                  // frames of this CTA
   const int left = k / 2, below = K / 2 - left;
   // stage stream positions [s0, s0 + 32): magnitude of bin reflect(s - left) of every frame of the CTA
+  constexpr int FPW = 32 / CH;                              // frames a warp stages per iteration
+  const int cl = lane % CH, fsub = lane / CH;
   auto stage_in = [&](int s0) {
-    const int j = s0 + lane - left;
+    const int j = s0 + cl - left;
     const int b = (unsigned)j < (unsigned)bins ? j : reflect_idx(j, bins);
-    for (int f = warp; f < kMedThreads; f += kMedThreads / 32) {
+    for (int f = warp * FPW + fsub; f < kMedThreads; f += kMedThreads / 32 * FPW) {
       float m = 0.f;
       if (f < nf) { const float2 v = src[(long long)f * bins + b]; m = sqrtf(v.x * v.x + v.y * v.y); }
-      tin[lane * (kMedThreads + 1) + f] = m;
+      tin[cl * (kMedThreads + 1) + f] = m;
     }
   };
-  // first window: stream positions 0 .. k-1 (k <= 32: one staged chunk)
-  stage_in(0);
-  __syncthreads();
-  for (int q = 0; q < k; ++q) {
-    const float v = tin[q * (kMedThreads + 1) + tid];
-    ring[q * kMedThreads] = v;
-    int p = q;
-    while (p > 0 && sw[(p - 1) * kMedThreads] > v) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
-    sw[p * kMedThreads] = v;
+  // first window: stream positions 0 .. k-1, one or two staged chunks
+  for (int q0 = 0; q0 < k; q0 += CH) {
+    if (q0) __syncthreads();
+    stage_in(q0);
+    __syncthreads();
+    for (int q = q0; q < k && q < q0 + CH; ++q) {
+      const float v = tin[(q - q0) * (kMedThreads + 1) + tid];
+      ring[q * kMedThreads] = v;
+      int p = q;
+      while (p > 0 && sw[(p - 1) * kMedThreads] > v) { sw[p * kMedThreads] = sw[(p - 1) * kMedThreads]; --p; }
+      sw[p * kMedThreads] = v;
+    }
   }
   float a[K];
 #pragma unroll
@@ -252,11 +259,11 @@ hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out
   if (tid < nf) dst[(long long)tid * bins] = a[K / 2];             // output 0
   int slot = 0;
   const int total = bins + k - 1;                                 // stream length
-  for (int s0 = k; s0 < total; s0 += kMedChunk) {
+  for (int s0 = k; s0 < total; s0 += CH) {
     __syncthreads();
     stage_in(s0);
     __syncthreads();
-    const int n = min(kMedChunk, total - s0);
+    const int n = min(CH, total - s0);
     for (int c = 0; c < n; ++c) {
       const float come = tin[c * (kMedThreads + 1) + tid];
       const float gone = ring[slot * kMedThreads];
@@ -267,8 +274,8 @@ hpss_median_freq_kernel(const float2* __restrict__ spec, float* __restrict__ out
     }
     __syncthreads();
     const int i0 = s0 - k + 1;
-    for (int f = warp; f < nf; f += kMedThreads / 32)
-      if (lane < n) dst[(long long)f * bins + i0 + lane] = tout[lane * (kMedThreads + 1) + f];
+    for (int f = warp * FPW + fsub; f < nf; f += kMedThreads / 32 * FPW)
+      if (cl < n) dst[(long long)f * bins + i0 + cl] = tout[cl * (kMedThreads + 1) + f];
   }
 }
 
@@ -711,15 +718,23 @@ extern "C" int mpcg_hpss_median_f32(const float* spec, float* out, int64_t rows,
   }
   cudaStream_t st = (cudaStream_t)stream;
   const float2* sp = (const float2*)spec;
-  const size_t smem_f = (size_t)k * kMedThreads * sizeof(float) + 2 * (size_t)kMedChunk * (kMedThreads + 1) * sizeof(float);
+  const int ch = (k <= 20 || bins <= 320) ? 16 : 32;              // staging chunk of the frequency direction (measured: k 17 / 30, 257 - 1025 bins)
+  const size_t out_tile = (size_t)ch * (kMedThreads + 1) > (size_t)k * kMedThreads ? (size_t)ch * (kMedThreads + 1)
+                                                                                  : (size_t)k * kMedThreads;
+  const size_t smem_f = ((size_t)k * kMedThreads + (size_t)ch * (kMedThreads + 1) + out_tile) * sizeof(float);
 #define MED_REG(KK)                                                                                                  \
   if (along_time) {                                                                                                  \
     hpss_median_reg_kernel<KK><<<flat, kMedThreads, smem, st>>>(sp, out, (int)frames, bins, k, 1, (long long)rows);     \
-  } else {                                                                                                           \
-    cudaError_t e = cudaFuncSetAttribute(hpss_median_freq_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+  } else if (ch == 16) {                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(hpss_median_freq_kernel<KK, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem_f);                                                               \
     if (e != cudaSuccess) return (int)e;                                                                             \
-    hpss_median_freq_kernel<KK><<<grid, kMedThreads, smem_f, st>>>(sp, out, (int)frames, bins, k);                     \
+    hpss_median_freq_kernel<KK, 16><<<grid, kMedThreads, smem_f, st>>>(sp, out, (int)frames, bins, k);                 \
+  } else {                                                                                                           \
+    cudaError_t e = cudaFuncSetAttribute(hpss_median_freq_kernel<KK, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem_f);                                                               \
+    if (e != cudaSuccess) return (int)e;                                                                             \
+    hpss_median_freq_kernel<KK, 32><<<grid, kMedThreads, smem_f, st>>>(sp, out, (int)frames, bins, k);                 \
   }
   switch ((k + 3) / 4) {
     case 1: MED_REG(4); break;
