@@ -96,9 +96,57 @@ __device__ __forceinline__ void fft_shared_dir(float2* a, int log2n, const float
   while (log2n - s >= 2) { fft_pass<2, INV>(a, log2n, tw, s); s += 2; }
   if (log2n - s == 1) fft_pass<1, INV>(a, log2n, tw, s);
 }
+// The same with the transform size and the stage known at compile time (n_fft 512 / 1024 / 2048, the reference's choices):
+// a pass at stage S touches a[fpad(i0 + (m << S))], and because bits S .. S+Q-1 of i0 are zero the padded index is
+// fpad(i0) + a CONSTANT per m -- one index computation per butterfly instead of 2^(Q+1) (the block transform is issue
+// bound: 78 % of the slots busy in the inverse kernel).
+template <int Q, bool INV, int LOG2N, int S>
+__device__ __forceinline__ void fft_pass_s(float2* a, const float2* __restrict__ tw) {
+  constexpr int R = 1 << Q;
+  constexpr int hl = LOG2N - 1, lg = LOG2N - Q;
+  for (int j = threadIdx.x; j < (1 << lg); j += kFftThreads) {
+    const int p = j & ((1 << S) - 1);
+    const int i0 = ((j >> S) << (S + Q)) + p;
+    float2* a0 = a + fpad(i0);
+    float2 r[R], base[Q];
+#pragma unroll
+    for (int m = 0; m < R; ++m) r[m] = a0[fpad(m << S)];
+    base[Q - 1] = __ldg(tw + (p << (hl - (S + Q - 1))));
+    if (INV) base[Q - 1].y = -base[Q - 1].y;
+#pragma unroll
+    for (int u = Q - 2; u >= 0; --u) base[u] = fmulc(base[u + 1], base[u + 1]);
+    FftStage<Q, INV, 0, 0>::run(r, base);
+    if constexpr (Q > 1) FftStage<Q, INV, 1, 0>::run(r, base);
+    if constexpr (Q > 2) FftStage<Q, INV, 2, 0>::run(r, base);
+#pragma unroll
+    for (int m = 0; m < R; ++m) a0[fpad(m << S)] = r[m];
+  }
+  __syncthreads();
+}
+template <bool INV, int LOG2N, int S = 0>
+__device__ __forceinline__ void fft_static(float2* a, const float2* __restrict__ tw) {
+  if constexpr (LOG2N - S > 4 || LOG2N - S == 3) {
+    fft_pass_s<3, INV, LOG2N, S>(a, tw);
+    fft_static<INV, LOG2N, S + 3>(a, tw);
+  } else if constexpr (LOG2N - S >= 2) {
+    fft_pass_s<2, INV, LOG2N, S>(a, tw);
+    fft_static<INV, LOG2N, S + 2>(a, tw);
+  } else if constexpr (LOG2N - S == 1) {
+    fft_pass_s<1, INV, LOG2N, S>(a, tw);
+  }
+}
+template <bool INV>
+__device__ __forceinline__ void fft_shared_any(float2* a, int log2n, const float2* __restrict__ tw) {
+  switch (log2n) {
+    case 9: fft_static<INV, 9>(a, tw); break;
+    case 10: fft_static<INV, 10>(a, tw); break;
+    case 11: fft_static<INV, 11>(a, tw); break;
+    default: fft_shared_dir<INV>(a, log2n, tw);
+  }
+}
 __device__ __forceinline__ void fft_shared(float2* a, int n, int log2n, bool inverse, const float2* __restrict__ tw) {
   (void)n;
-  if (inverse) fft_shared_dir<true>(a, log2n, tw); else fft_shared_dir<false>(a, log2n, tw);
+  if (inverse) fft_shared_any<true>(a, log2n, tw); else fft_shared_any<false>(a, log2n, tw);
 }
 
 // ---------------------------------------------------------------------------------------------- STFT
@@ -347,12 +395,14 @@ hpss_median_kernel(const float2* __restrict__ spec, float* __restrict__ out, int
 // ---------------------------------------------------------------------------------------------- masks + ISTFT
 __device__ __forceinline__ float softmask2(float x, float ref, bool split_zeros) {
   // librosa.util.softmask with power 2:  (x/z)^2 / ((x/z)^2 + (ref/z)^2),  z = max(x, ref).  One of the two ratios is
-  // exactly 1 (z / z), so only the other one is divided: same bits as the three-division form, two divisions.
+  // exactly 1 (z / z), so only the other one is divided: two divisions instead of three.
+  // The two divisions are reciprocal + multiply (MUFU.RCP, within 2 ulp = 1.2e-7 of the mask; magnitudes stay far below
+  // the 2^126 bound of that form): the inverse kernel is issue bound and four IEEE divisions per bin were 14 % of it.
   const float z = fmaxf(x, ref);
   if (z < FLT_MIN) return split_zeros ? 0.5f : 0.f;
-  const float q = fminf(x, ref) / z;
+  const float q = __fdividef(fminf(x, ref), z);
   const float q2 = q * q;
-  return (x >= ref ? 1.f : q2) / (q2 + 1.f);
+  return __fdividef(x >= ref ? 1.f : q2, q2 + 1.f);
 }
 
 // A CTA transforms kIstftGroup consecutive frames of one row and overlap-adds them in shared memory first: with n_fft / hop
