@@ -33,6 +33,11 @@ namespace mpcg {
 #ifndef MPCG_AC_P1_WEIGHTS
 #define MPCG_AC_P1_WEIGHTS 1            // 1: pass 1 as the weighted sum (a fresh constant per DFMA); 0: as the recurrence
 #endif
+#ifndef MPCG_AC_FOLD_ONE
+#define MPCG_AC_FOLD_ONE 1              // 1: one warp folds the exchanged statistics (second barrier); 0: every warp does
+                                        // (the kernel is issue bound: sixteen redundant folds cost more than the barrier --
+                                        //  1.245 -> 1.184 ms at configs[2], 0.499 -> 0.481 ms at the bench shape)
+#endif
 #ifndef MPCG_AC_UNROLL_SMEM
 #define MPCG_AC_UNROLL_SMEM 3          // unroll factor of the filter loops that read shared memory (0: full)
 #endif
@@ -89,6 +94,7 @@ struct AcShared {
   double xE[2][kAcMaxCluster][4];               // [group parity][rank]: end states exported by each rank
   unsigned long long load_bar;                  // mbarrier of the bulk load
   unsigned long long pad_;
+  float mapv[2][4];                             // (MPCG_AC_FOLD_ONE) the maps of the exchange in flight
   float volc[2][4];                             // wandering volume, per band: k = 2 sin(theta/2), cos(theta/2), sin(theta/2)
   float rowc[8];                                // the row's parameters: 0-5 wandering volume (amp, freq, phase) x 2, 6 / 7 noise scales
 };
@@ -173,9 +179,9 @@ __device__ __forceinline__ float ac_warp_max(float v) {
   return __int_as_float(o ^ ((o >> 31) & 0x7fffffff));
 }
 
-// Exchange NSETS row statistics across the cluster; every thread receives the maps.  ONE barrier: each warp leaves its
-// partials in every rank's table, and after the barrier every warp folds the whole table itself (no second barrier, no
-// warp waiting for another one's divisions).
+// Exchange NSETS row statistics across the cluster; every thread receives the maps.  Each warp leaves its partials in
+// every rank's table; after the (cluster) barrier warp 0 folds the table and the maps reach the others through shared
+// memory behind a CTA barrier.
 template <int NSETS>
 __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& cluster, int ncl, int rank, double inv_t, int& parity,
                                             AcAcc (&st)[NSETS], AcMap (&out)[NSETS]) {
@@ -191,6 +197,9 @@ __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& clu
     }
   }
   ac_cluster_sync(ncl);
+#if MPCG_AC_FOLD_ONE
+  if (warp == 0) {                                          // one warp folds; the others wait at a second (CTA) barrier
+#endif
 #pragma unroll
   for (int s = 0; s < NSETS; ++s) {
     const AcStat* all = &sm.xstat[s == 0 ? parity : 2][0][0];
@@ -208,10 +217,23 @@ __device__ __forceinline__ void ac_exchange(AcShared& sm, cg::cluster_group& clu
     const double peak = fmax((double)hi - mean, mean - (double)lo);
     const float inv = __frcp_rn((float)fmax(peak, 1e-12));
     const double c = -mean * (double)inv;                   // consistent with the ROUNDED scale: the FMA then cancels exactly
+#if MPCG_AC_FOLD_ONE
+    if (lane == 0) { sm.mapv[s][0] = inv; sm.mapv[s][1] = (float)c; sm.mapv[s][2] = (float)(c - (double)(float)c); }
+  }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NSETS; ++s) {
+    out[s].inv = sm.mapv[s][0];
+    out[s].chi = sm.mapv[s][1];
+    out[s].clo = sm.mapv[s][2];
+  }
+#else
     out[s].inv = inv;
     out[s].chi = (float)c;
     out[s].clo = (float)(c - (double)out[s].chi);
   }
+#endif
   parity ^= 1;
 }
 
