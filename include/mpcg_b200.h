@@ -193,7 +193,9 @@ int mpcg_aug_eq_mix_f32(const float* x, const float* coloured, float* y, int64_t
  * = w[n] cos(2 pi k n / n_fft) / sqrt(sum w^2)  |  -w[n] sin(...) / ...  for
  * the nbins DFT bins k0 .. k0+nbins-1 that carry mel weight (zero-padded to kpad, a multiple of 32) and the
  * window's non-zero span [n_lo, n_hi); fb: device [nbins][n_mels] HTK triangles of those bins.  Both are built
- * once per MelConfig by the host mirror.  log_map != 0 fuses log_mel's dB map (spectrogram.py:44-45). */
+ * once per MelConfig by the host mirror.  log_map != 0 fuses log_mel's dB map (spectrogram.py:44-45).
+ * A CTA stages the sample span of 32 frames (8 when 31 hops + a window exceed shared memory); MPCG_ERANGE when even
+ * 7 hops + a window exceed ~55 000 samples. */
 int mpcg_mel_f32(const float* x, float* out, int64_t rows, int64_t t, int n_fft, int hop, int n_lo, int n_hi, int nbins,
                  int kpad, const void* basis, int basis_f64, const float* fb, int n_mels, int64_t frames, int log_map,
                  void* stream);

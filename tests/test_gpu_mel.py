@@ -185,3 +185,20 @@ def test_more_rows_than_one_launch_takes(pkg):
     assert y.shape == (70000, 8, 13)
     assert torch.equal(y[65530:65540], pkg.log_mel(x[65530:65540], tr))
     assert torch.equal(y[:5], pkg.log_mel(x[:5], tr))
+
+
+def test_long_hops_take_fewer_frames_per_cta(pkg):
+    """hop = n_fft = 2048: 31 hops + a window of samples do not fit shared memory; the tensor tier hands over to the scalar
+    kernel with eight frames per CTA.  Same bound against the float64 oracle."""
+    kw = dict(sample_rate=16000, n_fft=2048, hop_length=2048, n_mels=40, f_max=800.0)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 40000)).astype(np.float32)
+    tr = pkg.MelConfig(**kw).build()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = otp.mel_transform(**kw).double()
+    want = otp.log_mel(torch.from_numpy(x).double(), ref).numpy()
+    got = pkg.log_mel(torch.from_numpy(x).cuda(), tr).cpu().numpy()
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-5
+    fast = pkg.log_mel(torch.from_numpy(x).cuda(), pkg.MelConfig(**kw).build(fast=True)).cpu().numpy()
+    assert np.abs(fast - want).max() < 1e-4

@@ -14,8 +14,6 @@ namespace mpcg {
 
 constexpr int kMelThreads = 256;
 constexpr int kMelWarps = kMelThreads / 32;
-constexpr int kMelFT = 32;                       // frames per CTA
-constexpr int kMelFPW = kMelFT / kMelWarps;      // frames per warp
 
 struct MelArgs {
   const float* x;         // [rows, t]
@@ -35,9 +33,12 @@ __device__ __forceinline__ float log_map(float mel) {
 // ACC = double: basis and accumulation in fp64.  Leakage skirts of tonal inputs sit 5-6 decades below the peak
 // and the dB map clamps at 1e-5, so float accumulation (error ~1e-7 of the frame's peak bin) is visible there;
 // fp64 keeps the 1e-5 bound against the float64 oracle on every input.  ACC = float is the fast path.
-template <typename ACC>
+// FPW = frames per warp (4, or 1 when 31 hops + a window of samples would not fit shared memory): the CTA covers
+// kMelFT = 8 FPW frames.
+template <typename ACC, int FPW>
 __global__ void __launch_bounds__(kMelThreads)
 mel_kernel(const MelArgs a) {
+  constexpr int kMelFPW = FPW, kMelFT = kMelWarps * FPW;
   extern __shared__ __align__(16) float ml_smem[];
   const int span = (kMelFT - 1) * a.hop + (a.n_hi - a.n_lo);     // samples this CTA's frames touch
   float* xs = ml_smem;                                           // [span]
@@ -113,19 +114,27 @@ extern "C" int mpcg_mel_f32(const float* x, float* out, int64_t rows, int64_t t,
   MelArgs a;
   a.x = x; a.out = out; a.basis = basis; a.fb = fb; a.t = t; a.n_fft = n_fft; a.hop = hop; a.n_lo = n_lo; a.n_hi = n_hi;
   a.nbins = nbins; a.kpad = kpad; a.n_mels = n_mels; a.frames = (int)frames; a.log_map = log_map;
-  const int span = (kMelFT - 1) * hop + (n_hi - n_lo);
-  const size_t smem = (size_t)(((span + 3) & ~3) + kMelFT * (kpad + 1)) * sizeof(float);
+  auto smem_of = [&](int ft) {
+    const int span = (ft - 1) * hop + (n_hi - n_lo);
+    return (size_t)(((span + 3) & ~3) + ft * (kpad + 1)) * sizeof(float);
+  };
+  const int fpw = smem_of(4 * kMelWarps) <= 220 * 1024 ? 4 : 1;     // long hops: fewer frames share a CTA's sample span
+  const int ft = fpw * kMelWarps;
+  const size_t smem = smem_of(ft);
   if (smem > 220 * 1024) return MPCG_ERANGE;
-  dim3 grid((unsigned)((frames + kMelFT - 1) / kMelFT), (unsigned)rows);
-  if (basis_f64) {
-    cudaError_t e = cudaFuncSetAttribute(mel_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    mel_kernel<double><<<grid, kMelThreads, smem, (cudaStream_t)stream>>>(a);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(mel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    mel_kernel<float><<<grid, kMelThreads, smem, (cudaStream_t)stream>>>(a);
+  dim3 grid((unsigned)((frames + ft - 1) / ft), (unsigned)rows);
+#define MPCG_MEL_LAUNCH(ACC, FPW)                                                                                     \
+  {                                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(mel_kernel<ACC, FPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                                              \
+    mel_kernel<ACC, FPW><<<grid, kMelThreads, smem, (cudaStream_t)stream>>>(a);                                        \
   }
+  if (basis_f64) {
+    if (fpw == 4) MPCG_MEL_LAUNCH(double, 4) else MPCG_MEL_LAUNCH(double, 1)
+  } else {
+    if (fpw == 4) MPCG_MEL_LAUNCH(float, 4) else MPCG_MEL_LAUNCH(float, 1)
+  }
+#undef MPCG_MEL_LAUNCH
   MPCG_LAUNCH_CHECK();
   return MPCG_OK;
 }
